@@ -1,0 +1,246 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference hot-path functions.
+
+TEST INFRASTRUCTURE (see oracle/ragraph_oracle.py header).  Run in the build container,
+where /root/reference exists:
+
+    python oracle/make_golden.py
+
+The reference is pure Python/torch and cannot travel to the GPU box, so the vectors it
+produces are committed as small fixtures together with this script.  Nothing in tests/,
+smoke() or bench.py reads /root/reference at run time.
+
+How the reference is made importable on CPU:
+  * torch_geometric / torch_scatter are absent -> stub modules in sys.modules (only names
+    the hot-path modules import at module scope; no stubbed function is on the path except
+    scatter_softmax, which is third-party torch_scatter and restated in plain torch here);
+  * ``.cuda()`` is hard-coded (ToyGraphBase.py:35-38, layers/gcn.py:28-29) ->
+    ``torch.Tensor.cuda`` is patched to the identity for the duration of this script;
+  * the five variants reuse the same top-level package names -> each variant is imported
+    after purging those names from sys.modules.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+_VARIANT_PKGS = ("ragraph_utils", "layers", "models", "utils", "modules", "RAGraph",
+                 "preprompt", "downprompt", "aug", "utility")
+
+
+def _install_stubs():
+    tg = types.ModuleType("torch_geometric")
+    tgl = types.ModuleType("torch_geometric.loader"); tgl.DataLoader = object
+    tgd = types.ModuleType("torch_geometric.datasets"); tgd.TUDataset = object
+    tg.loader, tg.datasets = tgl, tgd
+    sys.modules.update({"torch_geometric": tg, "torch_geometric.loader": tgl,
+                        "torch_geometric.datasets": tgd})
+
+    ts = types.ModuleType("torch_scatter")
+
+    def scatter_softmax(src, index, dim_size=None):
+        # torch_scatter.scatter_softmax restated (third-party, K10, out of hot-path scope)
+        n = int(dim_size) if dim_size is not None else int(index.max()) + 1
+        mx = torch.full((n,), -float("inf"), dtype=src.dtype).scatter_reduce(
+            0, index, src, reduce="amax", include_self=True)
+        e = torch.exp(src - mx[index])
+        den = torch.zeros(n, dtype=src.dtype).scatter_add_(0, index, e)
+        return e / den[index]
+
+    ts.scatter_softmax = scatter_softmax
+    sys.modules["torch_scatter"] = ts
+    torch.Tensor.cuda = lambda self, *a, **k: self          # CPU-only container
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+
+
+def _enter_variant(name, argv=None):
+    for m in list(sys.modules):
+        if m.split(".")[0] in _VARIANT_PKGS:
+            del sys.modules[m]
+    sys.path[:] = [p for p in sys.path if not p.startswith(REF)]
+    sys.path.insert(0, os.path.join(REF, name))
+    if argv is not None:
+        sys.argv = argv
+
+
+def _save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **{k: (v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
+                                 for k, v in arrays.items()})
+    print("wrote", os.path.relpath(path), {k: tuple(np.asarray(v).shape) for k, v in arrays.items()})
+
+
+def _sym_norm_adj(n, p, gen):
+    a = (torch.rand(n, n, generator=gen) < p).float()
+    a = torch.triu(a, 1); a = a + a.t() + torch.eye(n)
+    dinv = a.sum(1).pow(-0.5)
+    return dinv[:, None] * a * dinv[None, :]
+
+
+def gen_node():
+    _enter_variant("RAGraph_node")
+    from ragraph_utils.ToyGraphBase import ToyGraphBase
+    from ragraph_utils.Propagation import Propagation
+    from ragraph_utils.SimilarityFunctions import SimilarityFunctions
+    from ragraph_utils.TaskDecoder import TaskDecoder
+    from layers.gcn import GCN
+
+    g = torch.Generator().manual_seed(20241017)
+    Q, N, d, C = 37, 600, 32, 3
+    q = torch.randn(Q, d, generator=g)
+    q[5] = 0.0                                            # zero row -> eps clamp
+    keys = torch.nn.functional.normalize(torch.randn(N, d, generator=g), dim=-1)
+    keys[17] = keys[3]                                    # exact duplicate -> tie
+    keys[44] = 0.0                                        # zero key
+    values = torch.randn(N, d, generator=g)
+    labels = torch.nn.functional.one_hot(torch.randint(0, C, (N,), generator=g), C).float()
+
+    base = ToyGraphBase(None, C, d, 3)                    # real constructor (cuda() patched)
+    base.resource_keys, base.resource_values, base.resource_labels = keys, values, labels
+    S = SimilarityFunctions.calculate_cosine_similarity(q, keys)
+    emb, lab = base.retrieve(q, None, False)
+    torch.manual_seed(77)
+    emb_n, lab_n = base.retrieve(q, None, True)
+    torch.manual_seed(77)
+    noise_idx = torch.randint(0, N, (Q, base.noise_retrieve_num))
+    _save("node_retrieve", q=q, keys=keys, values=values, labels=labels, cosine=S,
+          retrieve_num=base.retrieve_num, rag_embeddings=emb, rag_labels=lab,
+          noise_indices=noise_idx, rag_embeddings_noise=emb_n, rag_labels_noise=lab_n)
+
+    # Propagation
+    n, Fdim = 50, 16
+    adj = _sym_norm_adj(n, 0.08, g)
+    x = torch.randn(n, Fdim, generator=g)
+    outs = {f"out_k{k}": Propagation.aggregate_k_hop_features(adj, x, k) for k in (0, 1, 2, 3)}
+    _save("propagation", adj=adj, x=x, **outs)
+
+    # GCN layer (dense branch, unmodified forward)
+    torch.manual_seed(5)
+    layer = GCN(24, 16, 'prelu')
+    with torch.no_grad():
+        layer.bias.copy_(torch.randn(16, generator=g) * 0.1)
+        layer.act.weight.fill_(0.25)
+    seq = torch.randn(n, 24, generator=g)
+    with torch.no_grad():
+        out = layer((seq, adj.unsqueeze(0)))
+    _save("gcn_layer", seq=seq, adj=adj, weight=layer.fc.weight.detach(), bias=layer.bias.detach(),
+          alpha=layer.act.weight.detach(), out=out)
+
+    # fusion arithmetic of RAGraph.forward (RAGraph_node/RAGraph.py:39-63), real method on a shim
+    import importlib
+    sys.modules.setdefault("utils", types.ModuleType("utils")).process = None
+    RAG = importlib.import_module("RAGraph").RAGraph
+    torch.manual_seed(11)
+    dec = TaskDecoder(d, d, C)
+    nq = 40
+    adj_q = _sym_norm_adj(nq, 0.1, g)
+    emb_q = torch.randn(nq, d, generator=g)
+
+    class _PM:
+        def inference(self, features, adj):
+            return emb_q
+
+    shim = object.__new__(RAG)
+    torch.nn.Module.__init__(shim)
+    shim.pretrain_model, shim.toy_graph_base, shim.decoder = _PM(), base, dec
+    shim.retrieve_weight, shim.label_weight, shim.finetune = 0.5, 0.5, True
+    shim.noise_finetune, shim.query_graph_hop = False, 3
+    shim.eval()
+    with torch.no_grad():
+        logits = shim.forward(None, adj_q)
+        shim.finetune = False
+        vanilla = shim.forward(None, adj_q)
+    _save("node_forward", emb_q=emb_q, adj_q=adj_q, keys=keys, values=values, labels=labels,
+          w1=dec.fc1.weight.detach(), b1=dec.fc1.bias.detach(), w2=dec.fc2.weight.detach(),
+          b2=dec.fc2.bias.detach(), logits=logits, vanilla=vanilla, retrieve_num=base.retrieve_num)
+
+
+def gen_graph():
+    _enter_variant("RAGraph_graph")
+    from ragraph_utils.ToyGraphBase import ToyGraphBase
+    g = torch.Generator().manual_seed(424242)
+    N, d, C = 300, 32, 6
+    keys = torch.randn(N, d, generator=g) * 0.3           # graph keys are means: NOT unit norm
+    values = torch.randn(N, d, generator=g)
+    labels = torch.nn.functional.one_hot(torch.randint(0, C, (N,), generator=g), C)   # int64
+    q1 = torch.randn(d, generator=g)
+    base = ToyGraphBase(None, C, d, 1)
+    base.resource_keys, base.resource_values = keys, values
+    base.resource_labels = torch.cat((torch.empty(0, C), labels), dim=0)   # promotion as in :126
+    emb, lab = base.retrieve(q1, None, False)
+    _save("graph_retrieve", q=q1, keys=keys, values=values, labels=base.resource_labels,
+          retrieve_num=base.retrieve_num, rag_embeddings=emb, rag_labels=lab)
+
+
+def gen_node_fewshot():
+    _enter_variant("RAGraph_node_fewshot")
+    from ragraph_utils.ToyGraphBase import ToyGraphBase
+    from ragraph_utils.PositionAwareEncoder import PositionAwareEncoder
+    g = torch.Generator().manual_seed(99)
+    nq, N, d, C = 30, 400, 32, 3
+    adj = _sym_norm_adj(nq, 0.12, g)
+    q = torch.randn(nq, d, generator=g)
+    keys = torch.nn.functional.normalize(torch.randn(N, d, generator=g), dim=-1)
+    values = torch.randn(N, d, generator=g)
+    labels = torch.nn.functional.one_hot(torch.randint(0, C, (N,), generator=g), C).float()
+    positions = torch.rand(N, 10, generator=g)
+    base = object.__new__(ToyGraphBase)
+    base.retrieve_num, base.noise_retrieve_num = 5, 1
+    base.num_anchors, base.dis_q = 10, 10
+    base.structure_weight, base.semantic_weight = 0.001, 0.999
+    base.resource_keys, base.resource_values = keys, values
+    base.resource_labels, base.resource_positions = labels, positions
+    torch.manual_seed(123)
+    emb, lab = base.retrieve(q, adj, False)
+    torch.manual_seed(123)
+    search_positions = PositionAwareEncoder.encode_position_aware_code(adj, 10, 10)
+    _save("fewshot_retrieve", q=q, search_positions=search_positions, keys=keys, positions=positions,
+          values=values, labels=labels, retrieve_num=5, rag_embeddings=emb, rag_labels=lab)
+
+
+def gen_edge():
+    _enter_variant("RAGraph_edge", argv=["x", "--device", "cpu", "--data_path", "dataset/amazon"])
+    from modules.RAGraph import RAGraph
+    from modules.utils import scatter_sum
+    from utils.parse_args import args
+    g = torch.Generator().manual_seed(31337)
+    nu, ni, d, E = 70, 50, 16, 900
+    n = nu + ni
+    u = torch.randint(0, nu, (E,), generator=g); i = torch.randint(0, ni, (E,), generator=g) + nu
+    edges = torch.cat([torch.stack([u, i], 1), torch.stack([i, u], 1)], 0)           # symmetrised
+    w = torch.rand(edges.shape[0], generator=g)
+    X = torch.randn(n, d, generator=g)
+    shim = types.SimpleNamespace(num_users=nu, num_items=ni)
+    Y = RAGraph._agg(shim, X, edges, w)
+    _save("edge_agg", X=X, edges=edges, w=w, num_nodes=n, Y=Y,
+          scatter=scatter_sum(X[edges[:, 0]], edges[:, 1], dim=0, dim_size=n))
+
+    # full forward (modules/RAGraph.py:265-333) on a shim, vanilla phase, no noise / LoRA
+    keys = torch.randn(n, d, generator=g)
+    values = torch.randn(n, d, generator=g)
+    times = torch.randint(0, 1000, (edges.shape[0],), generator=g)
+    fw = types.SimpleNamespace(
+        num_users=nu, num_items=ni, phase="vanilla", use_RAG=True, use_noise=False, use_LoRA=False,
+        training=False, user_embedding=X[:nu], item_embedding=X[nu:], emb_gate=lambda x: x,
+        batch_size=32, retrieve_num=10, noise_retrieve_num=1, retrieve_weight=0.3,
+        resource_keys=keys, resource_values=values)
+    fw._agg = types.MethodType(RAGraph._agg, fw)
+    fw._relative_edge_time_encoding = types.MethodType(RAGraph._relative_edge_time_encoding, fw)
+    with torch.no_grad():
+        time_norm = fw._relative_edge_time_encoding(edges, times)
+        ur, ir = RAGraph.forward(fw, edges, w, times)
+    _save("edge_forward", X=X, edges=edges, w=w, time_norm=time_norm, keys=keys, values=values,
+          num_layers=args.num_layers, batch_size=32, retrieve_num=10, retrieve_weight=0.3,
+          out=torch.cat([ur, ir], 0))
+
+
+if __name__ == "__main__":
+    assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
+    _install_stubs()
+    gen_node(); gen_graph(); gen_node_fewshot(); gen_edge()

@@ -1,0 +1,291 @@
+"""CPU oracle for the RAGraph retrieve -> gather -> propagate hot path.
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import it, and only as the checker / the timed CPU baseline.  Nothing under
+``ragraph_b200/`` imports this module; the product path fails loudly when the CUDA
+library is missing.
+
+Parity pinning: the reference ships no tests, golden vectors or fixtures for this path
+(SURVEY.md section 4 / 8c), so the oracle is pinned against outputs of the reference
+ITSELF: ``oracle/make_golden.py`` imports the unmodified reference functions from
+``/root/reference`` (in the build container, where it exists), runs them on seeded
+inputs and commits the input/output vectors under ``tests/golden/``.
+``tests/test_oracle_golden.py`` checks every function below against those vectors.
+
+The arithmetic of the reference lives in PyTorch (``F.normalize``, ``torch.matmul``,
+``torch.topk``, advanced indexing, ``scatter_add_``); the restatement therefore uses the
+same torch CPU calls in the same order (fp32), plus numpy fp64 arbiters used to decide
+near-ties.  Every function cites the reference lines it follows (paths relative to
+``/root/reference``).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+EPS = 1e-12  # F.normalize default eps
+
+
+# ----------------------------------------------------------------------------------------
+# a1  SimilarityFunctions.calculate_cosine_similarity
+# ----------------------------------------------------------------------------------------
+def cosine_similarity(search_keys: torch.Tensor, resource_keys: torch.Tensor) -> torch.Tensor:
+    """RAGraph_node/ragraph_utils/SimilarityFunctions.py:6-16 (identical in all 5 variants).
+
+    x / max(||x||_2, 1e-12) on BOTH operands (keys are re-normalised on every call),
+    then a dense fp32 matmul.  A 1-D query (graph variant, RAGraph_graph/RAGraph.py:50)
+    gives a 1-D result.
+    """
+    q = F.normalize(search_keys, p=2, dim=-1)
+    k = F.normalize(resource_keys, p=2, dim=-1)
+    return torch.matmul(q, k.t())
+
+
+def cosine_similarity_f64(search_keys, resource_keys) -> np.ndarray:
+    """fp64 arbiter for a1 (same formula, numpy float64)."""
+    q = np.asarray(search_keys, dtype=np.float64)
+    k = np.asarray(resource_keys, dtype=np.float64)
+    qn = q / np.maximum(np.linalg.norm(q, axis=-1, keepdims=True), EPS)
+    kn = k / np.maximum(np.linalg.norm(k, axis=-1, keepdims=True), EPS)
+    return qn @ kn.T
+
+
+def dot_similarity(search_keys: torch.Tensor, resource_keys: torch.Tensor) -> torch.Tensor:
+    """Un-normalised score used by the edge evaluation top-k,
+    RAGraph_edge/utils/metrics.py:102-117 (rating = U . I^T)."""
+    return torch.matmul(search_keys, resource_keys.t())
+
+
+# ----------------------------------------------------------------------------------------
+# a2 / a3  ToyGraphBase.retrieve  (top-k + gathers)
+# ----------------------------------------------------------------------------------------
+def topk(scores: torch.Tensor, k: int):
+    """RAGraph_node/ragraph_utils/ToyGraphBase.py:67 -- torch.topk(largest, sorted)."""
+    return torch.topk(scores, k, largest=True, sorted=True)
+
+
+def retrieve(search_keys, resource_keys, resource_values, resource_labels, retrieve_num,
+             noise_indices=None):
+    """RAGraph_node/ragraph_utils/ToyGraphBase.py:47-81.
+
+    Returns (topk_scores, topk_indices, rag_embeddings, rag_labels).  ``noise_indices``
+    ([Q, noise_retrieve_num] int64) stands in for the CPU ``torch.randint`` of :74 so that
+    the noisy branch is reproducible; the caller passes ``retrieve_num`` already doubled
+    when add_noise is set (:66).
+    """
+    scores = cosine_similarity(search_keys, resource_keys)
+    topk_scores, topk_indices = topk(scores, retrieve_num)
+    rag_embeddings = resource_values[topk_indices]
+    rag_labels = resource_labels[topk_indices]
+    if noise_indices is not None:
+        rag_embeddings = torch.cat([rag_embeddings, resource_values[noise_indices]], dim=1)
+        rag_labels = torch.cat([rag_labels, resource_labels[noise_indices]], dim=1)
+    return topk_scores, topk_indices, rag_embeddings, rag_labels
+
+
+def retrieve_graph(search_key_1d, resource_keys, resource_values, resource_labels, retrieve_num):
+    """RAGraph_graph/ragraph_utils/ToyGraphBase.py:56-87: the query is ONE vector [d]
+    (mean of node embeddings), similarity is [N] and is unsqueezed to [1, N] (:72)."""
+    scores = cosine_similarity(search_key_1d, resource_keys).unsqueeze(0)
+    topk_scores, topk_indices = topk(scores, retrieve_num)
+    return topk_scores, topk_indices, resource_values[topk_indices], resource_labels[topk_indices]
+
+
+def retrieve_two_metric(search_keys, search_positions, resource_keys, resource_positions,
+                        resource_values, resource_labels, retrieve_num,
+                        structure_weight=0.001, semantic_weight=0.999):
+    """RAGraph_node_fewshot/ragraph_utils/ToyGraphBase.py:47-79: weighted sum of two cosine
+    matrices (einsum 'ij,jkl->ikl' over a [1,2] weight row, :56-61) before the top-k."""
+    structure = cosine_similarity(search_positions, resource_positions)
+    semantic = cosine_similarity(search_keys, resource_keys)
+    w = torch.tensor([[structure_weight, semantic_weight]], dtype=semantic.dtype)
+    mats = torch.stack([structure, semantic], dim=0)
+    scores = torch.einsum('ij,jkl->ikl', w, mats).squeeze(0)
+    topk_scores, topk_indices = topk(scores, retrieve_num)
+    return topk_scores, topk_indices, resource_values[topk_indices], resource_labels[topk_indices]
+
+
+def gather_rows(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """ToyGraphBase.py:70-71 / RAGraph_edge/modules/RAGraph.py:314 -- ``table[idx]``."""
+    return table[idx]
+
+
+# ----------------------------------------------------------------------------------------
+# a4  Propagation.aggregate_k_hop_features
+# ----------------------------------------------------------------------------------------
+def aggregate_k_hop_features(adj: torch.Tensor, x: torch.Tensor, k: int) -> torch.Tensor:
+    """RAGraph_node/ragraph_utils/Propagation.py:7-27: row-normalise the dense adjacency by
+    its row sums (:15-16), then k x relu(A_norm @ x) (:19-25).  k = 0 returns x."""
+    out = x
+    degree = adj.sum(dim=1, keepdim=True)
+    adj_normalized = adj / degree
+    for _ in range(k):
+        out = torch.matmul(adj_normalized, out)
+        out = F.relu(out)
+    return out
+
+
+def aggregate_k_hop_features_f64(adj, x, k) -> np.ndarray:
+    a = np.asarray(adj, dtype=np.float64)
+    out = np.asarray(x, dtype=np.float64)
+    a = a / a.sum(axis=1, keepdims=True)
+    for _ in range(k):
+        out = np.maximum(a @ out, 0.0)
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# a5  GCN.forward
+# ----------------------------------------------------------------------------------------
+def gcn_layer(seq, adj, weight, bias, prelu_alpha) -> torch.Tensor:
+    """RAGraph_node/layers/gcn.py:26-40 (dense branch): PReLU(adj @ (seq @ W^T) + b).
+    ``weight`` is nn.Linear(in, out, bias=False).weight ([out, in]); ``prelu_alpha`` the
+    single nn.PReLU() parameter (:9).  adj may be [1, n, n] (squeezed at :36)."""
+    seq_fts = F.linear(seq, weight)
+    out = torch.mm(adj.squeeze(dim=0), seq_fts)
+    if bias is not None:
+        out = out + bias
+    alpha = torch.as_tensor(prelu_alpha, dtype=out.dtype).reshape(-1)
+    return F.prelu(out, alpha)
+
+
+# ----------------------------------------------------------------------------------------
+# a6  edge _agg + scatter_sum
+# ----------------------------------------------------------------------------------------
+def scatter_sum(src: torch.Tensor, index: torch.Tensor, dim: int = 0, dim_size=None) -> torch.Tensor:
+    """RAGraph_edge/modules/utils.py:17-32 (dim=0 form used by _agg): zeros + scatter_add_."""
+    assert dim == 0
+    if dim_size is None:
+        dim_size = int(index.max()) + 1 if index.numel() else 0
+    out = torch.zeros((dim_size,) + tuple(src.shape[1:]), dtype=src.dtype)
+    idx = index.reshape(-1, *([1] * (src.dim() - 1))).expand_as(src)
+    return out.scatter_add_(0, idx, src)
+
+
+def edge_agg(all_emb: torch.Tensor, edges: torch.Tensor, edge_norm: torch.Tensor, num_nodes: int):
+    """RAGraph_edge/modules/RAGraph.py:232-240: Y[dst] += w_e * X[src];
+    src = edges[:, 0], dst = edges[:, 1]."""
+    src_emb = all_emb[edges[:, 0]]
+    src_emb = src_emb * edge_norm.unsqueeze(1)
+    return scatter_sum(src_emb, edges[:, 1], dim=0, dim_size=num_nodes)
+
+
+def edge_agg_f64(all_emb, edges, edge_norm, num_nodes) -> np.ndarray:
+    x = np.asarray(all_emb, dtype=np.float64)
+    e = np.asarray(edges)
+    w = np.asarray(edge_norm, dtype=np.float64)
+    out = np.zeros((num_nodes, x.shape[1]), dtype=np.float64)
+    np.add.at(out, e[:, 1], x[e[:, 0]] * w[:, None])
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# a7  fusion arithmetic of RAGraph.forward
+# ----------------------------------------------------------------------------------------
+def task_decoder(x, w1, b1, w2, b2):
+    """RAGraph_node/ragraph_utils/TaskDecoder.py:3-17: Linear -> LeakyReLU(0.01) -> Linear."""
+    return F.linear(F.leaky_relu(F.linear(x, w1, b1), 0.01), w2, b2)
+
+
+def fuse_node(pretrain_emb, adj, rag_embeddings, rag_labels, decoder_params,
+              retrieve_weight=0.5, label_weight=0.5, hop=3, finetune=True):
+    """RAGraph_node/RAGraph.py:47-63."""
+    rag_label = torch.mean(rag_labels, dim=1)
+    if not finetune:
+        return rag_label
+    rag_embedding = torch.sum(rag_embeddings, dim=1)
+    query_embeddings = aggregate_k_hop_features(adj, pretrain_emb, hop)
+    hidden = query_embeddings * (1 - retrieve_weight) + rag_embedding * retrieve_weight
+    decode = torch.softmax(task_decoder(hidden, *decoder_params), dim=1)
+    return decode * (1 - label_weight) + rag_label * label_weight
+
+
+def fuse_graph(pretrain_emb, adj, rag_embeddings, rag_labels, decoder_params,
+               retrieve_weight=0.3, label_weight=0.3, hop=1, finetune=True):
+    """RAGraph_graph/RAGraph.py:58-75 (one query = mean over the graph's nodes)."""
+    rag_label = torch.mean(rag_labels.to(torch.float32), dim=1)
+    if not finetune:
+        return rag_label
+    rag_embedding = torch.sum(rag_embeddings, dim=1)
+    query_embedding = torch.mean(aggregate_k_hop_features(adj, pretrain_emb, hop), dim=0)
+    hidden = query_embedding * (1 - retrieve_weight) + rag_embedding * retrieve_weight
+    decode = torch.softmax(task_decoder(hidden, *decoder_params), dim=1)
+    return decode * (1 - label_weight) + rag_label * label_weight
+
+
+def edge_forward(all_emb, edges, edge_norm, resource_keys, resource_values, num_layers=3,
+                 retrieve_num=10, batch_size=4096, retrieve_weight=0.3):
+    """RAGraph_edge/modules/RAGraph.py:279-328 (no LoRA/gating/noise): LightGCN layers via
+    _agg, then per 4096-query batch cosine -> top-k -> values[idx].mean(1), then the blend
+    res = (1-w) * sum(layers) + w * rag_emb."""
+    n = all_emb.shape[0]
+    res_emb = [all_emb]
+    for _ in range(num_layers):
+        res_emb.append(edge_agg(res_emb[-1], edges, edge_norm, n))
+    query_emb = res_emb[0]
+    rag_emb = torch.empty((n, resource_values.shape[1]), dtype=query_emb.dtype)
+    for start in range(0, n, batch_size):
+        end = min(start + batch_size, n)
+        scores = cosine_similarity(query_emb[start:end], resource_keys)
+        _, idx = topk(scores, retrieve_num)
+        rag_emb[start:end] = resource_values[idx].mean(dim=1)
+    res = sum(res_emb)
+    return (1 - retrieve_weight) * res + retrieve_weight * rag_emb
+
+
+# ----------------------------------------------------------------------------------------
+# multi-GPU restatement (new functionality, C1): merge of per-shard candidates
+# ----------------------------------------------------------------------------------------
+def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k: int):
+    """scores/idx: [R, Q, k_r] per-shard candidates (idx already global).  Returns the
+    global top-k with the deterministic order the product uses: score desc, index asc."""
+    R, Q, kr = scores.shape
+    s = scores.permute(1, 0, 2).reshape(Q, R * kr).numpy()
+    i = idx.permute(1, 0, 2).reshape(Q, R * kr).numpy()
+    order = np.lexsort((i, -s.astype(np.float64)), axis=1)[:, :k]
+    return (torch.from_numpy(np.take_along_axis(s, order, axis=1)),
+            torch.from_numpy(np.take_along_axis(i, order, axis=1)))
+
+
+# ----------------------------------------------------------------------------------------
+# tolerance helpers (north_star: index sets identical except ties within 1e-6; scores and
+# propagated embeddings within 1e-5 relative in fp32; gathers bit-exact)
+# ----------------------------------------------------------------------------------------
+def topk_sets_match(got_idx, exact_scores_f64: np.ndarray, k: int, tie_tol: float = 1e-6):
+    """True iff every returned index has an fp64 score >= (k-th best fp64 score - tie_tol),
+    rows hold no duplicates, and every key whose score beats the k-th best by more than
+    tie_tol is present.  This is 'identical index sets except for ties within tie_tol'."""
+    got = np.asarray(got_idx)
+    S = np.asarray(exact_scores_f64)
+    if S.ndim == 1:
+        S = S[None]
+    Q, N = S.shape
+    assert got.shape == (Q, k), (got.shape, (Q, k))
+    kth = np.partition(S, N - k, axis=1)[:, N - k]
+    bad = []
+    for r in range(Q):
+        row = got[r]
+        if len(set(row.tolist())) != k:
+            bad.append((r, "duplicate")); continue
+        if np.any(S[r, row] < kth[r] - tie_tol):
+            bad.append((r, "below kth")); continue
+        must = np.nonzero(S[r] > kth[r] + tie_tol)[0]
+        if not set(must.tolist()).issubset(set(row.tolist())):
+            bad.append((r, "missing"))
+    return len(bad) == 0, bad
+
+
+def rel_err(got, ref) -> float:
+    """max |got-ref| / max(|ref|_inf, tiny): relative to the tensor's scale (a per-element
+    relative error is meaningless for entries that are exactly or nearly zero after ReLU)."""
+    g = np.asarray(got, dtype=np.float64)
+    r = np.asarray(ref, dtype=np.float64)
+    return float(np.max(np.abs(g - r)) / max(np.max(np.abs(r)), 1e-30)) if r.size else 0.0
+
+
+def recall_at_k(got_idx, ref_idx) -> float:
+    g = np.asarray(got_idx); r = np.asarray(ref_idx)
+    hits = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(g, r))
+    return hits / float(r.size)
