@@ -1,0 +1,180 @@
+/* ragraph_b200.h -- C ABI of libragraph_b200.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for RAGraph's retrieve -> gather -> propagate hot path.  The reference
+ * (Artessay/RAGraph, pure Python/PyTorch) has no FFI; the interface each entry point
+ * replaces is the torch call sequence cited beside it (paths relative to the reference
+ * root).  INTEGRATION.md shows the ctypes / torch custom-op binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; all tensors are
+ *     row-major and contiguous; float pointers 16-byte aligned where noted.
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library never
+ *     allocates or frees device memory, keeps no pointer after the call returns and never
+ *     synchronises the stream.  All work is enqueued on `stream` (a cudaStream_t).
+ *   - return value: RAG_OK (0) or a negative RAG_E* code; rag_last_error() gives a
+ *     thread-local human readable message for the last failing call on this thread.
+ *   - re-entrant: no global mutable state except that thread-local string and a
+ *     per-process cache of device attributes.
+ */
+#ifndef RAGRAPH_B200_H_
+#define RAGRAPH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RAG_API __attribute__((visibility("default")))
+#else
+#define RAG_API
+#endif
+
+typedef void* rag_stream_t; /* cudaStream_t */
+
+enum rag_status {
+  RAG_OK = 0,
+  RAG_EINVAL = -1,       /* bad argument (null pointer, negative size, k > N ...) */
+  RAG_EALIGN = -2,       /* pointer not aligned as documented */
+  RAG_EUNSUPPORTED = -3, /* shape outside the compiled range (k > RAG_MAX_K, d % 8 ...) */
+  RAG_ECUDA = -4,        /* a CUDA runtime / driver call failed */
+  RAG_EWORKSPACE = -5    /* workspace_bytes smaller than rag_*_workspace() asked for */
+};
+
+/* largest k handled by the fused similarity+top-k kernels */
+#define RAG_MAX_K 128
+
+/* similarity modes of rag_cosine_topk_f32 */
+enum rag_sim_mode {
+  RAG_SIM_FP32 = 0,       /* fp32 FMA on CUDA cores, exact-order oracle-grade path */
+  RAG_SIM_BF16 = 2,       /* tcgen05 bf16 x bf16 -> fp32 in TMEM, raw approximate scores */
+  RAG_SIM_BF16_REFINE = 3 /* bf16 tensor-core filter + fp32 re-score + certificate; results
+                             equal RAG_SIM_FP32 (uncertified rows are recomputed in fp32) */
+};
+/* flags */
+#define RAG_SIM_DOT 1u /* skip L2 normalisation: plain dot product (edge eval top-k,
+                          RAGraph_edge/utils/metrics.py:102-117) */
+
+/* epilogues of rag_csr_spmm_f32 (bit flags, applied in this order) */
+#define RAG_EPI_ROWNORM 1u /* divide row i by sum_j val[i,j]        (Propagation.py:15-16) */
+#define RAG_EPI_BIAS 2u    /* + bias[F]                              (layers/gcn.py:37-38)  */
+#define RAG_EPI_RELU 4u    /* max(x, 0)                              (Propagation.py:25)    */
+#define RAG_EPI_PRELU 8u   /* x >= 0 ? x : alpha[0] * x              (layers/gcn.py:40)     */
+#define RAG_EPI_BLEND 16u  /* (1 - blend_w) * y + blend_w * blend_in (RAGraph.py:53)        */
+#define RAG_EPI_ACCUM 32u  /* y + accum_in  (sum of LightGCN layers, modules/RAGraph.py:327)*/
+
+/* reduce ops of rag_gather_reduce_f32 */
+enum rag_reduce_op { RAG_REDUCE_SUM = 0, RAG_REDUCE_MEAN = 1 };
+
+RAG_API int rag_abi_version(void);
+RAG_API const char* rag_last_error(void);
+RAG_API const char* rag_status_string(int status);
+/* number of kernels this library has launched in this process (all threads) */
+RAG_API int64_t rag_launch_count(void);
+
+/* ---- a1/K1: F.normalize pieces (SimilarityFunctions.py:8,11) -------------------------- */
+/* out_inv_norm[r] = 1 / max(||x[r,:]||_2, eps) */
+RAG_API int rag_row_inv_norm_f32(const float* x, int64_t rows, int32_t d, float eps, float* out_inv_norm,
+                         rag_stream_t stream);
+/* bf16 shadow of the key matrix for the tensor-core filter: out[r, 0:d] =
+ * bf16_rn(x[r,:] * (normalize ? 1/max(||x[r]||,eps) : 1)), columns d..d_pad-1 zero filled.
+ * d_pad % 64 == 0, out is [rows, d_pad] bf16 (uint16 storage), 16-byte aligned. */
+RAG_API int rag_rows_to_bf16(const float* x, int64_t rows, int32_t d, int32_t normalize, float eps,
+                     uint16_t* out, int32_t d_pad, rag_stream_t stream);
+
+/* ---- a1/K2: materialised similarity (API compatibility) ------------------------------- */
+/* out[Q,N] = cosine (or dot with RAG_SIM_DOT) similarity, fp32.
+ * Replaces SimilarityFunctions.calculate_cosine_similarity (SimilarityFunctions.py:6-16). */
+RAG_API size_t rag_cosine_similarity_workspace(int64_t Q, int64_t N);
+RAG_API int rag_cosine_similarity_f32(const float* q, int64_t Q, const float* keys, int64_t N, int32_t d,
+                              uint32_t flags, float* out, void* workspace, size_t workspace_bytes,
+                              rag_stream_t stream);
+
+/* ---- a2/K1+K2+K3: fused similarity + top-k (scores never reach HBM) -------------------- */
+/* Replaces calculate_cosine_similarity + torch.topk(largest, sorted)
+ * (ToyGraphBase.py:53,67; RAGraph_edge/modules/RAGraph.py:303,311).
+ *   q[Q,d], keys[N,d] fp32.  key_inv_norm[N] nullable (computed into workspace if null and
+ *   cosine).  keys_bf16 [N,d_pad] nullable: the shadow made by rag_rows_to_bf16 (normalised
+ *   unless RAG_SIM_DOT); REQUIRED for the BF16 modes.  d_pad = round_up(d, 64).
+ *   out_scores[Q,k] fp32 descending; out_idx[Q,k] int64 = idx_offset + local row; order is
+ *   deterministic: score desc, index asc.  Requires 1 <= k <= min(N, RAG_MAX_K). */
+RAG_API size_t rag_cosine_topk_workspace(int64_t Q, int64_t N, int32_t d, int32_t k, int32_t mode);
+RAG_API int rag_cosine_topk_f32(const float* q, int64_t Q, const float* keys, const float* key_inv_norm,
+                        const uint16_t* keys_bf16, int64_t N, int32_t d, int32_t k, int32_t mode,
+                        uint32_t flags, int64_t idx_offset, float* out_scores, int64_t* out_idx,
+                        void* workspace, size_t workspace_bytes, rag_stream_t stream);
+
+/* weighted two-metric variant (RAGraph_node_fewshot/ragraph_utils/ToyGraphBase.py:47-79):
+ * score = w_a * cos(qa, ka) + w_b * cos(qb, kb), fp32 path only. */
+RAG_API size_t rag_cosine2_topk_workspace(int64_t Q, int64_t N, int32_t da, int32_t db, int32_t k);
+RAG_API int rag_cosine2_topk_f32(const float* qa, const float* ka, int32_t da, float w_a, const float* qb,
+                         const float* kb, int32_t db, float w_b, int64_t Q, int64_t N, int32_t k,
+                         float* out_scores, int64_t* out_idx, void* workspace,
+                         size_t workspace_bytes, rag_stream_t stream);
+
+/* ---- C1: merge of per-shard candidates after the NCCL all-gather ----------------------- */
+/* scores/idx [R, Q, k_in] -> out [Q, k_out]; order score desc, index asc; k_out <= R*k_in,
+ * R*k_in <= 4096. */
+RAG_API int rag_topk_merge(const float* scores, const int64_t* idx, int32_t R, int64_t Q, int32_t k_in,
+                   int32_t k_out, float* out_scores, int64_t* out_idx, rag_stream_t stream);
+
+/* ---- a3/K5: gathers (bit exact) ------------------------------------------------------- */
+/* out[m, :] = table[idx[m], :] for m < M; rows are row_bytes long (any dtype).  Negative
+ * indices wrap once (torch semantics); an index still out of range writes zeros and raises
+ * the sticky device flag readable with rag_gather_oob_count().
+ * Replaces resource_values[topk_indices] / resource_labels[topk_indices]
+ * (ToyGraphBase.py:70-71, modules/RAGraph.py:314).
+ * owner_lo/owner_hi: only rows with owner_lo <= idx < owner_hi are fetched (from
+ * table[idx - owner_lo]); other output rows are left untouched -- the sharded
+ * "owners gather" step.  Pass 0, N for the plain gather. */
+RAG_API int rag_gather_rows(const void* table, int64_t N, int64_t row_bytes, const int64_t* idx, int64_t M,
+                    int64_t owner_lo, int64_t owner_hi, void* out, rag_stream_t stream);
+RAG_API int64_t rag_gather_oob_count(void); /* host-side read of the sticky flag (synchronises) */
+
+/* out[q,:] = reduce_j table[idx[q,j],:] (sum or mean over k), optionally blended:
+ * out = (1-blend_w)*blend_in + blend_w*reduce when blend_in != NULL.
+ * Replaces values[idx].sum(1) / .mean(1) + the convex blend
+ * (RAGraph_node/RAGraph.py:49,53; modules/RAGraph.py:322,328).  Summation order j=0..k-1. */
+RAG_API int rag_gather_reduce_f32(const float* table, int64_t N, int32_t d, const int64_t* idx, int64_t Q,
+                          int32_t k, int32_t op, const float* blend_in, float blend_w, float* out,
+                          rag_stream_t stream);
+
+/* ---- a4/a5/a6/K6-K9: CSR SpMM with fused epilogues ------------------------------------ */
+/* Y[n_rows,F] = epilogue( sum_j val[j] * X[col[j], :] ), rowptr int64[n_rows+1] or
+ * int32[n_rows+1] (ptr_is_64), col int32[nnz], val fp32[nnz] nullable (= all ones).
+ * Replaces torch.matmul(adj_normalized, x)+relu (Propagation.py:15-25), torch.mm(adj, XW)
+ * +bias+PReLU (layers/gcn.py:32-40) and gather*w -> scatter_add_ (modules/RAGraph.py:232-240).
+ * X and Y must not alias.  F % 4 == 0 uses the 128-bit path; any F >= 1 is supported. */
+RAG_API int rag_csr_spmm_f32(const void* rowptr, int32_t ptr_is_64, const int32_t* col, const float* val,
+                     int64_t n_rows, int64_t n_src, int64_t nnz, const float* X, int32_t F,
+                     uint32_t epilogue, const float* bias, const float* alpha, const float* blend_in,
+                     float blend_w, const float* accum_in, float* Y, rag_stream_t stream);
+
+/* CSR construction on the device (no host round trip).
+ * COO (edges[E,2] int64: [:,0]=src, [:,1]=dst as in modules/RAGraph.py:22-24) -> CSR by dst.
+ * Entries inside a row land in atomic-cursor order (like the reference's scatter_add_, the
+ * fp32 sum order is then not fixed run to run); the host layer offers a stable-sorted build
+ * when bit-reproducibility matters.
+ * Step 1: rag_coo_count_rows -> counts int32[n_rows] (zero-initialised by the call);
+ * step 2: caller makes rowptr = exclusive cumsum(counts) (int64[n_rows+1]);
+ * step 3: rag_coo_fill_csr writes col/val; cursor int32[n_rows] is scratch it zeroes. */
+RAG_API int rag_coo_count_rows(const int64_t* edges, int64_t E, int64_t n_rows, int32_t* counts,
+                       rag_stream_t stream);
+RAG_API int rag_coo_fill_csr(const int64_t* edges, const float* w, int64_t E, int64_t n_rows,
+                     const int64_t* rowptr, int32_t* cursor, int32_t* col, float* val,
+                     rag_stream_t stream);
+/* dense adjacency [n,n] -> per-row nonzero counts, then fill (Propagation.py / gcn.py take
+ * dense block-diagonal adj). */
+RAG_API int rag_dense_count_rows(const float* adj, int64_t n_rows, int64_t n_cols, int32_t* counts,
+                         rag_stream_t stream);
+RAG_API int rag_dense_fill_csr(const float* adj, int64_t n_rows, int64_t n_cols, const int64_t* rowptr,
+                       int32_t* col, float* val, rag_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAGRAPH_B200_H_ */

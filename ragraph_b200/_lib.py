@@ -1,0 +1,84 @@
+"""ctypes binding of libragraph_b200.so (the C ABI declared in include/ragraph_b200.h).
+
+There is NO CPU fallback: if the library is missing this module raises at first use, and every
+entry point takes device pointers only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libragraph_b200.so")
+
+RAG_OK = 0
+RAG_MAX_K = 128
+SIM_FP32, SIM_BF16, SIM_BF16_REFINE = 0, 2, 3
+SIM_DOT = 1
+EPI_ROWNORM, EPI_BIAS, EPI_RELU, EPI_PRELU, EPI_BLEND, EPI_ACCUM = 1, 2, 4, 8, 16, 32
+REDUCE_SUM, REDUCE_MEAN = 0, 1
+
+_p, _i64, _i32, _u32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/ragraph_b200.h one to one
+SIGNATURES = {
+    "rag_abi_version": (C.c_int, []),
+    "rag_last_error": (C.c_char_p, []),
+    "rag_status_string": (C.c_char_p, [C.c_int]),
+    "rag_launch_count": (_i64, []),
+    "rag_row_inv_norm_f32": (C.c_int, [_p, _i64, _i32, _f32, _p, _p]),
+    "rag_rows_to_bf16": (C.c_int, [_p, _i64, _i32, _i32, _f32, _p, _i32, _p]),
+    "rag_cosine_similarity_workspace": (_sz, [_i64, _i64]),
+    "rag_cosine_similarity_f32": (C.c_int, [_p, _i64, _p, _i64, _i32, _u32, _p, _p, _sz, _p]),
+    "rag_cosine_topk_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),
+    "rag_cosine_topk_f32": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _i64, _p, _p, _p, _sz, _p]),
+    "rag_cosine2_topk_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),
+    "rag_cosine2_topk_f32": (C.c_int, [_p, _p, _i32, _f32, _p, _p, _i32, _f32, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
+    "rag_topk_merge": (C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _p, _p, _p]),
+    "rag_gather_rows": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _p]),
+    "rag_gather_oob_count": (_i64, []),
+    "rag_gather_reduce_f32": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _i32, _p, _f32, _p, _p]),
+    "rag_csr_spmm_f32": (C.c_int, [_p, _i32, _p, _p, _i64, _i64, _i64, _p, _i32, _u32, _p, _p, _p, _f32, _p, _p, _p]),
+    "rag_coo_count_rows": (C.c_int, [_p, _i64, _i64, _p, _p]),
+    "rag_coo_fill_csr": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p]),
+    "rag_dense_count_rows": (C.c_int, [_p, _i64, _i64, _p, _p]),
+    "rag_dense_fill_csr": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class RagError(RuntimeError):
+    """A C-ABI call returned a negative RAG_E* status."""
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"ragraph_b200: {LIB_PATH} is missing -- build it with `python -m ragraph_b200.build` "
+                    "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the retrieval/propagation ops.")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+                fn.restype, fn.argtypes = res, args
+            if lib.rag_abi_version() != 1:
+                raise RuntimeError(f"ragraph_b200: ABI version {lib.rag_abi_version()} != 1")
+            _lib = lib
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != RAG_OK:
+        lib = load()
+        raise RagError(f"{what}: {lib.rag_status_string(status).decode()}: {lib.rag_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(load().rag_launch_count())

@@ -1,0 +1,92 @@
+"""CSR handle used by the propagation ops (what the dense block-diagonal adjacency of the
+node/graph variants and the COO edge list of the edge variant are converted to, once)."""
+from __future__ import annotations
+
+import weakref
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+
+
+@dataclass
+class CSRGraph:
+    rowptr: Tensor            # int64 [n_rows+1]
+    col: Tensor               # int32 [nnz]
+    val: Optional[Tensor]     # float32 [nnz] or None (= ones)
+    n_rows: int
+    n_cols: int
+
+    @property
+    def nnz(self) -> int:
+        return self.col.numel()
+
+    @staticmethod
+    def from_dense(adj: Tensor) -> "CSRGraph":
+        """Dense adjacency ([n,n] or [1,n,n] as layers/gcn.py:36 squeezes it) -> CSR.  Cached per tensor
+        object + version so RAGraph.forward, which hands the same adj to GCN and Propagation, converts once."""
+        if adj.dim() == 3 and adj.shape[0] == 1:
+            adj = adj[0]
+        key = id(adj)
+        hit = _dense_cache.get(key)
+        if hit is not None and hit[0]() is adj and hit[1] == adj._version:
+            return hit[2]
+        rowptr, col, val = ops.csr_from_dense(adj)
+        g = CSRGraph(rowptr, col, val, adj.shape[0], adj.shape[1])
+        if len(_dense_cache) > 64:
+            _dense_cache.clear()
+        try:
+            _dense_cache[key] = (weakref.ref(adj), adj._version, g)
+        except TypeError:
+            pass
+        return g
+
+    @staticmethod
+    def from_coo(edges: Tensor, w: Optional[Tensor], n_rows: int, n_cols: Optional[int] = None,
+                 deterministic: bool = False) -> "CSRGraph":
+        """edges[E,2] int64 ([:,0]=src, [:,1]=dst; RAGraph_edge/modules/RAGraph.py:22-24) -> CSR by dst.
+        deterministic=True orders each row by original edge position (stable sort) so the fp32 sum order
+        is reproducible; the default atomic-cursor build is faster and, like the reference's scatter_add_,
+        fixes no order."""
+        n_cols = n_rows if n_cols is None else n_cols
+        if deterministic:
+            dst_sorted, perm = torch.sort(edges[:, 1], stable=True)
+            counts = torch.bincount(dst_sorted, minlength=n_rows)
+            rowptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=edges.device)
+            torch.cumsum(counts, 0, out=rowptr[1:])
+            col = edges[:, 0][perm].to(torch.int32)
+            val = None if w is None else w[perm].contiguous()
+            return CSRGraph(rowptr, col, val, n_rows, n_cols)
+        rowptr, col, val = ops.csr_from_coo(edges, w, n_rows)
+        return CSRGraph(rowptr, col, val, n_rows, n_cols)
+
+    @staticmethod
+    def from_torch_sparse(adj: Tensor) -> "CSRGraph":
+        """torch sparse COO/CSR tensor (the `sparse=True` branch of layers/gcn.py:33-34)."""
+        if adj.layout == torch.sparse_csr:
+            return CSRGraph(adj.crow_indices().to(torch.int64), adj.col_indices().to(torch.int32),
+                            adj.values().to(torch.float32), adj.shape[0], adj.shape[1])
+        adj = adj.coalesce()
+        ind = adj.indices()
+        edges = torch.stack([ind[1], ind[0]], dim=1).contiguous()      # row = dst, col = src
+        return CSRGraph.from_coo(edges, adj.values().to(torch.float32), adj.shape[0], adj.shape[1],
+                                 deterministic=True)
+
+    def spmm(self, x: Tensor, epilogue: int = 0, **kw) -> Tensor:
+        return ops.csr_spmm(self.rowptr, self.col, self.val, x, epilogue, **kw)
+
+
+_dense_cache: dict = {}
+
+
+def as_csr(adj) -> CSRGraph:
+    if isinstance(adj, CSRGraph):
+        return adj
+    if isinstance(adj, Tensor):
+        if adj.layout != torch.strided:
+            return CSRGraph.from_torch_sparse(adj)
+        return CSRGraph.from_dense(adj)
+    raise TypeError(f"adjacency must be a dense/sparse tensor or CSRGraph, got {type(adj)}")

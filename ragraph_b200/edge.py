@@ -1,0 +1,90 @@
+"""Mirror of the edge (link-prediction) variant's pieces of the hot path.
+
+scatter_sum / scatter_add : RAGraph_edge/modules/utils.py:17-38
+_agg                      : RAGraph_edge/modules/RAGraph.py:232-240
+retrieve loop + blend     : RAGraph_edge/modules/RAGraph.py:279-328
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+from . import ops
+from .csr import CSRGraph
+
+
+def scatter_sum(src: Tensor, index: Tensor, dim: int = -1, out: Optional[Tensor] = None,
+                dim_size: Optional[int] = None) -> Tensor:
+    """out[index[e]] += src[e] along dim 0 (the only form the hot path uses; index is 1-D as in _agg).
+    Runs as a CSR SpMM over the identity-column matrix: no atomics on the output."""
+    if dim not in (0, -src.dim()) or index.dim() != 1 or src.dim() != 2:
+        raise NotImplementedError("scatter_sum: only dim=0 with a 1-D index over a 2-D src is on the hot path")
+    E = src.shape[0]
+    if dim_size is None:
+        dim_size = out.shape[0] if out is not None else (int(index.max()) + 1 if E else 0)
+    edges = torch.stack([torch.arange(E, device=src.device), index], dim=1)
+    g = CSRGraph.from_coo(edges, None, dim_size, E)
+    if out is None:
+        return g.spmm(src.contiguous())
+    res = g.spmm(src.contiguous(), L.EPI_ACCUM, accum_in=out)
+    out.copy_(res)
+    return out
+
+
+def scatter_add(src, index, dim=-1, out=None, dim_size=None):
+    return scatter_sum(src, index, dim, out, dim_size)
+
+
+class EdgeAggregator:
+    """`_agg(all_emb, edges, edge_norm)` with the CSR built once per (edges, edge_norm) pair.
+    Y[dst] = sum_e w_e * X[src_e]  (src = edges[:,0], dst = edges[:,1])."""
+
+    def __init__(self, num_nodes: int, deterministic: bool = False):
+        self.num_nodes = num_nodes
+        self.deterministic = deterministic
+        self._key = None
+        self._csr: Optional[CSRGraph] = None
+
+    def csr(self, edges: Tensor, edge_norm: Tensor) -> CSRGraph:
+        key = (edges.data_ptr(), edges._version, edges.shape[0], edge_norm.data_ptr(), edge_norm._version)
+        if key != self._key:
+            self._csr = CSRGraph.from_coo(edges, edge_norm, self.num_nodes, self.num_nodes, self.deterministic)
+            self._key = key
+        return self._csr
+
+    def __call__(self, all_emb: Tensor, edges: Tensor, edge_norm: Tensor, **epi) -> Tensor:
+        return self.csr(edges, edge_norm).spmm(all_emb, **epi)
+
+
+def _agg(all_emb: Tensor, edges: Tensor, edge_norm: Tensor, num_nodes: int) -> Tensor:
+    """Stateless form with the reference argument order (+ num_users+num_items made explicit)."""
+    return CSRGraph.from_coo(edges, edge_norm, num_nodes, num_nodes).spmm(all_emb)
+
+
+def edge_rag_forward(all_emb: Tensor, edges: Tensor, edge_norm: Tensor, resource_keys: Tensor,
+                     resource_values: Tensor, num_layers: int = 3, retrieve_num: int = 10, batch_size: int = 4096,
+                     retrieve_weight: float = 0.3, key_inv_norm: Optional[Tensor] = None,
+                     keys_bf16: Optional[Tensor] = None, mode: int = L.SIM_FP32,
+                     aggregator: Optional[EdgeAggregator] = None) -> Tensor:
+    """modules/RAGraph.py:279-328 without LoRA/gating/noise: LightGCN layer sum + retrieval blend.
+    res = (1-w) * (X0 + A X0 + A^2 X0 + A^3 X0) + w * mean_k values[topk(cos(X0, keys))].
+    The layer sum rides in the SpMM epilogue (RAG_EPI_ACCUM); per 4096-query batch the retrieve is one fused
+    similarity+top-k launch and the mean + convex blend one gather_reduce launch."""
+    n = all_emb.shape[0]
+    agg = aggregator or EdgeAggregator(n)
+    g = agg.csr(edges, edge_norm)
+    layer, total = all_emb, all_emb
+    for _ in range(num_layers):
+        layer = g.spmm(layer)
+        total = total + layer
+    out = torch.empty_like(total)
+    if key_inv_norm is None:
+        key_inv_norm = ops.row_inv_norm(resource_keys)
+    for start in range(0, n, batch_size):
+        end = min(start + batch_size, n)
+        _, idx = ops.cosine_topk(all_emb[start:end], resource_keys, retrieve_num, key_inv_norm, keys_bf16, mode)
+        out[start:end] = ops.gather_reduce(resource_values, idx, L.REDUCE_MEAN, total[start:end], retrieve_weight)
+    return out

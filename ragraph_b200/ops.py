@@ -1,0 +1,337 @@
+"""torch custom ops ``torch.ops.ragraph.*`` -- a thin layer over the C ABI (include/ragraph_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every op body is one or
+two calls into libragraph_b200.so.  CUDA tensors only -- there is no CPU kernel and no PyTorch
+fallback; a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ragraph_b200 ops run on CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor")
+
+
+def _f32c(t: Tensor, name: str) -> Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _workspace(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ----------------------------------------------------------------------------- norms / shadow
+@torch.library.custom_op("ragraph::row_inv_norm", mutates_args=())
+def row_inv_norm(x: Tensor, eps: float = 1e-12) -> Tensor:
+    _need_cuda(x)
+    x = _f32c(x, "row_inv_norm")
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.load().rag_row_inv_norm_f32(_p(x), x.shape[0], x.shape[1], eps, _p(out), _stream()), "row_inv_norm")
+    return out
+
+
+@row_inv_norm.register_fake
+def _(x, eps=1e-12):
+    return x.new_empty(x.shape[0])
+
+
+@torch.library.custom_op("ragraph::rows_to_bf16", mutates_args=())
+def rows_to_bf16(x: Tensor, normalize: bool = True, eps: float = 1e-12) -> Tensor:
+    """bf16 (optionally L2-normalised) shadow [rows, round_up(d, 64)] for the tensor-core filter."""
+    _need_cuda(x)
+    x = _f32c(x, "rows_to_bf16")
+    d_pad = round_up(x.shape[1], 64)
+    out = torch.empty((x.shape[0], d_pad), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.load().rag_rows_to_bf16(_p(x), x.shape[0], x.shape[1], int(normalize), eps, _p(out), d_pad,
+                                          _stream()), "rows_to_bf16")
+    return out
+
+
+@rows_to_bf16.register_fake
+def _(x, normalize=True, eps=1e-12):
+    return x.new_empty((x.shape[0], round_up(x.shape[1], 64)), dtype=torch.bfloat16)
+
+
+# ----------------------------------------------------------------------------- similarity
+@torch.library.custom_op("ragraph::cosine_similarity", mutates_args=())
+def cosine_similarity(q: Tensor, keys: Tensor, flags: int = 0) -> Tensor:
+    _need_cuda(q, keys)
+    q, keys = _f32c(q, "cosine_similarity"), _f32c(keys, "cosine_similarity")
+    if q.shape[1] != keys.shape[1]:
+        raise RuntimeError(f"cosine_similarity: dim mismatch {tuple(q.shape)} vs {tuple(keys.shape)}")
+    Q, N, d = q.shape[0], keys.shape[0], q.shape[1]
+    out = torch.empty((Q, N), dtype=torch.float32, device=q.device)
+    lib = L.load()
+    ws = _workspace(lib.rag_cosine_similarity_workspace(Q, N), q.device)
+    with torch.cuda.device(q.device):
+        L.check(lib.rag_cosine_similarity_f32(_p(q), Q, _p(keys), N, d, flags, _p(out), _p(ws), ws.numel(),
+                                              _stream()), "cosine_similarity")
+    return out
+
+
+@cosine_similarity.register_fake
+def _(q, keys, flags=0):
+    return q.new_empty((q.shape[0], keys.shape[0]))
+
+
+@torch.library.custom_op("ragraph::cosine_topk", mutates_args=())
+def cosine_topk(q: Tensor, keys: Tensor, k: int, key_inv_norm: Optional[Tensor] = None,
+                keys_bf16: Optional[Tensor] = None, mode: int = 0, flags: int = 0,
+                idx_offset: int = 0) -> Tuple[Tensor, Tensor]:
+    """Fused similarity + top-k.  Returns (scores[Q,k] f32 desc, idx[Q,k] int64)."""
+    _need_cuda(q, keys, key_inv_norm, keys_bf16)
+    q, keys = _f32c(q, "cosine_topk"), _f32c(keys, "cosine_topk")
+    if q.dim() != 2 or keys.dim() != 2 or q.shape[1] != keys.shape[1]:
+        raise RuntimeError(f"cosine_topk: shapes {tuple(q.shape)} vs {tuple(keys.shape)}")
+    Q, N, d = q.shape[0], keys.shape[0], q.shape[1]
+    if key_inv_norm is not None:
+        key_inv_norm = _f32c(key_inv_norm, "key_inv_norm")
+        if key_inv_norm.numel() != N:
+            raise RuntimeError("cosine_topk: key_inv_norm must have N entries")
+    if keys_bf16 is not None:
+        if keys_bf16.dtype != torch.bfloat16 or tuple(keys_bf16.shape) != (N, round_up(d, 64)) \
+                or not keys_bf16.is_contiguous():
+            raise RuntimeError("cosine_topk: keys_bf16 must be the contiguous [N, round_up(d,64)] bf16 shadow")
+    scores = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+    lib = L.load()
+    ws = _workspace(lib.rag_cosine_topk_workspace(Q, N, d, k, mode), q.device)
+    with torch.cuda.device(q.device):
+        L.check(lib.rag_cosine_topk_f32(_p(q), Q, _p(keys), _p(key_inv_norm), _p(keys_bf16), N, d, k, mode, flags,
+                                        idx_offset, _p(scores), _p(idx), _p(ws), ws.numel(), _stream()),
+                "cosine_topk")
+    return scores, idx
+
+
+@cosine_topk.register_fake
+def _(q, keys, k, key_inv_norm=None, keys_bf16=None, mode=0, flags=0, idx_offset=0):
+    return q.new_empty((q.shape[0], k)), q.new_empty((q.shape[0], k), dtype=torch.int64)
+
+
+@torch.library.custom_op("ragraph::cosine2_topk", mutates_args=())
+def cosine2_topk(qa: Tensor, ka: Tensor, w_a: float, qb: Tensor, kb: Tensor, w_b: float,
+                 k: int) -> Tuple[Tensor, Tensor]:
+    """top-k of w_a*cos(qa,ka) + w_b*cos(qb,kb) (node_fewshot two-metric retrieval)."""
+    _need_cuda(qa, ka, qb, kb)
+    qa, ka, qb, kb = (_f32c(t, "cosine2_topk") for t in (qa, ka, qb, kb))
+    Q, N = qa.shape[0], ka.shape[0]
+    if qb.shape[0] != Q or kb.shape[0] != N or qa.shape[1] != ka.shape[1] or qb.shape[1] != kb.shape[1]:
+        raise RuntimeError("cosine2_topk: inconsistent shapes")
+    scores = torch.empty((Q, k), dtype=torch.float32, device=qa.device)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=qa.device)
+    lib = L.load()
+    ws = _workspace(lib.rag_cosine2_topk_workspace(Q, N, qa.shape[1], qb.shape[1], k), qa.device)
+    with torch.cuda.device(qa.device):
+        L.check(lib.rag_cosine2_topk_f32(_p(qa), _p(ka), qa.shape[1], w_a, _p(qb), _p(kb), qb.shape[1], w_b, Q, N, k,
+                                         _p(scores), _p(idx), _p(ws), ws.numel(), _stream()), "cosine2_topk")
+    return scores, idx
+
+
+@cosine2_topk.register_fake
+def _(qa, ka, w_a, qb, kb, w_b, k):
+    return qa.new_empty((qa.shape[0], k)), qa.new_empty((qa.shape[0], k), dtype=torch.int64)
+
+
+@torch.library.custom_op("ragraph::topk_merge", mutates_args=())
+def topk_merge(scores: Tensor, idx: Tensor, k_out: int) -> Tuple[Tensor, Tensor]:
+    """[R,Q,k_in] per-shard candidates -> global [Q,k_out] (score desc, index asc)."""
+    _need_cuda(scores, idx)
+    scores = _f32c(scores, "topk_merge")
+    idx = idx.contiguous()
+    if idx.dtype != torch.int64 or scores.shape != idx.shape or scores.dim() != 3:
+        raise RuntimeError("topk_merge: scores f32 [R,Q,k] and idx int64 [R,Q,k] expected")
+    R, Q, k_in = scores.shape
+    out_s = torch.empty((Q, k_out), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((Q, k_out), dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        L.check(L.load().rag_topk_merge(_p(scores), _p(idx), R, Q, k_in, k_out, _p(out_s), _p(out_i), _stream()),
+                "topk_merge")
+    return out_s, out_i
+
+
+@topk_merge.register_fake
+def _(scores, idx, k_out):
+    return scores.new_empty((scores.shape[1], k_out)), idx.new_empty((scores.shape[1], k_out))
+
+
+# ----------------------------------------------------------------------------- gathers
+def _row_bytes(table: Tensor) -> int:
+    n = table.element_size()
+    for s in table.shape[1:]:
+        n *= s
+    return n
+
+
+@torch.library.custom_op("ragraph::gather_rows", mutates_args=())
+def gather_rows(table: Tensor, idx: Tensor) -> Tensor:
+    """``table[idx]`` (advanced indexing on dim 0), bit exact, any dtype."""
+    _need_cuda(table, idx)
+    if idx.dtype != torch.int64:
+        raise RuntimeError("gather_rows: idx must be int64")
+    table, idx = table.contiguous(), idx.contiguous()
+    out = torch.empty(tuple(idx.shape) + tuple(table.shape[1:]), dtype=table.dtype, device=table.device)
+    if out.numel():
+        N = table.shape[0]
+        with torch.cuda.device(table.device):
+            L.check(L.load().rag_gather_rows(_p(table), N, _row_bytes(table), _p(idx), idx.numel(), 0, N, _p(out),
+                                             _stream()), "gather_rows")
+    return out
+
+
+@gather_rows.register_fake
+def _(table, idx):
+    return table.new_empty(tuple(idx.shape) + tuple(table.shape[1:]))
+
+
+@torch.library.custom_op("ragraph::gather_rows_owned", mutates_args=("out",))
+def gather_rows_owned(table_local: Tensor, idx: Tensor, owner_lo: int, n_global: int, out: Tensor) -> None:
+    """Sharded 'owners gather': fill out[m] = table_local[idx[m]-owner_lo] for the global indices
+    this shard owns ([owner_lo, owner_lo+rows)); other rows of ``out`` are left untouched."""
+    _need_cuda(table_local, idx, out)
+    if idx.dtype != torch.int64 or not (table_local.is_contiguous() and idx.is_contiguous() and out.is_contiguous()):
+        raise RuntimeError("gather_rows_owned: contiguous tensors and int64 idx expected")
+    if idx.numel():
+        with torch.cuda.device(out.device):
+            L.check(L.load().rag_gather_rows(_p(table_local), n_global, _row_bytes(table_local), _p(idx), idx.numel(),
+                                             owner_lo, owner_lo + table_local.shape[0], _p(out), _stream()),
+                    "gather_rows_owned")
+
+
+@torch.library.custom_op("ragraph::gather_reduce", mutates_args=())
+def gather_reduce(table: Tensor, idx: Tensor, op: int = 0, blend_in: Optional[Tensor] = None,
+                  blend_w: float = 0.0) -> Tensor:
+    """reduce_j table[idx[q,j]] (op 0 = sum, 1 = mean), optionally (1-w)*blend_in + w*reduce."""
+    _need_cuda(table, idx, blend_in)
+    table = _f32c(table, "gather_reduce")
+    idx = idx.contiguous()
+    if idx.dtype != torch.int64 or idx.dim() != 2 or table.dim() != 2:
+        raise RuntimeError("gather_reduce: table [N,d] f32 and idx [Q,k] int64 expected")
+    Q, k = idx.shape
+    out = torch.empty((Q, table.shape[1]), dtype=torch.float32, device=table.device)
+    if blend_in is not None:
+        blend_in = _f32c(blend_in, "blend_in")
+        if blend_in.shape != out.shape:
+            raise RuntimeError("gather_reduce: blend_in must be [Q,d]")
+    if Q:
+        with torch.cuda.device(table.device):
+            L.check(L.load().rag_gather_reduce_f32(_p(table), table.shape[0], table.shape[1], _p(idx), Q, k, op,
+                                                   _p(blend_in), blend_w, _p(out), _stream()), "gather_reduce")
+    return out
+
+
+@gather_reduce.register_fake
+def _(table, idx, op=0, blend_in=None, blend_w=0.0):
+    return table.new_empty((idx.shape[0], table.shape[1]))
+
+
+# ----------------------------------------------------------------------------- CSR SpMM
+@torch.library.custom_op("ragraph::csr_spmm", mutates_args=())
+def csr_spmm(rowptr: Tensor, col: Tensor, val: Optional[Tensor], x: Tensor, epilogue: int = 0,
+             bias: Optional[Tensor] = None, alpha: Optional[Tensor] = None, blend_in: Optional[Tensor] = None,
+             blend_w: float = 0.0, accum_in: Optional[Tensor] = None) -> Tensor:
+    _need_cuda(rowptr, col, val, x, bias, alpha, blend_in, accum_in)
+    x = _f32c(x, "csr_spmm")
+    if rowptr.dtype not in (torch.int64, torch.int32) or col.dtype != torch.int32:
+        raise RuntimeError("csr_spmm: rowptr int64/int32 and col int32 expected")
+    rowptr, col = rowptr.contiguous(), col.contiguous()
+    n_rows, n_src, F = rowptr.numel() - 1, x.shape[0], x.shape[1]
+    y = torch.empty((n_rows, F), dtype=torch.float32, device=x.device)
+    val = None if val is None else _f32c(val, "val")
+    bias = None if bias is None else _f32c(bias, "bias")
+    alpha = None if alpha is None else _f32c(alpha, "alpha").reshape(-1)
+    blend_in = None if blend_in is None else _f32c(blend_in, "blend_in")
+    accum_in = None if accum_in is None else _f32c(accum_in, "accum_in")
+    for t, nm in ((blend_in, "blend_in"), (accum_in, "accum_in")):
+        if t is not None and t.shape != y.shape:
+            raise RuntimeError(f"csr_spmm: {nm} must be [n_rows, F]")
+    if n_rows:
+        with torch.cuda.device(x.device):
+            L.check(L.load().rag_csr_spmm_f32(_p(rowptr), int(rowptr.dtype == torch.int64), _p(col), _p(val), n_rows,
+                                              n_src, col.numel(), _p(x), F, epilogue, _p(bias), _p(alpha),
+                                              _p(blend_in), blend_w, _p(accum_in), _p(y), _stream()), "csr_spmm")
+    return y
+
+
+@csr_spmm.register_fake
+def _(rowptr, col, val, x, epilogue=0, bias=None, alpha=None, blend_in=None, blend_w=0.0, accum_in=None):
+    return x.new_empty((rowptr.numel() - 1, x.shape[1]))
+
+
+@torch.library.custom_op("ragraph::csr_from_coo", mutates_args=())
+def csr_from_coo(edges: Tensor, w: Optional[Tensor], n_rows: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """COO edges[E,2] int64 ([:,0]=src, [:,1]=dst) (+ weights) -> CSR grouped by dst."""
+    _need_cuda(edges, w)
+    if edges.dtype != torch.int64 or edges.dim() != 2 or edges.shape[1] != 2:
+        raise RuntimeError("csr_from_coo: edges must be int64 [E,2]")
+    edges = edges.contiguous()
+    w = None if w is None else _f32c(w, "w")
+    E, dev = edges.shape[0], edges.device
+    lib = L.load()
+    counts = torch.empty(n_rows, dtype=torch.int32, device=dev)
+    rowptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(E, dtype=torch.int32, device=dev)
+    val = torch.empty(E, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.rag_coo_count_rows(_p(edges), E, n_rows, _p(counts), _stream()), "coo_count_rows")
+        torch.cumsum(counts, 0, dtype=torch.int64, out=rowptr[1:])
+        L.check(lib.rag_coo_fill_csr(_p(edges), _p(w), E, n_rows, _p(rowptr), _p(counts), _p(col), _p(val),
+                                     _stream()), "coo_fill_csr")
+    return rowptr, col, val
+
+
+@csr_from_coo.register_fake
+def _(edges, w, n_rows):
+    E = edges.shape[0]
+    return (edges.new_empty(n_rows + 1), edges.new_empty(E, dtype=torch.int32),
+            edges.new_empty(E, dtype=torch.float32))
+
+
+@torch.library.custom_op("ragraph::csr_from_dense", mutates_args=())
+def csr_from_dense(adj: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """dense [n,m] adjacency -> CSR of its non-zeros (column order kept)."""
+    _need_cuda(adj)
+    adj = _f32c(adj, "csr_from_dense")
+    if adj.dim() != 2:
+        raise RuntimeError("csr_from_dense: 2-D adjacency expected")
+    n, m, dev = adj.shape[0], adj.shape[1], adj.device
+    lib = L.load()
+    counts = torch.empty(n, dtype=torch.int32, device=dev)
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.rag_dense_count_rows(_p(adj), n, m, _p(counts), _stream()), "dense_count_rows")
+        torch.cumsum(counts, 0, dtype=torch.int64, out=rowptr[1:])
+        nnz = int(rowptr[-1].item())           # sizes col/val (one sync; CSR is built once per adjacency)
+        col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        val = torch.empty(nnz, dtype=torch.float32, device=dev)
+        L.check(lib.rag_dense_fill_csr(_p(adj), n, m, _p(rowptr), _p(col), _p(val), _stream()), "dense_fill_csr")
+    return rowptr, col, val
+
+
+def gather_oob_count() -> int:
+    return int(L.load().rag_gather_oob_count())

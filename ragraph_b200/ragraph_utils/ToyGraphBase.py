@@ -1,0 +1,172 @@
+"""Mirror of the reference's toy-graph vector store and its retrieve().
+
+Reference: RAGraph_node/ragraph_utils/ToyGraphBase.py:15-119 (node), RAGraph_graph/.../ToyGraphBase.py:56-87
+(graph: one 1-D query), RAGraph_node_fewshot/.../ToyGraphBase.py:47-79 (two-metric scores).
+
+What changes on B200: the four ever-growing ``torch.cat`` tensors (:35-38, :116-119) become a pre-sized
+device-resident store (capacity doubling), extended with two derived arrays the kernels want -- the fp32
+inverse key norms (so keys are not re-normalised on every call, SimilarityFunctions.py:11) and the
+normalised bf16 shadow read by the tcgen05 filter.  retrieve() keeps the reference signature and return
+shapes; similarity + top-k is one fused launch (scores never reach HBM) and the value/label lookups are
+the bit-exact gather kernel.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from .. import _lib as L
+from .. import ops
+
+
+class ToyGraphBase:
+    def __init__(self, pretrain_model=None, num_class: int = 3, emb_size: int = 256, query_graph_hop: int = 3,
+                 device: Optional[torch.device] = None, variant: str = "node", capacity: int = 1024,
+                 mode: Optional[int] = None, label_dtype: torch.dtype = torch.float32) -> None:
+        assert variant in ("node", "graph", "node_fewshot")
+        self.variant = variant
+        # inference-phase knobs, same names and defaults as the reference (:22-29)
+        self.retrieve_num = num_class + 1 if variant != "graph" else min(3, num_class + 1)
+        self.noise_retrieve_num = 1
+        self.num_anchors = 10
+        self.dis_q = 10
+        self.structure_weight = 0.001 if variant == "node_fewshot" else 0.0
+        self.semantic_weight = 0.999
+        self.noise_std = 0.1
+        self.toy_graph_hop = query_graph_hop - 1
+        self.pretrain_model = pretrain_model
+        self.mode = mode                      # None = pick per library size (see _pick_mode)
+
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.emb_size, self.num_class = emb_size, num_class
+        self._n = 0
+        self._cap = 0
+        self._label_dtype = label_dtype
+        self._keys = self._values = self._labels = self._positions = None
+        self._inv_norm = self._keys_bf16 = None
+        self._derived_rows = 0                # rows [0, _derived_rows) of inv_norm / bf16 shadow are valid
+        self._reserve(capacity)
+
+    # ---- store ---------------------------------------------------------------------------
+    def _reserve(self, cap: int) -> None:
+        if cap <= self._cap:
+            return
+        cap = max(cap, 2 * self._cap)
+        dev, n = self.device, self._n
+
+        def grow(old, shape, dtype):
+            new = torch.empty(shape, dtype=dtype, device=dev)
+            if old is not None and n:
+                new[:n].copy_(old[:n])
+            return new
+
+        self._keys = grow(self._keys, (cap, self.emb_size), torch.float32)
+        self._values = grow(self._values, (cap, self.emb_size), torch.float32)
+        self._labels = grow(self._labels, (cap, self.num_class), self._label_dtype)
+        self._positions = grow(self._positions, (cap, self.num_anchors), torch.float32)
+        self._inv_norm = grow(self._inv_norm, (cap,), torch.float32)
+        self._keys_bf16 = None                # rebuilt lazily at the size in use
+        self._cap = cap
+
+    def add_entries(self, keys: Tensor, values: Tensor, labels: Tensor, positions: Optional[Tensor] = None) -> None:
+        """Append library rows (the torch.cat of ToyGraphBase.py:116-119)."""
+        m = keys.shape[0]
+        self._reserve(self._n + m)
+        s = slice(self._n, self._n + m)
+        self._keys[s].copy_(keys)
+        self._values[s].copy_(values)
+        self._labels[s].copy_(labels.to(self._label_dtype))
+        if positions is not None:
+            self._positions[s].copy_(positions)
+        else:
+            self._positions[s].zero_()
+        self._n += m
+
+    def _refresh_derived(self, want_bf16: bool) -> None:
+        n = self._n
+        if self._derived_rows < n:
+            lo = self._derived_rows
+            self._inv_norm[lo:n].copy_(ops.row_inv_norm(self._keys[lo:n]))
+            self._derived_rows = n
+            self._keys_bf16 = None
+        if want_bf16 and (self._keys_bf16 is None or self._keys_bf16.shape[0] != n):
+            self._keys_bf16 = ops.rows_to_bf16(self._keys[:n], True)
+
+    # reference attribute names (views of the rows in use)
+    @property
+    def resource_keys(self) -> Tensor: return self._keys[:self._n]
+    @property
+    def resource_values(self) -> Tensor: return self._values[:self._n]
+    @property
+    def resource_labels(self) -> Tensor: return self._labels[:self._n]
+    @property
+    def resource_positions(self) -> Tensor: return self._positions[:self._n]
+    @property
+    def key_inv_norm(self) -> Tensor:
+        self._refresh_derived(False)
+        return self._inv_norm[:self._n]
+
+    def __len__(self) -> int:
+        return self._n
+
+    def show(self):
+        print('resource_keys', self.resource_keys.shape)
+        print('resource_values', self.resource_values.shape)
+        print('resource_labels', self.resource_labels.shape)
+        print("label count distribution", torch.sum(self.resource_labels, dim=0))
+
+    # ---- retrieval ------------------------------------------------------------------------
+    def _pick_mode(self, Q: int) -> int:
+        if self.mode is not None:
+            return self.mode
+        # tensor-core filter + fp32 refine pays off once the scan is large; both are exact-match
+        return L.SIM_BF16_REFINE if (self._n >= 65536 and self.emb_size % 64 == 0 and Q >= 16) else L.SIM_FP32
+
+    def topk(self, search_keys: Tensor, k: int, search_positions: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        """(scores[Q,k], indices[Q,k] int64): torch.topk(cosine(search_keys, resource_keys), k) fused."""
+        if self.variant == "node_fewshot" and self.structure_weight != 0.0:
+            if search_positions is None:
+                raise RuntimeError("node_fewshot retrieval needs search_positions (position-aware codes)")
+            return ops.cosine2_topk(search_positions, self.resource_positions, self.structure_weight,
+                                    search_keys, self.resource_keys, self.semantic_weight, k)
+        mode = self._pick_mode(search_keys.shape[0])
+        self._refresh_derived(mode != L.SIM_FP32)
+        return ops.cosine_topk(search_keys, self.resource_keys, k, self._inv_norm[:self._n],
+                               self._keys_bf16 if mode != L.SIM_FP32 else None, mode)
+
+    def retrieve(self, search_keys: Tensor, search_adj, add_noise: bool, search_positions: Optional[Tensor] = None):
+        """Same contract as the reference: returns (rag_embeddings[Q,k',d], rag_labels[Q,k',C]).
+        node (:47-81): add_noise doubles k and appends noise_retrieve_num random rows (CPU torch.randint,
+        same RNG call as the reference); graph (:56-87): a 1-D query gives Q=1, add_noise adds N(0, noise_std)
+        to the gathered values (:84-85)."""
+        if search_keys.dim() == 1:
+            search_keys = search_keys.unsqueeze(0)
+        retrieve_num = 2 * self.retrieve_num if add_noise else self.retrieve_num
+        _, topk_indices = self.topk(search_keys, retrieve_num, search_positions)
+        rag_embeddings = ops.gather_rows(self.resource_values, topk_indices)
+        rag_labels = ops.gather_rows(self.resource_labels, topk_indices)
+        if add_noise:
+            if self.variant == "graph":
+                noise = torch.normal(mean=0, std=self.noise_std, size=rag_embeddings.shape).to(rag_embeddings.device)
+                rag_embeddings = rag_embeddings + noise
+            else:
+                noise_indices = torch.randint(0, self._n, (search_keys.shape[0], self.noise_retrieve_num))
+                noise_indices = noise_indices.to(self.device)
+                rag_embeddings = torch.cat([rag_embeddings, ops.gather_rows(self.resource_values, noise_indices)], dim=1)
+                rag_labels = torch.cat([rag_labels, ops.gather_rows(self.resource_labels, noise_indices)], dim=1)
+        return rag_embeddings, rag_labels
+
+    def retrieve_fused(self, search_keys: Tensor, k: Optional[int] = None, reduce: int = L.REDUCE_SUM,
+                       blend_in: Optional[Tensor] = None, blend_w: float = 0.0):
+        """The reduction every caller applies next, without the [Q,k,d] round trip: returns
+        (sum|mean over k of values[idx] (optionally blended with blend_in), mean over k of labels[idx], idx)."""
+        if search_keys.dim() == 1:
+            search_keys = search_keys.unsqueeze(0)
+        k = self.retrieve_num if k is None else k
+        _, idx = self.topk(search_keys, k)
+        emb = ops.gather_reduce(self.resource_values, idx, reduce, blend_in, blend_w)
+        labels = self.resource_labels if self.resource_labels.dtype == torch.float32 else self.resource_labels.float()
+        lab = ops.gather_reduce(labels, idx, L.REDUCE_MEAN)
+        return emb, lab, idx

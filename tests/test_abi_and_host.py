@@ -1,0 +1,73 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every declared symbol; host logic."""
+import os
+import re
+
+import pytest
+import torch
+
+import ragraph_b200
+from ragraph_b200 import _lib
+from ragraph_b200.sharded import owner_of, shard_bounds
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ragraph_b200.h")).read()
+    return sorted(set(re.findall(r"RAG_API\s+[\w\s\*]+?\b(rag_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported_and_bound():
+    if not os.path.exists(_lib.LIB_PATH):
+        from ragraph_b200 import build
+        build.build()
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ragraph_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(names)
+    assert lib.rag_abi_version() == 1
+    assert lib.rag_status_string(-3) == b"RAG_EUNSUPPORTED"
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ragraph_b200.ops.cosine_topk(torch.randn(2, 8), torch.randn(9, 8), 2)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ragraph_b200.ops.gather_rows(torch.randn(4, 8), torch.zeros(2, dtype=torch.int64))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ragraph_b200.Propagation.aggregate_k_hop_features(torch.eye(3), torch.randn(3, 4), 1)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "ragraph_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+@pytest.mark.parametrize("n,world", [(10, 1), (10, 3), (7, 8), (100_000_000, 8), (5, 5), (0, 2)])
+def test_shard_bounds_partition(n, world):
+    spans = [shard_bounds(n, world, r) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    for (a, b), (c, d) in zip(spans, spans[1:]):
+        assert b == c and b >= a
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) - min(sizes) <= 1
+    if 0 < n <= 1000:
+        idx = torch.arange(n)
+        own = owner_of(idx, n, world)
+        for r, (a, b) in enumerate(spans):
+            assert torch.all(own[a:b] == r)
+
+
+def test_fake_kernels_shape_inference():
+    q = torch.empty(5, 16, device="meta"); keys = torch.empty(40, 16, device="meta")
+    s, i = torch.ops.ragraph.cosine_topk(q, keys, 3)
+    assert s.shape == (5, 3) and i.dtype == torch.int64
+    g = torch.ops.ragraph.gather_rows(keys, torch.empty(5, 3, dtype=torch.int64, device="meta"))
+    assert g.shape == (5, 3, 16)
