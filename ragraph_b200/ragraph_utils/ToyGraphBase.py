@@ -65,7 +65,8 @@ class ToyGraphBase:
         self._keys = grow(self._keys, (cap, self.emb_size), torch.float32)
         self._values = grow(self._values, (cap, self.emb_size), torch.float32)
         self._labels = grow(self._labels, (cap, self.num_class), self._label_dtype)
-        self._positions = grow(self._positions, (cap, self.num_anchors), torch.float32)
+        if self.variant == "node_fewshot":           # position codes only feed the two-metric score
+            self._positions = grow(self._positions, (cap, self.num_anchors), torch.float32)
         self._inv_norm = grow(self._inv_norm, (cap,), torch.float32)
         self._keys_bf16 = None                # rebuilt lazily at the size in use
         self._cap = cap
@@ -78,10 +79,11 @@ class ToyGraphBase:
         self._keys[s].copy_(keys)
         self._values[s].copy_(values)
         self._labels[s].copy_(labels.to(self._label_dtype))
-        if positions is not None:
-            self._positions[s].copy_(positions)
-        else:
-            self._positions[s].zero_()
+        if self._positions is not None:
+            if positions is not None:
+                self._positions[s].copy_(positions)
+            else:
+                self._positions[s].zero_()
         self._n += m
 
     def _refresh_derived(self, want_bf16: bool) -> None:
@@ -102,7 +104,8 @@ class ToyGraphBase:
     @property
     def resource_labels(self) -> Tensor: return self._labels[:self._n]
     @property
-    def resource_positions(self) -> Tensor: return self._positions[:self._n]
+    def resource_positions(self) -> Tensor:
+        return None if self._positions is None else self._positions[:self._n]
     @property
     def key_inv_norm(self) -> Tensor:
         self._refresh_derived(False)

@@ -1,0 +1,355 @@
+"""GPU parity tests: the CUDA path (through torch.ops.ragraph -> C ABI) against the CPU oracle and the
+reference-generated golden vectors.  Tolerances are the north-star ones: top-k index sets identical except
+ties within 1e-6, scores / propagated embeddings within 1e-5 relative (fp32), gathers bit exact."""
+import numpy as np
+import pytest
+import torch
+
+import ragraph_b200 as R
+from ragraph_b200 import _lib as L
+from ragraph_b200 import ops
+from oracle import ragraph_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+T = torch.from_numpy
+REL = 1e-5
+
+
+def cu(a):
+    return (T(a) if isinstance(a, np.ndarray) else a).to(DEV)
+
+
+def test_library_loaded_and_counts_launches():
+    before = L.launch_count()
+    ops.row_inv_norm(torch.randn(10, 8, device=DEV))
+    assert L.launch_count() == before + 1
+    assert L.load().rag_abi_version() == 1
+
+
+# ------------------------------------------------------------------------------------------ gathers
+@pytest.mark.parametrize("d", [3, 16, 64, 128, 256, 250])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.int64])
+def test_gather_rows_bit_exact(d, dtype):
+    g = torch.Generator().manual_seed(d)
+    N, Q, k = 5000, 333, 7
+    table = torch.randn(N, d, generator=g) if dtype == torch.float32 else torch.randint(-9, 9, (N, d), generator=g)
+    table = table.to(dtype)
+    if dtype == torch.float32:
+        table[0, 0] = -0.0                      # sign of zero must survive
+        table[1, 0] = float("nan")
+    idx = torch.randint(-N, N, (Q, k), generator=g)           # negative indices wrap like torch
+    idx[0, 0], idx[0, 1] = 0, 1
+    out = ops.gather_rows(cu(table), cu(idx)).cpu()
+    ref = O.gather_rows(table, idx)
+    assert out.shape == ref.shape and out.dtype == ref.dtype
+    assert np.array_equal(out.numpy().view(np.uint8), ref.numpy().view(np.uint8))
+
+
+def test_gather_rows_edge_cases():
+    table = torch.randn(10, 8, device=DEV)
+    assert ops.gather_rows(table, torch.empty((0, 4), dtype=torch.int64, device=DEV)).shape == (0, 4, 8)
+    idx = torch.tensor([9, 0, 9], device=DEV)
+    assert torch.equal(ops.gather_rows(table, idx), table[idx])
+    v = table[:, 1:5]                            # non-contiguous view is made contiguous by the wrapper
+    assert torch.equal(ops.gather_rows(v, idx), v[idx])
+    before = ops.gather_oob_count()
+    out = ops.gather_rows(table, torch.tensor([3, 10], device=DEV))
+    torch.cuda.synchronize()
+    assert ops.gather_oob_count() == before + 1 and torch.all(out[1] == 0) and torch.equal(out[0], table[3])
+
+
+@pytest.mark.parametrize("d", [16, 32, 64, 128, 256, 512, 20])
+@pytest.mark.parametrize("op", [L.REDUCE_SUM, L.REDUCE_MEAN])
+def test_gather_reduce(d, op):
+    g = torch.Generator().manual_seed(100 + d)
+    N, Q, k = 3000, 257, 10
+    table = torch.randn(N, d, generator=g); idx = torch.randint(0, N, (Q, k), generator=g)
+    ref = table[idx].sum(1) if op == L.REDUCE_SUM else table[idx].mean(1)
+    out = ops.gather_reduce(cu(table), cu(idx), op).cpu()
+    assert O.rel_err(out, ref) < REL
+    base = torch.randn(Q, d, generator=g)
+    outb = ops.gather_reduce(cu(table), cu(idx), op, cu(base), 0.3).cpu()
+    assert O.rel_err(outb, (1 - 0.3) * base + 0.3 * ref) < REL
+
+
+# ------------------------------------------------------------------------------------------ similarity
+def test_cosine_similarity_golden(golden):
+    g = golden("node_retrieve")
+    S = R.SimilarityFunctions.calculate_cosine_similarity(cu(g["q"]), cu(g["keys"])).cpu().numpy()
+    assert S.shape == g["cosine"].shape
+    assert O.rel_err(S, g["cosine"]) < REL
+    assert np.all(S[5] == 0.0) and np.all(S[:, 44] == 0.0)          # zero rows: eps clamp, no NaN
+    s1 = R.SimilarityFunctions.calculate_cosine_similarity(cu(g["q"][3]), cu(g["keys"])).cpu().numpy()
+    assert s1.shape == (600,) and O.rel_err(s1, g["cosine"][3]) < REL
+
+
+def _check_topk(q, keys, k, mode=L.SIM_FP32, **kw):
+    scores, idx = ops.cosine_topk(cu(q), cu(keys), k, mode=mode, **kw)
+    scores, idx = scores.cpu().numpy(), idx.cpu().numpy()
+    S64 = O.cosine_similarity_f64(q.numpy(), keys.numpy())
+    ok, bad = O.topk_sets_match(idx, S64, k)
+    assert ok, bad[:5]
+    exact = np.take_along_axis(S64, idx, axis=1)
+    assert np.max(np.abs(scores - exact)) <= REL * max(1.0, np.abs(exact).max())
+    assert np.all(scores[:, :-1] >= scores[:, 1:])                  # sorted descending
+    ref_s, _ = O.topk(O.cosine_similarity(q, keys), k)
+    assert O.rel_err(scores, ref_s.numpy()) < REL
+    return scores, idx
+
+
+@pytest.mark.parametrize("Q,N,d,k", [(37, 600, 32, 4), (1, 300, 256, 3), (300, 20000, 128, 10), (64, 1000, 30, 1),
+                                     (5, 128, 64, 128), (129, 4097, 266, 20), (4, 7, 8, 7), (1000, 50000, 64, 50)])
+def test_cosine_topk_fp32_vs_oracle(Q, N, d, k):
+    g = torch.Generator().manual_seed(Q * 131 + N)
+    q = torch.randn(Q, d, generator=g); keys = torch.randn(N, d, generator=g)
+    if N > 20:
+        keys[N // 2] = keys[1]                  # exact duplicate -> tie
+        keys[3] = 0.0
+    _check_topk(q, keys, k)
+
+
+def test_cosine_topk_golden_and_ties(golden):
+    g = golden("node_retrieve")
+    q, keys = T(g["q"]), T(g["keys"])
+    for k in (4, 8):
+        _check_topk(q, keys, k)
+    # deterministic order: score desc, index asc (key 17 duplicates key 3)
+    _, idx = ops.cosine_topk(cu(q), cu(keys), 100)
+    idx = idx.cpu().numpy()
+    for row in idx:
+        p3, p17 = np.where(row == 3)[0], np.where(row == 17)[0]
+        if len(p3) and len(p17):
+            assert p17[0] == p3[0] + 1
+    z = ops.cosine_topk(cu(q[5:6]), cu(keys), 5)[1].cpu().numpy()   # zero query: all ties -> lowest indices
+    assert z.tolist() == [[0, 1, 2, 3, 4]]
+
+
+def test_cosine_topk_precomputed_norms_and_offset():
+    g = torch.Generator().manual_seed(5)
+    q, keys = torch.randn(50, 64, generator=g), torch.randn(3000, 64, generator=g) * 3
+    inv = ops.row_inv_norm(cu(keys))
+    s0, i0 = ops.cosine_topk(cu(q), cu(keys), 10)
+    s1, i1 = ops.cosine_topk(cu(q), cu(keys), 10, key_inv_norm=inv, idx_offset=1_000_000_000_000)
+    assert torch.equal(s0, s1) and torch.equal(i0 + 1_000_000_000_000, i1)
+    sd, idd = ops.cosine_topk(cu(q), cu(keys), 10, flags=L.SIM_DOT)
+    ref_s, ref_i = torch.topk(q @ keys.t(), 10)
+    assert O.rel_err(sd.cpu(), ref_s) < REL and O.recall_at_k(idd.cpu(), ref_i) > 0.999
+
+
+def test_cosine_topk_errors():
+    q, keys = torch.randn(4, 8, device=DEV), torch.randn(20, 8, device=DEV)
+    with pytest.raises(L.RagError, match="RAG_EINVAL"):
+        ops.cosine_topk(q, keys, 21)
+    with pytest.raises(L.RagError, match="RAG_EUNSUPPORTED"):
+        ops.cosine_topk(q, torch.randn(500, 8, device=DEV), 200)
+    with pytest.raises(RuntimeError):
+        ops.cosine_topk(q, torch.randn(20, 9, device=DEV), 2)
+
+
+def test_two_metric_retrieve_golden(golden):
+    g = golden("fewshot_retrieve")
+    base = R.ToyGraphBase(None, 3, 32, 3, variant="node_fewshot")
+    base.retrieve_num = int(g["retrieve_num"])
+    base.add_entries(cu(g["keys"]), cu(g["values"]), cu(g["labels"]), cu(g["positions"]))
+    emb, lab = base.retrieve(cu(g["q"]), None, False, search_positions=cu(g["search_positions"]))
+    assert np.array_equal(emb.cpu().numpy(), g["rag_embeddings"])
+    assert np.array_equal(lab.cpu().numpy(), g["rag_labels"])
+
+
+def test_topk_merge_vs_oracle():
+    g = torch.Generator().manual_seed(11)
+    Rr, Q, k = 8, 100, 10
+    s = torch.randn(Rr, Q, k, generator=g).sort(dim=2, descending=True).values
+    s[3, :, 2] = s[5, :, 1]                                         # cross-shard ties
+    i = torch.randint(0, 10**9, (Rr, Q, k), generator=g)
+    ms, mi = ops.topk_merge(cu(s), cu(i), k)
+    rs, ri = O.merge_topk(s, i, k)
+    assert torch.equal(ms.cpu(), rs) and torch.equal(mi.cpu(), ri)
+    ms5, mi5 = ops.topk_merge(cu(s), cu(i), 5)
+    assert torch.equal(mi5.cpu(), ri[:, :5])
+    i2 = i.clone(); i2[0, :, 5:] = -1                               # padded candidates never win
+    _, mi2 = ops.topk_merge(cu(s), cu(i2), k)
+    assert (mi2 >= 0).all()
+
+
+# ------------------------------------------------------------------------------------------ ToyGraphBase
+def test_toygraphbase_retrieve_golden(golden):
+    g = golden("node_retrieve")
+    base = R.ToyGraphBase(None, 3, 32, 3, capacity=100)             # forces growth
+    base.add_entries(cu(g["keys"][:250]), cu(g["values"][:250]), cu(g["labels"][:250]))
+    base.add_entries(cu(g["keys"][250:]), cu(g["values"][250:]), cu(g["labels"][250:]))
+    assert len(base) == 600 and base.retrieve_num == int(g["retrieve_num"])
+    emb, lab = base.retrieve(cu(g["q"]), None, False)
+    # rows 5 (zero query) ties everywhere: compare all other rows bit-exactly against the reference
+    keep = [r for r in range(37) if r != 5]
+    assert np.array_equal(emb.cpu().numpy()[keep], g["rag_embeddings"][keep])
+    assert np.array_equal(lab.cpu().numpy()[keep], g["rag_labels"][keep])
+    torch.manual_seed(77)                                           # same CPU randint stream as the reference
+    emb_n, lab_n = base.retrieve(cu(g["q"]), None, True)
+    assert emb_n.shape == g["rag_embeddings_noise"].shape
+    keep = [r for r in keep if r != 22]      # row 22: duplicate keys 3/17 tie at ranks 7-8 (order unspecified in torch)
+    assert np.array_equal(emb_n.cpu().numpy()[keep], g["rag_embeddings_noise"][keep])
+    assert np.array_equal(lab_n.cpu().numpy()[keep], g["rag_labels_noise"][keep])
+    a, b = emb_n.cpu().numpy()[22], g["rag_embeddings_noise"][22]
+    assert np.array_equal(a[:6], b[:6]) and np.array_equal(a[[7, 6]], b[6:8]) and np.array_equal(a[8], b[8])
+
+
+def test_toygraphbase_graph_variant_golden(golden):
+    g = golden("graph_retrieve")
+    base = R.ToyGraphBase(None, 6, 32, 1, variant="graph")
+    base.add_entries(cu(g["keys"]), cu(g["values"]), cu(g["labels"]))
+    emb, lab = base.retrieve(cu(g["q"]), None, False)               # 1-D query
+    assert emb.shape == (1, 3, 32) and lab.shape == (1, 3, 6)
+    assert np.array_equal(emb.cpu().numpy(), g["rag_embeddings"])
+    assert np.array_equal(lab.cpu().numpy(), g["rag_labels"])
+
+
+# ------------------------------------------------------------------------------------------ propagation
+def test_propagation_golden(golden):
+    g = golden("propagation")
+    adj, x = cu(g["adj"]), cu(g["x"])
+    for k in (0, 1, 2, 3):
+        out = R.Propagation.aggregate_k_hop_features(adj, x, k).cpu().numpy()
+        assert O.rel_err(out, g[f"out_k{k}"]) < REL
+
+
+def test_gcn_layer_golden(golden):
+    g = golden("gcn_layer")
+    layer = R.GCN(24, 16, 'prelu').to(DEV)
+    with torch.no_grad():
+        layer.fc.weight.copy_(cu(g["weight"])); layer.bias.copy_(cu(g["bias"])); layer.act.weight.copy_(cu(g["alpha"]))
+    out = layer((cu(g["seq"]), cu(g["adj"]).unsqueeze(0))).cpu().numpy()
+    assert np.max(np.abs(out - g["out"])) < 2e-5 * max(1.0, np.abs(g["out"]).max())   # includes cuBLAS XW
+    sp = cu(g["adj"]).to_sparse()
+    out_sp = layer((cu(g["seq"]), sp), sparse=True).cpu().numpy()
+    assert np.max(np.abs(out_sp - g["out"])) < 2e-5 * max(1.0, np.abs(g["out"]).max())
+
+
+def test_edge_agg_golden(golden):
+    g = golden("edge_agg")
+    n = int(g["num_nodes"])
+    Y = R.edge._agg(cu(g["X"]), cu(g["edges"]), cu(g["w"]), n).cpu().numpy()
+    ref64 = O.edge_agg_f64(g["X"], g["edges"], g["w"], n)
+    assert O.rel_err(Y, ref64) < REL and O.rel_err(Y, g["Y"]) < REL
+    Yd = R.CSRGraph.from_coo(cu(g["edges"]), cu(g["w"]), n, deterministic=True).spmm(cu(g["X"])).cpu().numpy()
+    assert O.rel_err(Yd, ref64) < REL
+    src = T(g["X"])[T(g["edges"])[:, 0]]
+    S = R.scatter_sum(cu(src), cu(g["edges"][:, 1]), dim=0, dim_size=n).cpu().numpy()
+    assert O.rel_err(S, g["scatter"]) < REL
+
+
+def _powerlaw_csr(n, avg, max_deg, F, seed):
+    rng = np.random.default_rng(seed)
+    deg = np.minimum((rng.pareto(1.5, n) + 1) * avg / 3, max_deg).astype(np.int64)
+    deg[0] = max_deg; deg[1] = 0; deg[n - 1] = 0; deg[7] = 1025; deg[8] = 1024
+    rowptr = np.zeros(n + 1, np.int64); rowptr[1:] = np.cumsum(deg)
+    nnz = int(rowptr[-1])
+    col = rng.integers(0, n, nnz).astype(np.int32)
+    val = rng.random(nnz).astype(np.float32)
+    x = rng.standard_normal((n, F)).astype(np.float32)
+    return rowptr, col, val, x
+
+
+@pytest.mark.parametrize("F", [16, 32, 64, 128, 256, 512, 20, 1])
+def test_csr_spmm_powerlaw_vs_fp64(F):
+    import scipy.sparse as sp
+    n = 3000
+    rowptr, col, val, x = _powerlaw_csr(n, 20, 5000, F, seed=F)
+    A = sp.csr_matrix((val.astype(np.float64), col, rowptr), shape=(n, n))
+    ref = A @ x.astype(np.float64)
+    y = ops.csr_spmm(cu(rowptr), cu(col), cu(val), cu(x)).cpu().numpy()
+    assert O.rel_err(y, ref) < REL
+    y32 = ops.csr_spmm(cu(rowptr.astype(np.int32)), cu(col), None, cu(x)).cpu().numpy()     # int32 rowptr, val=None
+    A1 = sp.csr_matrix((np.ones_like(val, dtype=np.float64), col, rowptr), shape=(n, n))
+    assert O.rel_err(y32, A1 @ x.astype(np.float64)) < REL
+    # all epilogues at once, against numpy
+    bias = np.linspace(-1, 1, F).astype(np.float32); alpha = np.array([0.25], np.float32)
+    blend = np.random.default_rng(1).standard_normal((n, F)).astype(np.float32)
+    acc = np.random.default_rng(2).standard_normal((n, F)).astype(np.float32)
+    epi = L.EPI_ROWNORM | L.EPI_BIAS | L.EPI_PRELU | L.EPI_BLEND | L.EPI_ACCUM
+    got = ops.csr_spmm(cu(rowptr), cu(col), cu(val), cu(x), epi, cu(bias), cu(alpha), cu(blend), 0.3, cu(acc)).cpu().numpy()
+    deg = np.asarray(A.sum(1)).reshape(-1, 1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        e = ref / deg + bias
+    e = np.where(e >= 0, e, 0.25 * e) * 0.7 + blend * 0.3 + acc
+    assert np.array_equal(np.isnan(got), np.isnan(e))               # empty rows: 0/0 = NaN like adj/degree
+    m = ~np.isnan(e)
+    assert O.rel_err(got[m], e[m]) < REL
+    r = ops.csr_spmm(cu(rowptr), cu(col), cu(val), cu(x), L.EPI_RELU).cpu().numpy()
+    assert O.rel_err(r, np.maximum(ref, 0)) < REL
+    assert np.array_equal(ops.csr_spmm(cu(rowptr), cu(col), cu(val), cu(x)).cpu().numpy(), y)   # deterministic
+
+
+def test_csr_from_dense_roundtrip():
+    g = torch.Generator().manual_seed(3)
+    adj = (torch.rand(70, 90, generator=g) < 0.1).float() * torch.rand(70, 90, generator=g)
+    adj[5] = 0
+    c = R.CSRGraph.from_dense(cu(adj))
+    dense = torch.zeros_like(adj)
+    rp, col, val = c.rowptr.cpu(), c.col.cpu().long(), c.val.cpu()
+    for r in range(70):
+        dense[r, col[rp[r]:rp[r + 1]]] = val[rp[r]:rp[r + 1]]
+    assert torch.equal(dense, adj) and c.nnz == int((adj != 0).sum())
+
+
+# ------------------------------------------------------------------------------------------ forwards
+class _PM:
+    def __init__(self, emb): self.emb = emb
+    def inference(self, features, adj): return self.emb
+
+
+def test_node_forward_golden(golden):
+    g = golden("node_forward")
+    base = R.ToyGraphBase(None, 3, 32, 3)
+    base.add_entries(cu(g["keys"]), cu(g["values"]), cu(g["labels"]))
+    model = R.RAGraph(_PM(cu(g["emb_q"])), base, 0, 3, 32).to(DEV).eval()
+    with torch.no_grad():
+        model.decoder.fc1.weight.copy_(cu(g["w1"])); model.decoder.fc1.bias.copy_(cu(g["b1"]))
+        model.decoder.fc2.weight.copy_(cu(g["w2"])); model.decoder.fc2.bias.copy_(cu(g["b2"]))
+        out = model(None, cu(g["adj_q"])).cpu().numpy()
+        model.finetune = False
+        van = model(None, cu(g["adj_q"])).cpu().numpy()
+    assert np.max(np.abs(out - g["logits"])) < 1e-5
+    assert np.max(np.abs(van - g["vanilla"])) < 1e-6
+
+
+def test_edge_forward_golden(golden):
+    g = golden("edge_forward")
+    w = cu(g["w"]) * 0.5 + cu(g["time_norm"]) * 0.5
+    out = R.edge_rag_forward(cu(g["X"]), cu(g["edges"]), w, cu(g["keys"]), cu(g["values"]), int(g["num_layers"]),
+                             int(g["retrieve_num"]), int(g["batch_size"]), float(g["retrieve_weight"])).cpu().numpy()
+    assert O.rel_err(out, g["out"]) < REL
+
+
+# ------------------------------------------------------------------------------------------ size-independent properties
+def test_large_properties():
+    """Sizes the CPU oracle cannot finish quickly: check invariants instead."""
+    torch.manual_seed(0)
+    N, d, Q, k = 1_000_000, 128, 512, 10
+    keys = torch.randn(N, d, device=DEV); q = torch.randn(Q, d, device=DEV)
+    s, i = ops.cosine_topk(q, keys, k)
+    assert (s[:, :-1] >= s[:, 1:]).all() and (i >= 0).all() and (i < N).all()
+    # scores recomputed exactly from the returned indices (fp64) agree, and beat a random sample of keys
+    kk = keys[i.reshape(-1)].double().reshape(Q, k, d)
+    ex = (torch.nn.functional.normalize(q.double(), dim=-1)[:, None] * torch.nn.functional.normalize(kk, dim=-1)).sum(-1)
+    assert (s.double() - ex).abs().max() < 1e-5
+    # retrieving from the union of two halves == merging the halves (the multi-GPU invariant)
+    s0, i0 = ops.cosine_topk(q, keys[: N // 2], k)
+    s1, i1 = ops.cosine_topk(q, keys[N // 2:], k, idx_offset=N // 2)
+    ms, mi = ops.topk_merge(torch.stack([s0, s1]), torch.stack([i0, i1]), k)
+    assert torch.equal(mi, i) and torch.equal(ms, s)
+    # gather: checksum of a permutation gather equals checksum of the table
+    perm = torch.randperm(N, device=DEV)
+    assert torch.equal(ops.gather_rows(keys, perm).view(torch.int32).sum(0), keys.view(torch.int32).sum(0))
+    # SpMM linearity and A.1 = rowsum on a random graph
+    n, nnz, F = 200_000, 4_000_000, 256
+    dst = torch.randint(0, n, (nnz,), device=DEV); src = torch.randint(0, n, (nnz,), device=DEV)
+    w = torch.rand(nnz, device=DEV)
+    gcsr = R.CSRGraph.from_coo(torch.stack([src, dst], 1), w, n, deterministic=True)
+    x, y = torch.randn(n, F, device=DEV), torch.randn(n, F, device=DEV)
+    lhs = gcsr.spmm(x + y); rhs = gcsr.spmm(x) + gcsr.spmm(y)
+    assert (lhs - rhs).abs().max() / rhs.abs().max() < 1e-5
+    ones = gcsr.spmm(torch.ones(n, F, device=DEV))[:, 0]
+    rowsum = torch.zeros(n, device=DEV, dtype=torch.float64).index_add_(0, dst, w.double())
+    assert (ones.double() - rowsum).abs().max() / rowsum.abs().max() < 1e-5
