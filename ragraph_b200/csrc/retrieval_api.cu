@@ -9,6 +9,7 @@ int topk_f32_run(const float* q, int64_t Q, const float* keys, const float* key_
                  cudaStream_t s);
 // topk_tc.cu (tcgen05 filter + fp32 refine)
 size_t topk_tc_workspace(int64_t Q, int64_t N, int d, int k, int mode);
+bool topk_tc_available();
 int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const uint16_t* keys_bf16,
                 int64_t N, int d, int k, int mode, uint32_t flags, int64_t idx_offset, float* out_scores,
                 int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s);
@@ -45,6 +46,12 @@ static int check_topk_args(const char* fn, const float* q, int64_t Q, const floa
   RAG_REQUIRE(q && keys && out_scores && out_idx, RAG_EINVAL, "%s: null pointer", fn);
   RAG_REQUIRE(rag::aligned16(q) && rag::aligned16(keys), RAG_EALIGN, "%s: q/keys must be 16-byte aligned", fn);
   return RAG_OK;
+}
+
+extern "C" int rag_sim_mode_supported(int32_t mode) {
+  if (mode == RAG_SIM_FP32) return 1;
+  if (mode == RAG_SIM_BF16 || mode == RAG_SIM_BF16_REFINE) return rag::topk_tc_available() ? 1 : 0;
+  return 0;
 }
 
 extern "C" size_t rag_cosine_topk_workspace(int64_t Q, int64_t N, int32_t d, int32_t k, int32_t mode) {

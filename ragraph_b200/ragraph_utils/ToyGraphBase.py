@@ -125,7 +125,8 @@ class ToyGraphBase:
         if self.mode is not None:
             return self.mode
         # tensor-core filter + fp32 refine pays off once the scan is large; both are exact-match
-        return L.SIM_BF16_REFINE if (self._n >= 65536 and self.emb_size % 64 == 0 and Q >= 16) else L.SIM_FP32
+        big = self._n >= 65536 and self.emb_size % 64 == 0 and Q >= 16
+        return L.SIM_BF16_REFINE if (big and L.load().rag_sim_mode_supported(L.SIM_BF16_REFINE)) else L.SIM_FP32
 
     def topk(self, search_keys: Tensor, k: int, search_positions: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         """(scores[Q,k], indices[Q,k] int64): torch.topk(cosine(search_keys, resource_keys), k) fused."""

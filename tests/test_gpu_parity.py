@@ -117,7 +117,9 @@ def test_cosine_topk_golden_and_ties(golden):
     # deterministic order: score desc, index asc (key 17 duplicates key 3)
     _, idx = ops.cosine_topk(cu(q), cu(keys), 100)
     idx = idx.cpu().numpy()
-    for row in idx:
+    for r, row in enumerate(idx):
+        if r == 5:
+            continue                              # zero query: every score ties, order is plain index order
         p3, p17 = np.where(row == 3)[0], np.where(row == 17)[0]
         if len(p3) and len(p17):
             assert p17[0] == p3[0] + 1
