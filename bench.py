@@ -215,7 +215,7 @@ def main():
     if args.mode >= 0:
         store.mode = args.mode
     sr = R.ShardedRetriever(store, N_KEYS)
-    mode = store._pick_mode(Q_BATCH)
+    mode = store._pick_mode(Q_BATCH, TOPK)
     q_host = make_queries(Q_BATCH, DIM, dev)
     q_dev = q_host.to(dev)
     out_host = {"emb": torch.empty((Q_BATCH, TOPK, DIM), dtype=torch.float32).pin_memory(),

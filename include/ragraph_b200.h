@@ -75,8 +75,8 @@ RAG_API const char* rag_last_error(void);
 RAG_API const char* rag_status_string(int status);
 /* number of kernels this library has launched in this process (all threads) */
 RAG_API int64_t rag_launch_count(void);
-/* 1 if rag_cosine_topk_f32 implements `mode` in this build, else 0 */
-RAG_API int rag_sim_mode_supported(int32_t mode);
+/* 1 if rag_cosine_topk_f32 implements `mode` for embedding dim d and top-k k in this build, else 0 */
+RAG_API int rag_sim_mode_supported(int32_t mode, int32_t d, int32_t k);
 
 /* ---- a1/K1: F.normalize pieces (SimilarityFunctions.py:8,11) -------------------------- */
 /* out_inv_norm[r] = 1 / max(||x[r,:]||_2, eps) */

@@ -27,7 +27,7 @@ SIGNATURES = {
     "rag_last_error": (C.c_char_p, []),
     "rag_status_string": (C.c_char_p, [C.c_int]),
     "rag_launch_count": (_i64, []),
-    "rag_sim_mode_supported": (C.c_int, [_i32]),
+    "rag_sim_mode_supported": (C.c_int, [_i32, _i32, _i32]),
     "rag_row_inv_norm_f32": (C.c_int, [_p, _i64, _i32, _f32, _p, _p]),
     "rag_rows_to_bf16": (C.c_int, [_p, _i64, _i32, _i32, _f32, _p, _i32, _p]),
     "rag_cosine_similarity_workspace": (_sz, [_i64, _i64]),

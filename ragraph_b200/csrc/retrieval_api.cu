@@ -9,7 +9,7 @@ int topk_f32_run(const float* q, int64_t Q, const float* keys, const float* key_
                  cudaStream_t s);
 // topk_tc.cu (tcgen05 filter + fp32 refine)
 size_t topk_tc_workspace(int64_t Q, int64_t N, int d, int k, int mode);
-bool topk_tc_available();
+bool topk_tc_available(int d, int k);
 int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const uint16_t* keys_bf16,
                 int64_t N, int d, int k, int mode, uint32_t flags, int64_t idx_offset, float* out_scores,
                 int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s);
@@ -48,9 +48,9 @@ static int check_topk_args(const char* fn, const float* q, int64_t Q, const floa
   return RAG_OK;
 }
 
-extern "C" int rag_sim_mode_supported(int32_t mode) {
-  if (mode == RAG_SIM_FP32) return 1;
-  if (mode == RAG_SIM_BF16 || mode == RAG_SIM_BF16_REFINE) return rag::topk_tc_available() ? 1 : 0;
+extern "C" int rag_sim_mode_supported(int32_t mode, int32_t d, int32_t k) {
+  if (mode == RAG_SIM_FP32) return (d >= 1 && k >= 1 && k <= RAG_MAX_K) ? 1 : 0;
+  if (mode == RAG_SIM_BF16 || mode == RAG_SIM_BF16_REFINE) return rag::topk_tc_available(d, k) ? 1 : 0;
   return 0;
 }
 

@@ -33,6 +33,8 @@ struct TopkArgs {
   int64_t idx_offset;
   float* out_scores; int64_t* out_idx;            // [n_splits, Q, k] (partials) or [Q, k]
   float* dense_out;                               // MATERIALIZE: [Q, N]
+  const int32_t* row_map;                         // optional: compact row r -> query row row_map[r]
+  const int32_t* n_rows_dev;                      // optional: device-side count of rows in row_map
 };
 
 template <bool MATERIALIZE>
@@ -54,14 +56,18 @@ __global__ void __launch_bounds__(TK_THREADS, 2) cosine_topk_f32_kernel(const To
   const int64_t key_lo = (int64_t)split * a.keys_per_split;
   const int64_t key_hi = min(key_lo + a.keys_per_split, a.N);
   const bool vec4 = (d & 3) == 0;
+  // restricted-row mode (rows the tensor-core certificate rejected): the row count lives on the device
+  const int64_t Qeff = a.n_rows_dev ? (int64_t)__ldg(a.n_rows_dev) : a.Q;
+  if (q0 >= Qeff) return;
 
   // ---- stage the normalised query block, transposed ------------------------------------
   for (int i = tid; i < dk * TK_BM; i += TK_THREADS) {
     const int r = i / dk, c = i - r * dk;                     // coalesced over c (query row)
     float v = 0.f;
-    if (q0 + r < a.Q && c < d) {
-      v = __ldg(a.q + (q0 + r) * d + c);
-      if (a.q_inv_norm) v *= __ldg(a.q_inv_norm + q0 + r);
+    if (q0 + r < Qeff && c < d) {
+      const int64_t qr = a.row_map ? (int64_t)__ldg(a.row_map + q0 + r) : q0 + r;
+      v = __ldg(a.q + qr * d + c);
+      if (a.q_inv_norm) v *= __ldg(a.q_inv_norm + qr);
     }
     Qs[(size_t)c * TK_BM + r] = v;
   }
@@ -206,8 +212,10 @@ __global__ void __launch_bounds__(TK_THREADS, 2) cosine_topk_f32_kernel(const To
   __syncthreads();
   for (int i = tid; i < TK_BM * k; i += TK_THREADS) {
     const int r = i / k, p = i - r * k;
-    if (q0 + r >= a.Q) continue;
-    const size_t o = ((size_t)split * a.Q + (q0 + r)) * k + p;
+    if (q0 + r >= Qeff) continue;
+    int64_t orow = q0 + r;
+    if (a.n_splits == 1 && a.row_map) orow = __ldg(a.row_map + q0 + r);   // direct write to the final row
+    const size_t o = ((size_t)split * a.Q + orow) * k + p;
     const float v = lvals[i];
     const int32_t li = lidx[i];
     a.out_scores[o] = v;
@@ -227,14 +235,17 @@ static size_t tk_smem_host(int d, int k, bool materialize) {
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ scores,
                                                          const int64_t* __restrict__ idx, int R, int64_t Q,
                                                          int k_in, int k_out, float* __restrict__ out_scores,
-                                                         int64_t* __restrict__ out_idx) {
+                                                         int64_t* __restrict__ out_idx,
+                                                         const int32_t* __restrict__ row_map,
+                                                         const int32_t* __restrict__ n_rows_dev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   int64_t* li = reinterpret_cast<int64_t*>(smem_raw) + (size_t)warp * k_out;
   float* lv = reinterpret_cast<float*>(reinterpret_cast<int64_t*>(smem_raw) + (size_t)wpb * k_out) +
               (size_t)warp * k_out;
-  for (int64_t q = (int64_t)blockIdx.x * wpb + warp; q < Q; q += (int64_t)gridDim.x * wpb) {
+  const int64_t Qeff = n_rows_dev ? (int64_t)__ldg(n_rows_dev) : Q;
+  for (int64_t q = (int64_t)blockIdx.x * wpb + warp; q < Qeff; q += (int64_t)gridDim.x * wpb) {
     for (int p = lane; p < k_out; p += 32) { lv[p] = -FLT_MAX; li[p] = INT64_MAX; }
     __syncwarp();
     const int total = R * k_in;
@@ -257,22 +268,25 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
           warp_sorted_insert<int64_t>(lv, li, k_out, sv, jv, lane);
       }
     }
+    const int64_t orow = row_map ? (int64_t)__ldg(row_map + q) : q;
     for (int p = lane; p < k_out; p += 32) {
-      out_scores[q * k_out + p] = lv[p];
-      out_idx[q * k_out + p] = (li[p] == INT64_MAX) ? (int64_t)-1 : li[p];
+      out_scores[orow * k_out + p] = lv[p];
+      out_idx[orow * k_out + p] = (li[p] == INT64_MAX) ? (int64_t)-1 : li[p];
     }
     __syncwarp();
   }
 }
 
 static int launch_merge(const float* scores, const int64_t* idx, int R, int64_t Q, int k_in, int k_out,
-                        float* out_scores, int64_t* out_idx, cudaStream_t s) {
+                        float* out_scores, int64_t* out_idx, cudaStream_t s, const int32_t* row_map = nullptr,
+                        const int32_t* n_rows_dev = nullptr) {
   const int wpb = 8;
   int64_t blocks = (Q + wpb - 1) / wpb;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   const size_t smem = (size_t)wpb * k_out * 12;
-  topk_merge_kernel<<<(unsigned)blocks, wpb * 32, smem, s>>>(scores, idx, R, Q, k_in, k_out, out_scores, out_idx);
+  topk_merge_kernel<<<(unsigned)blocks, wpb * 32, smem, s>>>(scores, idx, R, Q, k_in, k_out, out_scores, out_idx,
+                                                                row_map, n_rows_dev);
   RAG_LAUNCH_OK("topk_merge_kernel");
   return RAG_OK;
 }
@@ -307,6 +321,31 @@ static TkPlan tk_plan(int64_t Q, int64_t N, int d, int k, bool need_kinv) {
 
 size_t topk_f32_workspace(int64_t Q, int64_t N, int d, int k) { return tk_plan(Q, N, d, k, true).total; }
 
+static int topk_f32_core(const float* q, int64_t Q, const float* keys, const float* key_inv_norm,
+                         const float* q_inv_norm, int64_t N, int d, int k, int64_t idx_offset, const TkPlan& p,
+                         unsigned char* w, const int32_t* row_map, const int32_t* n_rows_dev, float* out_scores,
+                         int64_t* out_idx, cudaStream_t s) {
+  TopkArgs a{};
+  a.q = q; a.Q = Q; a.keys = keys; a.key_inv_norm = key_inv_norm; a.q_inv_norm = q_inv_norm;
+  a.N = N; a.d = d; a.k = k; a.keys_per_split = p.keys_per_split; a.n_splits = p.n_splits;
+  a.idx_offset = idx_offset; a.row_map = row_map; a.n_rows_dev = n_rows_dev;
+  const bool direct = p.n_splits == 1;
+  a.out_scores = direct ? out_scores : reinterpret_cast<float*>(w + p.off_ps);
+  a.out_idx = direct ? out_idx : reinterpret_cast<int64_t*>(w + p.off_pi);
+  const size_t smem = tk_smem_host(d, k, false);
+  RAG_REQUIRE(smem <= (size_t)max_smem_optin(), RAG_EUNSUPPORTED,
+              "cosine_topk(fp32): d=%d k=%d needs %zu bytes of shared memory (> %d)", d, k, smem, max_smem_optin());
+  cudaError_t e = cudaFuncSetAttribute(cosine_topk_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(cosine_topk_f32_kernel)");
+  dim3 grid((unsigned)((Q + TK_BM - 1) / TK_BM), (unsigned)p.n_splits);
+  cosine_topk_f32_kernel<false><<<grid, TK_THREADS, smem, s>>>(a);
+  RAG_LAUNCH_OK("cosine_topk_f32_kernel");
+  if (!direct)
+    return launch_merge(a.out_scores, a.out_idx, p.n_splits, Q, k, k, out_scores, out_idx, s, row_map, n_rows_dev);
+  return RAG_OK;
+}
+
 int topk_f32_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, int64_t N, int d, int k,
                  uint32_t flags, int64_t idx_offset, float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes,
                  cudaStream_t s) {
@@ -327,26 +366,21 @@ int topk_f32_run(const float* q, int64_t Q, const float* keys, const float* key_
       if (st) return st;
     }
   }
-  TopkArgs a{};
-  a.q = q; a.Q = Q; a.keys = keys;
-  a.key_inv_norm = dot ? nullptr : (need_kinv ? kinv : key_inv_norm);
-  a.q_inv_norm = dot ? nullptr : qinv;
-  a.N = N; a.d = d; a.k = k; a.keys_per_split = p.keys_per_split; a.n_splits = p.n_splits;
-  a.idx_offset = idx_offset;
-  const bool direct = p.n_splits == 1;
-  a.out_scores = direct ? out_scores : reinterpret_cast<float*>(w + p.off_ps);
-  a.out_idx = direct ? out_idx : reinterpret_cast<int64_t*>(w + p.off_pi);
-  const size_t smem = tk_smem_host(d, k, false);
-  RAG_REQUIRE(smem <= (size_t)max_smem_optin(), RAG_EUNSUPPORTED,
-              "cosine_topk(fp32): d=%d k=%d needs %zu bytes of shared memory (> %d)", d, k, smem, max_smem_optin());
-  cudaError_t e = cudaFuncSetAttribute(cosine_topk_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(cosine_topk_f32_kernel)");
-  dim3 grid((unsigned)((Q + TK_BM - 1) / TK_BM), (unsigned)p.n_splits);
-  cosine_topk_f32_kernel<false><<<grid, TK_THREADS, smem, s>>>(a);
-  RAG_LAUNCH_OK("cosine_topk_f32_kernel");
-  if (!direct) return launch_merge(a.out_scores, a.out_idx, p.n_splits, Q, k, k, out_scores, out_idx, s);
-  return RAG_OK;
+  return topk_f32_core(q, Q, keys, dot ? nullptr : (need_kinv ? kinv : key_inv_norm), dot ? nullptr : qinv, N, d, k,
+                       idx_offset, p, w, nullptr, nullptr, out_scores, out_idx, s);
+}
+
+// fp32 path over a device-side list of rows (the tensor-core refine's uncertified rows).  The grid covers the
+// worst case (all Q rows); CTAs beyond the device-side count exit at once.
+size_t topk_f32_rows_workspace(int64_t Q, int64_t N, int d, int k) { return tk_plan(Q, N, d, k, false).total; }
+
+int topk_f32_run_rows(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const float* q_inv_norm,
+                      int64_t N, int d, int k, int64_t idx_offset, const int32_t* row_map, const int32_t* n_rows_dev,
+                      float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
+  TkPlan p = tk_plan(Q, N, d, k, false);
+  RAG_REQUIRE(ws_bytes >= p.total, RAG_EWORKSPACE, "cosine_topk(rows): workspace %zu < %zu bytes", ws_bytes, p.total);
+  return topk_f32_core(q, Q, keys, key_inv_norm, q_inv_norm, N, d, k, idx_offset, p, static_cast<unsigned char*>(ws),
+                       row_map, n_rows_dev, out_scores, out_idx, s);
 }
 
 }  // namespace rag

@@ -1,10 +1,514 @@
-// placeholder until the tcgen05 filter lands (next commit)
+// K1+K2+K3 on the 5th-gen tensor cores: bf16 similarity filter (tcgen05.mma, accumulators in TMEM,
+// operands staged by TMA) with a fused per-row top-k' selection, followed by an exact fp32 re-score of
+// the surviving candidates with a correctness certificate (RAG_SIM_BF16_REFINE), or by a plain merge of
+// the approximate scores (RAG_SIM_BF16).
+//
+// Replaces SimilarityFunctions.calculate_cosine_similarity + torch.topk for large libraries
+// (RAGraph_node/ragraph_utils/SimilarityFunctions.py:6-16, ToyGraphBase.py:53,67;
+//  RAGraph_edge/modules/RAGraph.py:298-311).
+//
+// Filter kernel (one CTA per (query tile, key split); 10 warps, 1 CTA/SM):
+//   * a CTA owns 256 query rows (two 128-row blocks) whose normalised bf16 image stays in shared memory
+//     for the whole kernel (TMA, SWIZZLE_128B, K-major);
+//   * warp 8 (one elected lane) streams the split's keys, 128 keys x 64 K (16 KB) per pipeline stage;
+//   * warp 9 (one elected lane) issues tcgen05.mma.cta_group::1.kind::f16 M=128 N=128 K=16 into one of two
+//     TMEM accumulator buffers (2 row blocks x 128 columns each -> all 512 columns), tcgen05.commit frees
+//     smem stages and publishes finished accumulators through mbarriers;
+//   * warps 0-7 drain the other buffer: tcgen05.ld 32x32b.x32 gives each thread 32 scores of ITS query
+//     row; a 3-input-max tree compares them with the row's running k'-th best held in a register, and only
+//     on a hit does the thread insert into its row's sorted list in shared memory.  Scores never reach HBM.
+//   CTAs that share a key split run side by side (blockIdx = split * q_tiles + q_tile), so a key tile is
+//   fetched from HBM once and served to the other query tiles from L2.
+//
+// Exactness (mode 3): for unit vectors |s_bf16 - s| <= EPS (2 roundings of 2^-9 each, Cauchy-Schwarz).
+// Every key NOT in a split's list has s_bf16 <= t_split (the list's last score), hence s <= t_split + EPS.
+// The refine kernel re-scores all S*k' candidates in fp32, keeps the best k (score desc, index asc) and
+// certifies the row iff its k-th exact score > max_split t_split + EPS.  Uncertified rows (ties or dense
+// clusters at the boundary) are recomputed by the fp32 kernel, so results always equal RAG_SIM_FP32.
+#include <cuda.h>
+#include <cfloat>
+#include <cuda_bf16.h>
 #include "common.cuh"
+
 namespace rag {
-bool topk_tc_available() { return false; }
-size_t topk_tc_workspace(int64_t, int64_t, int, int, int) { return 256; }
-int topk_tc_run(const float*, int64_t, const float*, const float*, const uint16_t*, int64_t, int, int, int mode,
-                uint32_t, int64_t, float*, int64_t*, void*, size_t, cudaStream_t) {
-  return fail(RAG_EUNSUPPORTED, "cosine_topk: mode %d not built yet", mode);
+
+// topk_f32.cu: fp32 path restricted to a device-side list of rows
+int topk_f32_run_rows(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const float* q_inv_norm,
+                      int64_t N, int d, int k, int64_t idx_offset, const int32_t* row_map, const int32_t* n_rows_dev,
+                      float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t topk_f32_rows_workspace(int64_t Q, int64_t N, int d, int k);
+
+constexpr int TC_ROWS = 256;          // query rows per CTA (2 row blocks of 128)
+constexpr int TC_BN = 128;            // keys per tile
+constexpr int TC_BOX_BYTES = 128 * 128;   // one TMA box: 128 rows x 64 bf16
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+constexpr float TC_EPS = 0.00390625f + 0.0009765625f;   // 2^-8 (bf16 x bf16, unit vectors) + 2^-10 slack (fp32 sums)
+constexpr unsigned long long TC_TIMEOUT_CYCLES = 20000000000ull;   // ~10 s: trap instead of hanging the GPU
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  const unsigned long long t0 = clock64();
+  while (true) {
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) break;
+    if (clock64() - t0 > TC_TIMEOUT_CYCLES) __trap();     // a broken pipeline must fail loudly, not hang
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (8-row x 128-byte atoms, SBO = 1024 B, LBO unused,
+// descriptor version 1, layout type 2); `addr` is the 1024-aligned box base (+32 B per K=16 step).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
+  const uint32_t lo = (addr >> 4) & 0x3FFFu;
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((128u >> 4) << 24);
+
+// sorted insert into this thread's row list (entry p at ls[p*256]); score desc, and because keys arrive in
+// ascending index order a tie keeps the lower index first.  Returns the new k'-th best (threshold).
+template <int KP>
+__device__ __noinline__ float tc_list_insert(float* ls, int32_t* li, float s, int32_t idx) {
+  int p = KP - 1;
+  while (p > 0 && ls[(p - 1) * TC_ROWS] < s) {
+    ls[p * TC_ROWS] = ls[(p - 1) * TC_ROWS];
+    li[p * TC_ROWS] = li[(p - 1) * TC_ROWS];
+    --p;
+  }
+  ls[p * TC_ROWS] = s;
+  li[p * TC_ROWS] = idx;
+  return ls[(KP - 1) * TC_ROWS];
+}
+
+struct TcArgs {
+  int64_t Q; int64_t N;            // rows in use
+  int n_qtiles; int n_splits; int tiles_per_split; int n_tiles;
+  int kp;                          // list length per (row, split)
+  float* part_s; int32_t* part_i;  // [n_splits][Q][kp]
+};
+
+struct __align__(8) TcBarriers {
+  uint64_t a_full;
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+// KH = K halves of 64 (d_pad = 64*KH); NSTAGE = pipeline depth in 16 KB boxes; KP = list length
+template <int KH, int NSTAGE, int KP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                      const TcArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  // carve: [A: 2*KH boxes][B: NSTAGE boxes][lists: KP x 256 x (f32 + i32)][barriers]
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = base;
+  unsigned char* sB = sA + 2 * KH * TC_BOX_BYTES;
+  float* list_s = reinterpret_cast<float*>(sB + NSTAGE * TC_BOX_BYTES);    // [KP][256]
+  int32_t* list_i = reinterpret_cast<int32_t*>(list_s + KP * TC_ROWS);     // [KP][256]
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(list_i + KP * TC_ROWS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qtile = blockIdx.x % a.n_qtiles;
+  const int split = blockIdx.x / a.n_qtiles;
+  const int tile0 = split * a.tiles_per_split;
+  const int tile1 = min(tile0 + a.tiles_per_split, a.n_tiles);
+  const int n_my_tiles = max(tile1 - tile0, 0);
+
+  // ---- one-time setup ---------------------------------------------------------------------------
+  if (warp == TC_EPI_WARPS && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
+    mbar_init(&bars->a_full, 1);
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], TC_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == TC_EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < KP * TC_ROWS; i += TC_THREADS) { list_s[i] = -INFINITY; list_i[i] = -1; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == TC_EPI_WARPS) {
+    // =============================== TMA producer ===============================================
+    if (elect_one()) {
+      mbar_expect_tx(&bars->a_full, 2 * KH * TC_BOX_BYTES);
+      for (int rb = 0; rb < 2; ++rb)
+        for (int kh = 0; kh < KH; ++kh)
+          tma_load_2d(sA + (rb * KH + kh) * TC_BOX_BYTES, &map_q, kh * 64, qtile * TC_ROWS + rb * 128, &bars->a_full);
+      int s = 0; uint32_t ph = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+        for (int kh = 0; kh < KH; ++kh) {
+          mbar_wait(&bars->empty[s], ph ^ 1);
+          mbar_expect_tx(&bars->full[s], TC_BOX_BYTES);
+          tma_load_2d(sB + s * TC_BOX_BYTES, &map_k, kh * 64, (tile0 + t) * TC_BN, &bars->full[s]);
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == TC_EPI_WARPS + 1) {
+    // =============================== MMA issuer =================================================
+    if (elect_one()) {
+      mbar_wait(&bars->a_full, 0);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+      int s = 0; uint32_t ph = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+        const int b = t & 1;
+        mbar_wait(&bars->tmem_empty[b], (((uint32_t)t >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        for (int kh = 0; kh < KH; ++kh) {
+          mbar_wait(&bars->full[s], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int rb = 0; rb < 2; ++rb) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t da = umma_desc(a_addr + (rb * KH + kh) * TC_BOX_BYTES + k4 * 32);
+              const uint64_t db = umma_desc(b_addr + s * TC_BOX_BYTES + k4 * 32);
+              tc_mma_bf16(tmem_base + (uint32_t)((b * 2 + rb) * TC_BN), da, db, TC_IDESC, (kh | k4) != 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(&bars->empty[s]);                       // smem stage reusable once these MMAs retire
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+        }
+        tc_commit(&bars->tmem_full[b]);                     // accumulators of tile t complete
+      }
+    }
+  } else {
+    // =============================== epilogue: fused top-k' =====================================
+    const int quarter = warp & 3, rb = warp >> 2;
+    const int row = rb * 128 + quarter * 32 + lane;         // this thread's query row inside the CTA tile
+    float* my_s = list_s + row;                             // entry p at my_s[p * 256] (conflict free)
+    int32_t* my_i = list_i + row;
+    float thr = -INFINITY;
+    const int64_t key_base = (int64_t)tile0 * TC_BN;
+    for (int t = 0; t < n_my_tiles; ++t) {
+      const int b = t & 1;
+      mbar_wait(&bars->tmem_full[b], ((uint32_t)t >> 1) & 1u);
+      tc_fence_after();
+      const int64_t tile_key0 = key_base + (int64_t)t * TC_BN;
+      const int n_valid = (int)min((int64_t)TC_BN, a.N - tile_key0);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((b * 2 + rb) * TC_BN);
+#pragma unroll 1
+      for (int c = 0; c < TC_BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        float m = max3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+#pragma unroll
+        for (int j = 3; j < 31; j += 2) m = max3(m, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+        m = fmaxf(m, __uint_as_float(v[31]));
+        if (m > thr) {                                      // rare once the list has warmed up
+          const int col0 = c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float s = __uint_as_float(v[j]);
+            if (s > thr && col0 + j < n_valid)
+              thr = tc_list_insert<KP>(my_s, my_i, s, (int32_t)(tile_key0 + col0 + j));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[b]);
+    }
+    // ---- publish this split's list --------------------------------------------------------------
+    const int64_t grow = (int64_t)qtile * TC_ROWS + row;
+    if (grow < a.Q) {
+      float* ps = a.part_s + ((int64_t)split * a.Q + grow) * KP;
+      int32_t* pi = a.part_i + ((int64_t)split * a.Q + grow) * KP;
+#pragma unroll
+      for (int p = 0; p < KP; ++p) { ps[p] = my_s[p * TC_ROWS]; pi[p] = my_i[p * TC_ROWS]; }
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_EPI_WARPS + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- refine: exact fp32 re-score of the candidates + certificate ------------------------------------
+struct RefineArgs {
+  const float* q; const float* keys; const float* q_inv_norm; const float* key_inv_norm;
+  int64_t Q; int64_t N; int d; int k; int kp; int n_splits;
+  const float* part_s; const int32_t* part_i;
+  int exact;                         // 1: fp32 re-score + certificate, 0: keep bf16 scores (RAG_SIM_BF16)
+  int64_t idx_offset;
+  float* out_scores; int64_t* out_idx;
+  int32_t* fb_rows; int32_t* fb_count;   // uncertified rows (exact only)
+};
+
+__global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  int64_t* li = reinterpret_cast<int64_t*>(smem_raw) + (size_t)warp * a.k;
+  float* lv = reinterpret_cast<float*>(reinterpret_cast<int64_t*>(smem_raw) + (size_t)wpb * a.k) + (size_t)warp * a.k;
+  const int total = a.n_splits * a.kp;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < a.Q; row += (int64_t)gridDim.x * wpb) {
+    for (int p = lane; p < a.k; p += 32) { lv[p] = -FLT_MAX; li[p] = INT64_MAX; }
+    __syncwarp();
+    const float* qr = a.q + row * a.d;
+    const float qinv = a.q_inv_norm ? __ldg(a.q_inv_norm + row) : 1.0f;
+    float tmax = -INFINITY;                                  // max over splits of the list's last bf16 score
+    for (int c0 = 0; c0 < total; c0 += 4) {
+      float sc[4]; int64_t id[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u;
+        sc[u] = -FLT_MAX; id[u] = -1;
+        if (c < total) {
+          const int sp = c / a.kp, p = c - sp * a.kp;
+          const size_t o = ((size_t)sp * a.Q + row) * a.kp + p;
+          const int32_t j = __ldg(a.part_i + o);
+          const float approx = __ldg(a.part_s + o);
+          if (p == a.kp - 1 && j >= 0) tmax = fmaxf(tmax, approx);
+          if (j >= 0) {
+            id[u] = j;
+            if (a.exact) {
+              const float* kr = a.keys + (int64_t)j * a.d;
+              float dot = 0.f;
+              for (int e = lane; e < a.d; e += 32) dot = fmaf(__ldg(qr + e) * qinv, __ldg(kr + e), dot);
+              dot = warp_sum(dot);
+              sc[u] = dot * (a.key_inv_norm ? __ldg(a.key_inv_norm + j) : 1.0f);
+            } else {
+              sc[u] = approx;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (id[u] >= 0 && ranks_before(sc[u], id[u], lv[a.k - 1], li[a.k - 1]))
+          warp_sorted_insert<int64_t>(lv, li, a.k, sc[u], id[u], lane);
+    }
+    const float kth = lv[a.k - 1];
+    const bool certified = !a.exact || (li[a.k - 1] != INT64_MAX && kth > tmax + TC_EPS);
+    for (int p = lane; p < a.k; p += 32) {
+      a.out_scores[row * a.k + p] = lv[p];
+      a.out_idx[row * a.k + p] = (li[p] == INT64_MAX) ? (int64_t)-1 : li[p] + a.idx_offset;
+    }
+    if (!certified && lane == 0) a.fb_rows[atomicAdd(a.fb_count, 1)] = (int32_t)row;
+    __syncwarp();
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<PFN_encodeTiled>(p);
+  }();
+  return fn;
+}
+
+static int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int d_pad, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  RAG_REQUIRE(enc, RAG_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RAG_REQUIRE(r == CUDA_SUCCESS, RAG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return RAG_OK;
+}
+
+struct TcPlan {
+  int kh, kp, nstage, n_qtiles, n_splits, tiles_per_split, n_tiles, d_pad;
+  size_t smem;
+  size_t off_qbf, off_qinv, off_ps, off_pi, off_fb, off_fbn, off_f32, total;
+};
+
+bool tc_shape_ok(int d, int k) {
+  if (d < 1 || k < 1) return false;
+  if (d <= 128) return k <= 26;
+  if (d > 192 && d <= 256) return k <= 10;        // 128 KB of resident queries leave room for 16-entry lists only
+  return false;
+}
+
+static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k) {
+  TcPlan p{};
+  p.d_pad = (d + 63) / 64 * 64;
+  p.kh = p.d_pad / 64;                       // 1, 2, 3 (-> 4) or 4
+  if (p.kh == 3) p.kh = 4;                   // kernel instantiations: 1, 2, 4 (a zero K half costs nothing but time)
+  p.kp = (k <= 10) ? 16 : 32;
+  // shared memory: A 2*KH boxes + NSTAGE boxes + lists + barriers + 1 KB alignment slack  <= 227 KB
+  const int list_bytes = p.kp * TC_ROWS * 8;
+  const int budget = 232448 - 1024 - 256 - list_bytes - 2 * p.kh * TC_BOX_BYTES;
+  p.nstage = budget / TC_BOX_BYTES;
+  if (p.nstage > 8) p.nstage = 8;
+  p.nstage = (p.nstage >= 8) ? 8 : (p.nstage >= 6 ? 6 : 4);
+  p.smem = 1024 + (size_t)(2 * p.kh + p.nstage) * TC_BOX_BYTES + list_bytes + 256;
+  p.n_qtiles = (int)((Q + TC_ROWS - 1) / TC_ROWS);
+  p.n_tiles = (int)((N + TC_BN - 1) / TC_BN);
+  int s = sm_count() / p.n_qtiles;
+  if (s < 1) s = 1;
+  if (s > p.n_tiles) s = p.n_tiles;
+  p.tiles_per_split = (p.n_tiles + s - 1) / s;
+  p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  size_t off = 0;
+  p.off_qbf = off; off += align_up((size_t)p.n_qtiles * TC_ROWS * p.d_pad * 2, 256);
+  p.off_qinv = off; off += align_up((size_t)Q * 4, 256);
+  p.off_ps = off; off += align_up((size_t)p.n_splits * Q * p.kp * 4, 256);
+  p.off_pi = off; off += align_up((size_t)p.n_splits * Q * p.kp * 4, 256);
+  p.off_fb = off; off += align_up((size_t)Q * 4, 256);
+  p.off_fbn = off; off += 256;
+  p.off_f32 = off; off += topk_f32_rows_workspace(Q, N, d, k);
+  p.total = off;
+  return p;
+}
+
+bool topk_tc_available(int d, int k) { return tc_shape_ok(d, k); }
+
+size_t topk_tc_workspace(int64_t Q, int64_t N, int d, int k, int mode) {
+  if (!tc_shape_ok(d, k)) return 256;
+  return tc_plan(Q, N, d, k).total;
+}
+
+template <int KH, int NSTAGE, int KP>
+static int launch_filter(const CUtensorMap& mq, const CUtensorMap& mk, const TcArgs& a, const TcPlan& p, cudaStream_t s) {
+  auto kern = cosine_topk_tc_kernel<KH, NSTAGE, KP>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(cosine_topk_tc_kernel)");
+  kern<<<(unsigned)(p.n_qtiles * p.n_splits), TC_THREADS, p.smem, s>>>(mq, mk, a);
+  RAG_LAUNCH_OK("cosine_topk_tc_kernel");
+  return RAG_OK;
+}
+
+int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const uint16_t* keys_bf16,
+                int64_t N, int d, int k, int mode, uint32_t flags, int64_t idx_offset, float* out_scores,
+                int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
+  RAG_REQUIRE(!(flags & RAG_SIM_DOT), RAG_EUNSUPPORTED, "cosine_topk: the tensor-core modes implement cosine only");
+  RAG_REQUIRE(tc_shape_ok(d, k), RAG_EUNSUPPORTED,
+              "cosine_topk: tensor-core modes cover d <= 128 with k <= 26 and 192 < d <= 256 with k <= 10 (d=%d k=%d)", d, k);
+  RAG_REQUIRE(key_inv_norm, RAG_EINVAL, "cosine_topk: the tensor-core modes need key_inv_norm (rag_row_inv_norm_f32)");
+  RAG_REQUIRE(aligned16(keys_bf16), RAG_EALIGN, "cosine_topk: keys_bf16 must be 16-byte aligned");
+  TcPlan p = tc_plan(Q, N, d, k);
+  RAG_REQUIRE(ws_bytes >= p.total, RAG_EWORKSPACE, "cosine_topk: workspace %zu < %zu bytes", ws_bytes, p.total);
+  RAG_REQUIRE(ws && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, RAG_EALIGN, "cosine_topk: workspace must be 256-byte aligned");
+  RAG_REQUIRE(p.smem <= (size_t)max_smem_optin(), RAG_EUNSUPPORTED, "cosine_topk: needs %zu bytes of shared memory", p.smem);
+  unsigned char* w = static_cast<unsigned char*>(ws);
+  uint16_t* q_bf = reinterpret_cast<uint16_t*>(w + p.off_qbf);
+  float* qinv = reinterpret_cast<float*>(w + p.off_qinv);
+  const int d_pad_keys = (d + 63) / 64 * 64;        // layout of the caller's shadow
+  RAG_REQUIRE(p.d_pad == d_pad_keys, RAG_EUNSUPPORTED, "internal: d_pad mismatch");
+
+  int st = rag_rows_to_bf16(q, Q, d, 1, 1e-12f, q_bf, p.d_pad, s);
+  if (st) return st;
+  st = rag_row_inv_norm_f32(q, Q, d, 1e-12f, qinv, s);
+  if (st) return st;
+  cudaError_t e = cudaMemsetAsync(w + p.off_fbn, 0, 4, s);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(fb_count)");
+
+  CUtensorMap mq, mk;
+  st = make_map_bf16(&mq, q_bf, Q, p.d_pad, 128);
+  if (st) return st;
+  st = make_map_bf16(&mk, keys_bf16, N, p.d_pad, TC_BN);
+  if (st) return st;
+
+  TcArgs a{};
+  a.Q = Q; a.N = N; a.n_qtiles = p.n_qtiles; a.n_splits = p.n_splits; a.tiles_per_split = p.tiles_per_split;
+  a.n_tiles = p.n_tiles; a.kp = p.kp;
+  a.part_s = reinterpret_cast<float*>(w + p.off_ps);
+  a.part_i = reinterpret_cast<int32_t*>(w + p.off_pi);
+  const int kh_real = p.d_pad / 64;
+  if (kh_real == 3) return fail(RAG_EUNSUPPORTED, "cosine_topk: d in (128,192] is not instantiated on the tensor-core path");
+#define RAG_TC_CASE(KH_, NS_, KP_) \
+  if (p.kh == KH_ && p.nstage == NS_ && p.kp == KP_) st = launch_filter<KH_, NS_, KP_>(mq, mk, a, p, s); else
+  RAG_TC_CASE(1, 8, 16) RAG_TC_CASE(1, 8, 32) RAG_TC_CASE(2, 8, 16) RAG_TC_CASE(2, 6, 32)
+  RAG_TC_CASE(4, 4, 16) RAG_TC_CASE(4, 4, 32)
+  return fail(RAG_EUNSUPPORTED, "cosine_topk: no tensor-core instantiation for kh=%d nstage=%d kp=%d", p.kh, p.nstage, p.kp);
+#undef RAG_TC_CASE
+  if (st) return st;
+
+  RefineArgs r{};
+  r.q = q; r.keys = keys; r.q_inv_norm = qinv; r.key_inv_norm = key_inv_norm;
+  r.Q = Q; r.N = N; r.d = d; r.k = k; r.kp = p.kp; r.n_splits = p.n_splits;
+  r.part_s = a.part_s; r.part_i = a.part_i; r.exact = (mode == RAG_SIM_BF16_REFINE) ? 1 : 0;
+  r.idx_offset = idx_offset; r.out_scores = out_scores; r.out_idx = out_idx;
+  r.fb_rows = reinterpret_cast<int32_t*>(w + p.off_fb);
+  r.fb_count = reinterpret_cast<int32_t*>(w + p.off_fbn);
+  const int wpb = 8;
+  int64_t blocks = (Q + wpb - 1) / wpb;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  refine_kernel<<<(unsigned)blocks, wpb * 32, (size_t)wpb * k * 12, s>>>(r);
+  RAG_LAUNCH_OK("refine_kernel");
+  if (mode != RAG_SIM_BF16_REFINE) return RAG_OK;
+  // rows whose certificate failed are recomputed in fp32 (device-side row list; usually empty)
+  return topk_f32_run_rows(q, Q, keys, key_inv_norm, qinv, N, d, k, idx_offset, r.fb_rows, r.fb_count, out_scores,
+                           out_idx, w + p.off_f32, ws_bytes - p.off_f32, s);
+}
+
 }  // namespace rag

@@ -121,12 +121,14 @@ class ToyGraphBase:
         print("label count distribution", torch.sum(self.resource_labels, dim=0))
 
     # ---- retrieval ------------------------------------------------------------------------
-    def _pick_mode(self, Q: int) -> int:
+    def _pick_mode(self, Q: int, k: Optional[int] = None) -> int:
         if self.mode is not None:
             return self.mode
         # tensor-core filter + fp32 refine pays off once the scan is large; both are exact-match
-        big = self._n >= 65536 and self.emb_size % 64 == 0 and Q >= 16
-        return L.SIM_BF16_REFINE if (big and L.load().rag_sim_mode_supported(L.SIM_BF16_REFINE)) else L.SIM_FP32
+        k = self.retrieve_num if k is None else k
+        big = self._n >= 65536 and Q >= 16
+        ok = big and L.load().rag_sim_mode_supported(L.SIM_BF16_REFINE, self.emb_size, k)
+        return L.SIM_BF16_REFINE if ok else L.SIM_FP32
 
     def topk(self, search_keys: Tensor, k: int, search_positions: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         """(scores[Q,k], indices[Q,k] int64): torch.topk(cosine(search_keys, resource_keys), k) fused."""
@@ -135,7 +137,7 @@ class ToyGraphBase:
                 raise RuntimeError("node_fewshot retrieval needs search_positions (position-aware codes)")
             return ops.cosine2_topk(search_positions, self.resource_positions, self.structure_weight,
                                     search_keys, self.resource_keys, self.semantic_weight, k)
-        mode = self._pick_mode(search_keys.shape[0])
+        mode = self._pick_mode(search_keys.shape[0], k)
         self._refresh_derived(mode != L.SIM_FP32)
         return ops.cosine_topk(search_keys, self.resource_keys, k, self._inv_norm[:self._n],
                                self._keys_bf16 if mode != L.SIM_FP32 else None, mode)
