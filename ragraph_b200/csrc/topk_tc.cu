@@ -27,6 +27,7 @@
 // clusters at the boundary) are recomputed by the fp32 kernel, so results always equal RAG_SIM_FP32.
 #include <cuda.h>
 #include <cfloat>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -45,6 +46,9 @@ constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
 constexpr float TC_EPS = 0.00390625f + 0.0009765625f;   // 2^-8 (bf16 x bf16, unit vectors) + 2^-10 slack (fp32 sums)
 constexpr unsigned long long TC_TIMEOUT_CYCLES = 20000000000ull;   // ~10 s: trap instead of hanging the GPU
+
+// profiling trace (RAG_TC_DEBUG=3): CTA 0 stamps clock64 at pipeline events of its first 512 tiles
+__device__ unsigned long long g_tc_trace[4 * 512];
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,6 +103,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait for the outstanding tcgen05.ld and tie the destination registers to the wait, so that no consumer of
+// v[] can be scheduled above it when another chunk's load is issued in between (software pipelining)
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :: "memory");
+}
+// v[j] for a per-lane dynamic j: 31 selects (registers cannot be indexed dynamically)
+__device__ __forceinline__ float select32(const uint32_t (&v)[32], int j) {
+  uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+  return __uint_as_float((j & 16) ? d[1] : d[0]);
+}
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -115,19 +142,34 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
 // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((128u >> 4) << 24);
 
-// sorted insert into this thread's row list (entry p at ls[p*256]); score desc, and because keys arrive in
-// ascending index order a tie keeps the lower index first.  Returns the new k'-th best (threshold).
+// Candidate list of one (query row, key split): KP unsorted (score, index) slots in shared memory, entry p of
+// row r at ls[p*256 + r] (conflict free across a warp), plus meta[r] = slots in use | (position of the
+// current minimum << 8).  A new candidate (s > threshold) fills a free slot or overwrites the minimum, then
+// the minimum is found again (KP independent LDS, no dependent shifting).  Returns the new threshold: the
+// list minimum once all KP slots are in use, -inf before.  Ties at the minimum evict the larger index.
 template <int KP>
-__device__ __noinline__ float tc_list_insert(float* ls, int32_t* li, float s, int32_t idx) {
-  int p = KP - 1;
-  while (p > 0 && ls[(p - 1) * TC_ROWS] < s) {
-    ls[p * TC_ROWS] = ls[(p - 1) * TC_ROWS];
-    li[p * TC_ROWS] = li[(p - 1) * TC_ROWS];
-    --p;
+__device__ __forceinline__ float tc_list_push(float* ls, int32_t* li, int32_t* meta, float s, int32_t idx) {
+  const int m = *meta;
+  int cnt = m & 0xff;
+  const int pos = (cnt < KP) ? cnt : (m >> 8);
+  ls[pos * TC_ROWS] = s;
+  li[pos * TC_ROWS] = idx;
+  if (cnt < KP) {
+    ++cnt;
+    if (cnt < KP) { *meta = cnt; return -INFINITY; }
   }
-  ls[p * TC_ROWS] = s;
-  li[p * TC_ROWS] = idx;
-  return ls[(KP - 1) * TC_ROWS];
+  float best = ls[0];
+  int32_t besti = li[0];
+  int bpos = 0;
+#pragma unroll
+  for (int p = 1; p < KP; ++p) {
+    const float v = ls[p * TC_ROWS];
+    const int32_t vi = li[p * TC_ROWS];
+    const bool worse = (v < best) || (v == best && vi > besti);
+    best = worse ? v : best; besti = worse ? vi : besti; bpos = worse ? p : bpos;
+  }
+  *meta = KP | (bpos << 8);
+  return best;
 }
 
 struct TcArgs {
@@ -135,6 +177,7 @@ struct TcArgs {
   int n_qtiles; int n_splits; int tiles_per_split; int n_tiles;
   int kp;                          // list length per (row, split)
   float* part_s; int32_t* part_i;  // [n_splits][Q][kp]
+  int debug;                       // RAG_TC_DEBUG (profiling experiments only): 1 = epilogue skips TMEM reads, 2 = reads but skips the filter
 };
 
 struct __align__(8) TcBarriers {
@@ -158,7 +201,8 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   unsigned char* sB = sA + 2 * KH * TC_BOX_BYTES;
   float* list_s = reinterpret_cast<float*>(sB + NSTAGE * TC_BOX_BYTES);    // [KP][256]
   int32_t* list_i = reinterpret_cast<int32_t*>(list_s + KP * TC_ROWS);     // [KP][256]
-  TcBarriers* bars = reinterpret_cast<TcBarriers*>(list_i + KP * TC_ROWS);
+  int32_t* list_meta = list_i + KP * TC_ROWS;                              // [256]
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(list_meta + TC_ROWS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qtile = blockIdx.x % a.n_qtiles;
@@ -181,6 +225,7 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < KP * TC_ROWS; i += TC_THREADS) { list_s[i] = -INFINITY; list_i[i] = -1; }
+  for (int i = threadIdx.x; i < TC_ROWS; i += TC_THREADS) list_meta[i] = 0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -214,6 +259,7 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const int b = t & 1;
         mbar_wait(&bars->tmem_empty[b], (((uint32_t)t >> 1) & 1u) ^ 1u);
         tc_fence_after();
+        if (a.debug == 3 && blockIdx.x == 0 && t < 512) g_tc_trace[4 * t + 0] = clock64();
         for (int kh = 0; kh < KH; ++kh) {
           mbar_wait(&bars->full[s], ph);
           tc_fence_after();
@@ -230,6 +276,7 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
         tc_commit(&bars->tmem_full[b]);                     // accumulators of tile t complete
+        if (a.debug == 3 && blockIdx.x == 0 && t < 512) g_tc_trace[4 * t + 1] = clock64();
       }
     }
   } else {
@@ -238,37 +285,66 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const int row = rb * 128 + quarter * 32 + lane;         // this thread's query row inside the CTA tile
     float* my_s = list_s + row;                             // entry p at my_s[p * 256] (conflict free)
     int32_t* my_i = list_i + row;
+    int32_t* my_meta = list_meta + row;
     float thr = -INFINITY;
     const int64_t key_base = (int64_t)tile0 * TC_BN;
     for (int t = 0; t < n_my_tiles; ++t) {
       const int b = t & 1;
       mbar_wait(&bars->tmem_full[b], ((uint32_t)t >> 1) & 1u);
       tc_fence_after();
+      if (a.debug == 3 && blockIdx.x == 0 && t < 512 && threadIdx.x == 0) g_tc_trace[4 * t + 2] = clock64();
       const int64_t tile_key0 = key_base + (int64_t)t * TC_BN;
       const int n_valid = (int)min((int64_t)TC_BN, a.N - tile_key0);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((b * 2 + rb) * TC_BN);
-#pragma unroll 1
-      for (int c = 0; c < TC_BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld_wait();
-        float m = max3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+      // one 32-column chunk: max tree vs the row threshold; on a hit, per-lane candidate mask -> push loop
+      auto process = [&](const uint32_t (&v)[32], int col0) {
+        float m1[11];
 #pragma unroll
-        for (int j = 3; j < 31; j += 2) m = max3(m, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-        m = fmaxf(m, __uint_as_float(v[31]));
+        for (int j = 0; j < 10; ++j)
+          m1[j] = max3(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
+        m1[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+        const float m2a = max3(m1[0], m1[1], m1[2]), m2b = max3(m1[3], m1[4], m1[5]);
+        const float m2c = max3(m1[6], m1[7], m1[8]), m2d = fmaxf(m1[9], m1[10]);
+        const float m = fmaxf(max3(m2a, m2b, m2c), m2d);
         if (m > thr) {                                      // rare once the list has warmed up
-          const int col0 = c * 32;
+          uint32_t mask = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float s = __uint_as_float(v[j]);
-            if (s > thr && col0 + j < n_valid)
-              thr = tc_list_insert<KP>(my_s, my_i, s, (int32_t)(tile_key0 + col0 + j));
+          for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
+          const int room = n_valid - col0;                  // columns >= n_valid are TMA zero fill past the library end
+          if (room < 32) mask &= (room <= 0) ? 0u : ((1u << room) - 1u);
+          while (mask) {                                    // each lane walks ITS OWN candidates
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float sc = select32(v, j);
+            if (sc > thr) thr = tc_list_push<KP>(my_s, my_i, my_meta, sc, (int32_t)(tile_key0 + col0 + j));
           }
         }
+      };
+      uint32_t va[32], vb[32];
+      const bool filter = (a.debug == 0 || a.debug == 3);
+      if (a.debug == 1) {
+      } else if (a.debug == 2) {
+        for (int c = 0; c < TC_BN / 32; ++c) { tmem_ld32(taddr + c * 32, va); tmem_ld_wait(); if (__uint_as_float(va[5]) == 123.456f) thr = 1.f; }
+      } else {
+        // software pipeline: the load of chunk c+1 is in flight while chunk c is filtered
+        tmem_ld32(taddr, va);
+        tmem_ld_wait_regs(va);
+        tmem_ld32(taddr + 32, vb);
+        process(va, 0);
+        tmem_ld_wait_regs(vb);
+        tmem_ld32(taddr + 64, va);
+        process(vb, 32);
+        tmem_ld_wait_regs(va);
+        tmem_ld32(taddr + 96, vb);
+        process(va, 64);
+        tmem_ld_wait_regs(vb);
       }
+      // every score of this accumulator is in registers: hand the TMEM buffer back before the last filter
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[b]);
+      if (filter) process(vb, 96);
+      if (a.debug == 3 && blockIdx.x == 0 && t < 512 && threadIdx.x == 0) g_tc_trace[4 * t + 3] = clock64();
     }
     // ---- publish this split's list --------------------------------------------------------------
     const int64_t grow = (int64_t)qtile * TC_ROWS + row;
@@ -311,7 +387,8 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
     __syncwarp();
     const float* qr = a.q + row * a.d;
     const float qinv = a.q_inv_norm ? __ldg(a.q_inv_norm + row) : 1.0f;
-    float tmax = -INFINITY;                                  // max over splits of the list's last bf16 score
+    float tmax = -INFINITY;                                  // max over splits of the list's minimum bf16 score
+    float split_min = INFINITY; bool split_full = true;
     for (int c0 = 0; c0 < total; c0 += 4) {
       float sc[4]; int64_t id[4];
 #pragma unroll
@@ -323,7 +400,11 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
           const size_t o = ((size_t)sp * a.Q + row) * a.kp + p;
           const int32_t j = __ldg(a.part_i + o);
           const float approx = __ldg(a.part_s + o);
-          if (p == a.kp - 1 && j >= 0) tmax = fmaxf(tmax, approx);
+          // split threshold = minimum approx score of a FULL list (lists are unsorted)
+          if (p == 0) { split_min = INFINITY; split_full = true; }
+          split_full = split_full && (j >= 0);
+          split_min = fminf(split_min, approx);
+          if (p == a.kp - 1 && split_full) tmax = fmaxf(tmax, split_min);
           if (j >= 0) {
             id[u] = j;
             if (a.exact) {
@@ -404,7 +485,7 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k) {
   if (p.kh == 3) p.kh = 4;                   // kernel instantiations: 1, 2, 4 (a zero K half costs nothing but time)
   p.kp = (k <= 10) ? 16 : 32;
   // shared memory: A 2*KH boxes + NSTAGE boxes + lists + barriers + 1 KB alignment slack  <= 227 KB
-  const int list_bytes = p.kp * TC_ROWS * 8;
+  const int list_bytes = p.kp * TC_ROWS * 8 + TC_ROWS * 4;
   const int budget = 232448 - 1024 - 256 - list_bytes - 2 * p.kh * TC_BOX_BYTES;
   p.nstage = budget / TC_BOX_BYTES;
   if (p.nstage > 8) p.nstage = 8;
@@ -480,6 +561,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   TcArgs a{};
   a.Q = Q; a.N = N; a.n_qtiles = p.n_qtiles; a.n_splits = p.n_splits; a.tiles_per_split = p.tiles_per_split;
   a.n_tiles = p.n_tiles; a.kp = p.kp;
+  { const char* dbg = getenv("RAG_TC_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
   a.part_s = reinterpret_cast<float*>(w + p.off_ps);
   a.part_i = reinterpret_cast<int32_t*>(w + p.off_pi);
   const int kh_real = p.d_pad / 64;
@@ -512,3 +594,9 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
 }
 
 }  // namespace rag
+
+// diagnostics: copy the RAG_TC_DEBUG=3 pipeline trace (4 x 512 clock64 stamps) to the host
+extern "C" RAG_API int rag_tc_trace_read(unsigned long long* host_out) {
+  cudaError_t e = cudaMemcpyFromSymbol(host_out, rag::g_tc_trace, sizeof(unsigned long long) * 4 * 512);
+  return e == cudaSuccess ? RAG_OK : rag::cuda_fail(e, "rag_tc_trace_read");
+}
