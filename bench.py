@@ -196,6 +196,8 @@ def main():
         N_KEYS = args.n_keys
         return run_reference(args)
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
     import torch.distributed as dist
     import ragraph_b200 as R
     from ragraph_b200 import _lib as L, ops
