@@ -44,11 +44,13 @@ constexpr int TC_BN = 128;            // keys per tile
 constexpr int TC_BOX_BYTES = 128 * 128;   // one TMA box: 128 rows x 64 bf16
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+constexpr int TC_PQ = 4;               // per-row pending-candidate queue depth (drained after the TMEM hand-back)
 constexpr float TC_EPS = 0.00390625f + 0.0009765625f;   // 2^-8 (bf16 x bf16, unit vectors) + 2^-10 slack (fp32 sums)
 constexpr unsigned long long TC_TIMEOUT_CYCLES = 20000000000ull;   // ~10 s: trap instead of hanging the GPU
 
 // profiling trace (RAG_TC_DEBUG=3): CTA 0 stamps clock64 at pipeline events of its first 512 tiles
 __device__ unsigned long long g_tc_trace[4 * 512];
+__device__ unsigned int g_tc_trace2[2 * 512];   // per tile: drains by warp 0, cycles from tmem_full to tmem_empty arrive
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -102,6 +104,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr));
+}
+// wait for the outstanding tcgen05.ld and tie the destination registers to the wait, so that no consumer of v[]
+// can be scheduled above it when another chunk's load is issued in between (software pipelining)
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :: "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // wait for the outstanding tcgen05.ld and tie the destination registers to the wait, so that no consumer of
 // v[] can be scheduled above it when another chunk's load is issued in between (software pipelining)
@@ -145,8 +162,12 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3)
 // Candidate list of one (query row, key split): KP unsorted (score, index) slots in shared memory, entry p of
 // row r at ls[p*256 + r] (conflict free across a warp), plus meta[r] = slots in use | (position of the
 // current minimum << 8).  A new candidate (s > threshold) fills a free slot or overwrites the minimum, then
-// the minimum is found again (KP independent LDS, no dependent shifting).  Returns the new threshold: the
-// list minimum once all KP slots are in use, -inf before.  Ties at the minimum evict the larger index.
+// the minimum is found again by one pass over the KP scores.  Returns the new threshold: the list minimum once
+// all KP slots are in use, -inf before.
+// NOTE (measured): this kernel leaves ~1 KB of L1 (226 KB of the SM's 228 KB are shared memory), so ANY local
+// memory traffic -- register spills, ABI saves around a non-inlined call -- costs an L2 round trip (~2000 cycles
+// per slow-path visit in the first versions).  Everything below is written as small rolled loops over shared
+// memory so the kernel has a zero-byte stack frame.
 template <int KP>
 __device__ __forceinline__ float tc_list_push(float* ls, int32_t* li, int32_t* meta, float s, int32_t idx) {
   const int m = *meta;
@@ -158,18 +179,23 @@ __device__ __forceinline__ float tc_list_push(float* ls, int32_t* li, int32_t* m
     ++cnt;
     if (cnt < KP) { *meta = cnt; return -INFINITY; }
   }
-  float best = ls[0];
-  int32_t besti = li[0];
-  int bpos = 0;
+  // new minimum: KP independent loads issued back to back, then a depth-log2(KP) tournament -- dependent
+  // load->compare->branch chains cost ~50 cycles per element on a lone warp (measured), this costs ~150 in all
+  float v[KP];
+  int ps[KP];
 #pragma unroll
-  for (int p = 1; p < KP; ++p) {
-    const float v = ls[p * TC_ROWS];
-    const int32_t vi = li[p * TC_ROWS];
-    const bool worse = (v < best) || (v == best && vi > besti);
-    best = worse ? v : best; besti = worse ? vi : besti; bpos = worse ? p : bpos;
+  for (int p = 0; p < KP; ++p) { v[p] = ls[p * TC_ROWS]; ps[p] = p; }
+#pragma unroll
+  for (int w = KP / 2; w >= 1; w >>= 1) {
+#pragma unroll
+    for (int p = 0; p < w; ++p) {
+      const bool hi = v[p + w] < v[p];
+      v[p] = hi ? v[p + w] : v[p];
+      ps[p] = hi ? ps[p + w] : ps[p];
+    }
   }
-  *meta = KP | (bpos << 8);
-  return best;
+  *meta = KP | (ps[0] << 8);
+  return v[0];
 }
 
 struct TcArgs {
@@ -202,7 +228,9 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   float* list_s = reinterpret_cast<float*>(sB + NSTAGE * TC_BOX_BYTES);    // [KP][256]
   int32_t* list_i = reinterpret_cast<int32_t*>(list_s + KP * TC_ROWS);     // [KP][256]
   int32_t* list_meta = list_i + KP * TC_ROWS;                              // [256]
-  TcBarriers* bars = reinterpret_cast<TcBarriers*>(list_meta + TC_ROWS);
+  float* pq_s = reinterpret_cast<float*>(list_meta + TC_ROWS);             // [TC_PQ][256] pending scores
+  int32_t* pq_i = reinterpret_cast<int32_t*>(pq_s + TC_PQ * TC_ROWS);      // [TC_PQ][256] pending indices
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(pq_i + TC_PQ * TC_ROWS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qtile = blockIdx.x % a.n_qtiles;
@@ -279,14 +307,18 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         if (a.debug == 3 && blockIdx.x == 0 && t < 512) g_tc_trace[4 * t + 1] = clock64();
       }
     }
-  } else {
+  } else if (warp < TC_EPI_WARPS) {
     // =============================== epilogue: fused top-k' =====================================
     const int quarter = warp & 3, rb = warp >> 2;
     const int row = rb * 128 + quarter * 32 + lane;         // this thread's query row inside the CTA tile
     float* my_s = list_s + row;                             // entry p at my_s[p * 256] (conflict free)
     int32_t* my_i = list_i + row;
     int32_t* my_meta = list_meta + row;
+    float* my_pqs = pq_s + row;                             // pending entry q at my_pqs[q * 256]
+    int32_t* my_pqi = pq_i + row;
+    int npend = 0;
     float thr = -INFINITY;
+    unsigned int n_drain = 0;
     const int64_t key_base = (int64_t)tile0 * TC_BN;
     for (int t = 0; t < n_my_tiles; ++t) {
       const int b = t & 1;
@@ -296,8 +328,19 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       const int64_t tile_key0 = key_base + (int64_t)t * TC_BN;
       const int n_valid = (int)min((int64_t)TC_BN, a.N - tile_key0);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((b * 2 + rb) * TC_BN);
-      // one 32-column chunk: max tree vs the row threshold; on a hit, per-lane candidate mask -> push loop
-      auto process = [&](const uint32_t (&v)[32], int col0) {
+      // Deferred half of the slow path: fold this row's pending candidates into its list (runs after the TMEM
+      // buffer went back to the MMA warp, or when the 4-deep queue is full).
+      auto flush = [&]() {
+        for (int q = 0; q < npend; ++q) {
+          const float sc = my_pqs[q * TC_ROWS];
+          if (sc > thr) thr = tc_list_push<KP>(my_s, my_i, my_meta, sc, my_pqi[q * TC_ROWS]);
+        }
+        npend = 0;
+      };
+      // One 32-column chunk: max tree vs the row threshold (registers only).  On a hit the lane extracts ITS
+      // candidates (bitmask + 31-select, no memory) and appends them to its pending queue: ~150 cycles on the
+      // critical path instead of a full list update.
+      auto filter = [&](const uint32_t (&v)[32], int col0) {
         float m1[11];
 #pragma unroll
         for (int j = 0; j < 10; ++j)
@@ -305,46 +348,51 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         m1[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
         const float m2a = max3(m1[0], m1[1], m1[2]), m2b = max3(m1[3], m1[4], m1[5]);
         const float m2c = max3(m1[6], m1[7], m1[8]), m2d = fmaxf(m1[9], m1[10]);
-        const float m = fmaxf(max3(m2a, m2b, m2c), m2d);
-        if (m > thr) {                                      // rare once the list has warmed up
+        if (fmaxf(max3(m2a, m2b, m2c), m2d) > thr) {        // rare once the list has warmed up
           uint32_t mask = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
           const int room = n_valid - col0;                  // columns >= n_valid are TMA zero fill past the library end
           if (room < 32) mask &= (room <= 0) ? 0u : ((1u << room) - 1u);
-          while (mask) {                                    // each lane walks ITS OWN candidates
+          while (mask) {
             const int j = __ffs(mask) - 1;
             mask &= mask - 1;
-            const float sc = select32(v, j);
-            if (sc > thr) thr = tc_list_push<KP>(my_s, my_i, my_meta, sc, (int32_t)(tile_key0 + col0 + j));
+            if (npend == TC_PQ) { ++n_drain; flush(); }
+            my_pqs[npend * TC_ROWS] = select32(v, j);
+            my_pqi[npend * TC_ROWS] = (int32_t)(tile_key0 + col0 + j);
+            ++npend;
           }
         }
       };
       uint32_t va[32], vb[32];
-      const bool filter = (a.debug == 0 || a.debug == 3);
+      const bool do_filter = (a.debug == 0 || a.debug == 3);
       if (a.debug == 1) {
-      } else if (a.debug == 2) {
-        for (int c = 0; c < TC_BN / 32; ++c) { tmem_ld32(taddr + c * 32, va); tmem_ld_wait(); if (__uint_as_float(va[5]) == 123.456f) thr = 1.f; }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->tmem_empty[b]);
       } else {
-        // software pipeline: the load of chunk c+1 is in flight while chunk c is filtered
+        // software pipeline over the 4 chunks of the tile: the load of chunk c+1 is in flight while chunk c is
+        // filtered; the TMEM buffer goes back to the MMA warp as soon as the last chunk is in registers
         tmem_ld32(taddr, va);
         tmem_ld_wait_regs(va);
-        tmem_ld32(taddr + 32, vb);
-        process(va, 0);
-        tmem_ld_wait_regs(vb);
-        tmem_ld32(taddr + 64, va);
-        process(vb, 32);
-        tmem_ld_wait_regs(va);
-        tmem_ld32(taddr + 96, vb);
-        process(va, 64);
-        tmem_ld_wait_regs(vb);
+#pragma unroll 1
+        for (int c = 0; c < TC_BN / 32; c += 2) {
+          tmem_ld32(taddr + (c + 1) * 32, vb);
+          if (do_filter) filter(va, c * 32);
+          tmem_ld_wait_regs(vb);
+          if (c + 2 < TC_BN / 32) {
+            tmem_ld32(taddr + (c + 2) * 32, va);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[b]);
+          }
+          if (do_filter) filter(vb, (c + 1) * 32);
+          if (c + 2 < TC_BN / 32) tmem_ld_wait_regs(va);
+        }
+        if (npend) { ++n_drain; flush(); }
       }
-      // every score of this accumulator is in registers: hand the TMEM buffer back before the last filter
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tmem_empty[b]);
-      if (filter) process(vb, 96);
-      if (a.debug == 3 && blockIdx.x == 0 && t < 512 && threadIdx.x == 0) g_tc_trace[4 * t + 3] = clock64();
+      if (a.debug == 3 && blockIdx.x == 0 && t < 512 && threadIdx.x == 0) { g_tc_trace[4 * t + 3] = clock64(); g_tc_trace2[2 * t] = n_drain; n_drain = 0; }
     }
     // ---- publish this split's list --------------------------------------------------------------
     const int64_t grow = (int64_t)qtile * TC_ROWS + row;
@@ -485,11 +533,11 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k) {
   if (p.kh == 3) p.kh = 4;                   // kernel instantiations: 1, 2, 4 (a zero K half costs nothing but time)
   p.kp = (k <= 10) ? 16 : 32;
   // shared memory: A 2*KH boxes + NSTAGE boxes + lists + barriers + 1 KB alignment slack  <= 227 KB
-  const int list_bytes = p.kp * TC_ROWS * 8 + TC_ROWS * 4;
+  const int list_bytes = p.kp * TC_ROWS * 8 + TC_ROWS * 4 + TC_PQ * TC_ROWS * 8;   // lists + meta + pending queues
   const int budget = 232448 - 1024 - 256 - list_bytes - 2 * p.kh * TC_BOX_BYTES;
   p.nstage = budget / TC_BOX_BYTES;
   if (p.nstage > 8) p.nstage = 8;
-  p.nstage = (p.nstage >= 8) ? 8 : (p.nstage >= 6 ? 6 : 4);
+  if (p.nstage < 2) p.nstage = 2;
   p.smem = 1024 + (size_t)(2 * p.kh + p.nstage) * TC_BOX_BYTES + list_bytes + 256;
   p.n_qtiles = (int)((Q + TC_ROWS - 1) / TC_ROWS);
   p.n_tiles = (int)((N + TC_BN - 1) / TC_BN);
@@ -568,8 +616,8 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   if (kh_real == 3) return fail(RAG_EUNSUPPORTED, "cosine_topk: d in (128,192] is not instantiated on the tensor-core path");
 #define RAG_TC_CASE(KH_, NS_, KP_) \
   if (p.kh == KH_ && p.nstage == NS_ && p.kp == KP_) st = launch_filter<KH_, NS_, KP_>(mq, mk, a, p, s); else
-  RAG_TC_CASE(1, 8, 16) RAG_TC_CASE(1, 8, 32) RAG_TC_CASE(2, 8, 16) RAG_TC_CASE(2, 6, 32)
-  RAG_TC_CASE(4, 4, 16) RAG_TC_CASE(4, 4, 32)
+  RAG_TC_CASE(1, 8, 16) RAG_TC_CASE(1, 7, 32) RAG_TC_CASE(2, 7, 16) RAG_TC_CASE(2, 5, 32)
+  RAG_TC_CASE(4, 3, 16)
   return fail(RAG_EUNSUPPORTED, "cosine_topk: no tensor-core instantiation for kh=%d nstage=%d kp=%d", p.kh, p.nstage, p.kp);
 #undef RAG_TC_CASE
   if (st) return st;
@@ -595,8 +643,9 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
 
 }  // namespace rag
 
-// diagnostics: copy the RAG_TC_DEBUG=3 pipeline trace (4 x 512 clock64 stamps) to the host
+// diagnostics: copy the RAG_TC_DEBUG=3 pipeline trace (4 x 512 clock64 stamps + 2 x 512 uint32) to the host (20 KB)
 extern "C" RAG_API int rag_tc_trace_read(unsigned long long* host_out) {
   cudaError_t e = cudaMemcpyFromSymbol(host_out, rag::g_tc_trace, sizeof(unsigned long long) * 4 * 512);
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host_out + 4 * 512, rag::g_tc_trace2, sizeof(unsigned int) * 2 * 512);
   return e == cudaSuccess ? RAG_OK : rag::cuda_fail(e, "rag_tc_trace_read");
 }

@@ -33,15 +33,20 @@ print(f"RAG_TC_DEBUG={os.environ.get('RAG_TC_DEBUG','0')} N={N} d={d} Q={Q} mode
 if os.environ.get("RAG_TC_DEBUG") == "3":
     import ctypes, numpy as np
     lib = L.load()
-    buf = (ctypes.c_ulonglong * 2048)()
+    buf = (ctypes.c_ulonglong * (2048 + 512))()
     lib.rag_tc_trace_read.argtypes = [ctypes.c_void_p]
     lib.rag_tc_trace_read(buf)
-    tr = np.array(buf, dtype=np.int64).reshape(512, 4)
+    tr = np.array(buf[:2048], dtype=np.int64).reshape(512, 4)
+    tr2 = np.frombuffer(np.array(buf[2048:], dtype=np.uint64).tobytes(), dtype=np.uint32).reshape(512, 2)
     t0 = tr[0, 0]
     print("tile: mma_start mma_issued | epi_start epi_done   (cycles since first)   d(mma_start) d(epi_done)")
     for t in list(range(0, 12)) + list(range(400, 412)):
         r = tr[t] - t0
         dm = tr[t, 0] - tr[t - 1, 0] if t else 0
         de = tr[t, 3] - tr[t - 1, 3] if t else 0
-        print(f"{t:4d}: {r[0]:8d} {r[1]:8d} | {r[2]:8d} {r[3]:8d}    {dm:6d} {de:6d}   epi_len={tr[t,3]-tr[t,2]}  full_lat={tr[t,2]-tr[t,1]}")
+        print(f"{t:4d}: {r[0]:8d} {r[1]:8d} | {r[2]:8d} {r[3]:8d}    {dm:6d} {de:6d}   epi_len={tr[t,3]-tr[t,2]}  full_lat={tr[t,2]-tr[t,1]}  drains={tr2[t,0]}  tmem_hold={tr2[t,1]}")
+    print("drains per tile (100..500):", float(tr2[100:500, 0].mean()), " mean tmem_hold:", float(tr2[100:500, 1].mean()),
+          " mean epi_len for drains==0:", float(np.mean([(tr[t,3]-tr[t,2]) for t in range(100,500) if tr2[t,0]==0] or [0])),
+          " ==1:", float(np.mean([(tr[t,3]-tr[t,2]) for t in range(100,500) if tr2[t,0]==1] or [0])),
+          " ==2:", float(np.mean([(tr[t,3]-tr[t,2]) for t in range(100,500) if tr2[t,0]==2] or [0])))
     print("mean period (tiles 100..500):", (tr[500, 0] - tr[100, 0]) / 400.0, " mean epi_len:", float(np.mean(tr[100:500, 3] - tr[100:500, 2])))
