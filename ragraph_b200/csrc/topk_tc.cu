@@ -210,8 +210,8 @@ struct __align__(8) TcBarriers {
   uint64_t a_full;
   uint64_t full[8];
   uint64_t empty[8];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[2][2];    // [buffer][row block]: the two 128-row accumulators of a tile are handed over separately
+  uint64_t tmem_empty[2][2];
   uint32_t tmem_base;
 };
 
@@ -245,7 +245,8 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
     mbar_init(&bars->a_full, 1);
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], TC_EPI_WARPS); }
+    for (int b = 0; b < 2; ++b)
+      for (int rb = 0; rb < 2; ++rb) { mbar_init(&bars->tmem_full[b][rb], 1); mbar_init(&bars->tmem_empty[b][rb], TC_EPI_WARPS / 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_EPI_WARPS + 1) {
@@ -285,25 +286,58 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       int s = 0; uint32_t ph = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
         const int b = t & 1;
-        mbar_wait(&bars->tmem_empty[b], (((uint32_t)t >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        if (a.debug == 3 && blockIdx.x == 0 && t < 512) g_tc_trace[4 * t + 0] = clock64();
-        for (int kh = 0; kh < KH; ++kh) {
-          mbar_wait(&bars->full[s], ph);
-          tc_fence_after();
+        const uint32_t use_parity = ((uint32_t)t >> 1) & 1u;
+        if constexpr (KH <= 2) {
+          // Row block 0 first, then row block 1, each published on its own barrier: the epilogue of block 0 starts
+          // half a tile earlier and each accumulator has 1.5 tile times (not 1) to be drained before its reuse.
+          // (A tile's KH stages stay occupied until both row blocks have consumed them: needs NSTAGE >= 2*KH.)
+          static_assert(NSTAGE >= 2 * KH, "row-block-major MMA order holds a tile's stages for the whole tile");
 #pragma unroll
           for (int rb = 0; rb < 2; ++rb) {
+            mbar_wait(&bars->tmem_empty[b][rb], use_parity ^ 1u);
+            tc_fence_after();
+            if (a.debug == 3 && blockIdx.x == 0 && t < 512 && rb == 0) g_tc_trace[4 * t + 0] = clock64();
+            int sk = s; uint32_t phk = ph;
+            for (int kh = 0; kh < KH; ++kh) {
+              if (rb == 0) { mbar_wait(&bars->full[sk], phk); tc_fence_after(); }
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const uint64_t da = umma_desc(a_addr + (rb * KH + kh) * TC_BOX_BYTES + k4 * 32);
-              const uint64_t db = umma_desc(b_addr + s * TC_BOX_BYTES + k4 * 32);
-              tc_mma_bf16(tmem_base + (uint32_t)((b * 2 + rb) * TC_BN), da, db, TC_IDESC, (kh | k4) != 0 ? 1u : 0u);
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint64_t da = umma_desc(a_addr + (rb * KH + kh) * TC_BOX_BYTES + k4 * 32);
+                const uint64_t db = umma_desc(b_addr + sk * TC_BOX_BYTES + k4 * 32);
+                tc_mma_bf16(tmem_base + (uint32_t)((b * 2 + rb) * TC_BN), da, db, TC_IDESC, (kh | k4) != 0 ? 1u : 0u);
+              }
+              if (++sk == NSTAGE) { sk = 0; phk ^= 1; }
             }
+            tc_commit(&bars->tmem_full[b][rb]);             // this row block's accumulator is complete
           }
-          tc_commit(&bars->empty[s]);                       // smem stage reusable once these MMAs retire
-          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          for (int kh = 0; kh < KH; ++kh) {                 // smem stages reusable once all 2*KH*4 MMAs retire
+            tc_commit(&bars->empty[s]);
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          }
+        } else {
+          // d = 256: the resident query tile leaves room for 3 stages only, so stages are released K-half by K-half
+          // (both row blocks consume a stage back to back); the MMA time per tile doubles, the epilogue has slack.
+          mbar_wait(&bars->tmem_empty[b][0], use_parity ^ 1u);
+          mbar_wait(&bars->tmem_empty[b][1], use_parity ^ 1u);
+          tc_fence_after();
+          for (int kh = 0; kh < KH; ++kh) {
+            mbar_wait(&bars->full[s], ph);
+            tc_fence_after();
+#pragma unroll
+            for (int rb = 0; rb < 2; ++rb) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint64_t da = umma_desc(a_addr + (rb * KH + kh) * TC_BOX_BYTES + k4 * 32);
+                const uint64_t db = umma_desc(b_addr + s * TC_BOX_BYTES + k4 * 32);
+                tc_mma_bf16(tmem_base + (uint32_t)((b * 2 + rb) * TC_BN), da, db, TC_IDESC, (kh | k4) != 0 ? 1u : 0u);
+              }
+            }
+            tc_commit(&bars->empty[s]);
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          }
+          tc_commit(&bars->tmem_full[b][0]);
+          tc_commit(&bars->tmem_full[b][1]);
         }
-        tc_commit(&bars->tmem_full[b]);                     // accumulators of tile t complete
         if (a.debug == 3 && blockIdx.x == 0 && t < 512) g_tc_trace[4 * t + 1] = clock64();
       }
     }
@@ -322,7 +356,7 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const int64_t key_base = (int64_t)tile0 * TC_BN;
     for (int t = 0; t < n_my_tiles; ++t) {
       const int b = t & 1;
-      mbar_wait(&bars->tmem_full[b], ((uint32_t)t >> 1) & 1u);
+      mbar_wait(&bars->tmem_full[b][rb], ((uint32_t)t >> 1) & 1u);
       tc_fence_after();
       if (a.debug == 3 && blockIdx.x == 0 && t < 512 && threadIdx.x == 0) g_tc_trace[4 * t + 2] = clock64();
       const int64_t tile_key0 = key_base + (int64_t)t * TC_BN;
@@ -369,7 +403,7 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       if (a.debug == 1) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->tmem_empty[b]);
+        if (lane == 0) mbar_arrive(&bars->tmem_empty[b][rb]);
       } else {
         // software pipeline over the 4 chunks of the tile: the load of chunk c+1 is in flight while chunk c is
         // filtered; the TMEM buffer goes back to the MMA warp as soon as the last chunk is in registers
@@ -385,7 +419,7 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           } else {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty[b]);
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[b][rb]);
           }
           if (do_filter) filter(vb, (c + 1) * 32);
           if (c + 2 < TC_BN / 32) tmem_ld_wait_regs(va);
