@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=250_000)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--no-spmm", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true", help="multi-GPU: all-gather formulation instead of the peer-memory kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -196,8 +197,8 @@ def main():
         N_KEYS = args.n_keys
         return run_reference(args)
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
+    # rank 0 prints ONE JSON line on stdout: NCCL's own log (version banner at VERSION/WARN level) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch.distributed as dist
     import ragraph_b200 as R
     from ragraph_b200 import _lib as L, ops
@@ -216,6 +217,8 @@ def main():
     store = make_library_shard(lo, hi, DIM, N_CLASS, dev)
     if args.mode >= 0:
         store.mode = args.mode
+    if args.nccl_exchange:
+        os.environ["RAG_P2P"] = "0"
     sr = R.ShardedRetriever(store, N_KEYS)
     mode = store._pick_mode(Q_BATCH, TOPK)
     q_host = make_queries(Q_BATCH, DIM, dev)
@@ -240,13 +243,8 @@ def main():
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
 
     def step(q, it=None):
-        if it is not None:
-            k_ev[it][0].record()
-        scores, idx = sr.topk(q, TOPK)
-        if it is not None:
-            k_ev[it][1].record()
-        emb = sr.gather(store.resource_values, idx)
-        lab = sr.gather(store.resource_labels, idx)
+        # local fused top-k (event-timed for the roofline) + the sharded finish; N=1: plain gathers
+        emb, lab, scores, idx = sr.retrieve(q, TOPK, copy=False, events=k_ev[it] if it is not None else None)
         return emb, lab, scores, idx
 
     # ---- device-resident timing ("value") --------------------------------------------------
@@ -312,7 +310,9 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"top-{TOPK} cosine retrieve + value/label gather, {N_KEYS} keys d={DIM} sharded by key rows over "
                                    f"{world} GPU(s), {Q_BATCH}-query batches", "mode": mode,
-                       "l2": "inputs larger than L2 (key shard streamed every step)", "parallelism": f"key-row shard x{world}"},
+                       "l2": "inputs larger than L2 (key shard streamed every step)", "parallelism": f"key-row shard x{world}",
+                       "exchange": {"p2p": "one kernel over NVLink peer memory (push candidates, merge, owners store rows to peers)",
+                                    "nccl": "NCCL all-gather + merge + owner gather + all-gather", "single": "none"}[sr.last_path]},
             "roofline": roof,
             "e2e": {"value": Q_BATCH / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},

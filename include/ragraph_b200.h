@@ -124,6 +124,31 @@ RAG_API int rag_cosine2_topk_f32(const float* qa, const float* ka, int32_t da, f
 RAG_API int rag_topk_merge(const float* scores, const int64_t* idx, int32_t R, int64_t Q, int32_t k_in,
                    int32_t k_out, float* out_scores, int64_t* out_idx, rag_stream_t stream);
 
+/* ---- e: sharded retrieval finish as ONE kernel over NVLink peer memory ------------------- */
+/* New functionality (the reference is single-GPU): replaces "all-gather candidates -> merge ->
+ * owners gather -> all-gather rows -> select" by peer-memory stores + two flag waits.
+ * Every rank owns one block of a SYMMETRIC allocation (same size everywhere, every block
+ * mapped into every process, e.g. torch.distributed._symmetric_memory); peers_dev is a DEVICE
+ * array of `world` pointers, entry r = rank r's block as mapped in this process.  The block
+ * must be zero-filled once (and all ranks synchronised) before the first call.
+ * rag_xchg_layout fills offsets_out[8] = { total bytes, flags offset, result-A offset, result-A
+ * bytes per parity, result-B offset, result-B bytes per parity, candidate-score offset,
+ * candidate-index offset } for blocks sized for (Q_max, k_max, world, row bytes).
+ * rag_sharded_finish: local_scores/local_idx [Q,k] = this rank's fused top-k with GLOBAL row
+ * indices; table_a/table_b = this rank's rows [lo,hi) of the value / label tables (table_b
+ * nullable); step = 1, 2, 3, ... identical on all ranks.  Outputs: out_scores/out_idx [Q,k]
+ * (merged, identical on all ranks, order score desc / index asc) in ordinary memory, and
+ * the gathered rows [Q,k,row_bytes] inside this rank's block at result offset + (step & 1) *
+ * bytes per parity (valid until the next-but-one call).  Row copies are bit exact.
+ * All ranks must call with the same Q, k, step; a missing peer traps after ~10 s. */
+RAG_API int rag_xchg_layout(int64_t Q_max, int32_t k_max, int32_t world, int64_t row_bytes_a,
+                    int64_t row_bytes_b, size_t* offsets_out);
+RAG_API int rag_sharded_finish(const float* local_scores, const int64_t* local_idx, int64_t Q, int32_t k,
+                       int32_t world, int32_t rank, void* const* peers_dev, int64_t Q_max,
+                       int32_t k_max, const void* table_a, int64_t row_bytes_a, const void* table_b,
+                       int64_t row_bytes_b, int64_t lo, int64_t hi, uint64_t step, float* out_scores,
+                       int64_t* out_idx, rag_stream_t stream);
+
 /* ---- a3/K5: gathers (bit exact) ------------------------------------------------------- */
 /* out[m, :] = table[idx[m], :] for m < M; rows are row_bytes long (any dtype).  Negative
  * indices wrap once (torch semantics); an index still out of range writes zeros and raises

@@ -37,6 +37,9 @@ SIGNATURES = {
     "rag_cosine2_topk_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "rag_cosine2_topk_f32": (C.c_int, [_p, _p, _i32, _f32, _p, _p, _i32, _f32, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
     "rag_topk_merge": (C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _p, _p, _p]),
+    "rag_xchg_layout": (C.c_int, [_i64, _i32, _i32, _i64, _i64, _p]),
+    "rag_sharded_finish": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p, _i64, _i32, _p, _i64, _p, _i64, _i64, _i64,
+                                     C.c_uint64, _p, _p, _p]),
     "rag_gather_rows": (C.c_int, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _p]),
     "rag_gather_oob_count": (_i64, []),
     "rag_gather_reduce_f32": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _i32, _p, _f32, _p, _p]),

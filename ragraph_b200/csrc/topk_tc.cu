@@ -458,53 +458,114 @@ struct RefineArgs {
   int32_t* fb_rows; int32_t* fb_count;   // uncertified rows (exact only)
 };
 
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// One warp per query row.
+//   pass 1: stage the row's S*kp approximate scores in shared memory and take every full split list's minimum
+//           (t_split; lists are unsorted, kp in {16, 32} so a list is a lane segment of the warp);
+//   pass 2: tau = k-th largest approximate score over all candidates (max-below-previous iteration);
+//   pass 3: only candidates with s_bf16 >= tau - 2 EPS can be among the exact top k (the k candidates that define
+//           tau have exact scores >= tau - EPS, everything below the cut has exact score < tau - EPS), so only
+//           those are re-scored in fp32 from the master keys -- typically 15-30 of the 144+ candidates;
+//   certificate: k-th exact score > max_split t_split + EPS, else the row goes to the fp32 fallback list.
 __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int total = a.n_splits * a.kp;
   int64_t* li = reinterpret_cast<int64_t*>(smem_raw) + (size_t)warp * a.k;
   float* lv = reinterpret_cast<float*>(reinterpret_cast<int64_t*>(smem_raw) + (size_t)wpb * a.k) + (size_t)warp * a.k;
-  const int total = a.n_splits * a.kp;
+  float* ap = reinterpret_cast<float*>(reinterpret_cast<int64_t*>(smem_raw) + (size_t)wpb * a.k) + (size_t)wpb * a.k +
+              (size_t)warp * total;
+  const int nd = (a.d + 31) >> 5;                              // <= 8 (tensor-core shapes have d <= 256)
   for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < a.Q; row += (int64_t)gridDim.x * wpb) {
     for (int p = lane; p < a.k; p += 32) { lv[p] = -FLT_MAX; li[p] = INT64_MAX; }
+    // ---- pass 1 ------------------------------------------------------------------------------------
+    float tmax = -INFINITY;
+    for (int c0 = 0; c0 < total; c0 += 32) {
+      const int c = c0 + lane;
+      const bool in = c < total;
+      const int sp = c / a.kp, p = c - sp * a.kp;
+      const size_t o = ((size_t)sp * a.Q + row) * a.kp + p;
+      const int32_t j = in ? __ldg(a.part_i + o) : -1;
+      const float s = in ? __ldg(a.part_s + o) : 0.f;
+      const bool valid = j >= 0;
+      if (in) ap[c] = valid ? s : -INFINITY;
+      float mn = valid ? s : INFINITY;
+      int full = valid ? 1 : 0;
+      for (int w = 1; w < a.kp; w <<= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, w));
+        full &= __shfl_xor_sync(0xffffffffu, full, w);
+      }
+      if (in && full) tmax = fmaxf(tmax, mn);
+    }
+    tmax = warp_max(tmax);
     __syncwarp();
-    const float* qr = a.q + row * a.d;
+    // ---- pass 2 ------------------------------------------------------------------------------------
+    float prev = INFINITY;
+    int cnt = 0;
+    while (cnt < a.k) {
+      float m = -INFINITY;
+      for (int c = lane; c < total; c += 32) { const float v = ap[c]; if (v < prev) m = fmaxf(m, v); }
+      m = warp_max(m);
+      if (m == -INFINITY) break;                               // fewer than k valid candidates
+      int n = 0;
+      for (int c = lane; c < total; c += 32) n += (ap[c] == m) ? 1 : 0;
+      cnt += __reduce_add_sync(0xffffffffu, n);
+      prev = m;
+    }
+    const float cut = (cnt >= a.k) ? (a.exact ? prev - 2.0f * TC_EPS : prev) : -INFINITY;
+    // ---- pass 3 ------------------------------------------------------------------------------------
+    float qreg[8];
     const float qinv = a.q_inv_norm ? __ldg(a.q_inv_norm + row) : 1.0f;
-    float tmax = -INFINITY;                                  // max over splits of the list's minimum bf16 score
-    float split_min = INFINITY; bool split_full = true;
-    for (int c0 = 0; c0 < total; c0 += 4) {
-      float sc[4]; int64_t id[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = c0 + u;
-        sc[u] = -FLT_MAX; id[u] = -1;
-        if (c < total) {
-          const int sp = c / a.kp, p = c - sp * a.kp;
-          const size_t o = ((size_t)sp * a.Q + row) * a.kp + p;
-          const int32_t j = __ldg(a.part_i + o);
-          const float approx = __ldg(a.part_s + o);
-          // split threshold = minimum approx score of a FULL list (lists are unsorted)
-          if (p == 0) { split_min = INFINITY; split_full = true; }
-          split_full = split_full && (j >= 0);
-          split_min = fminf(split_min, approx);
-          if (p == a.kp - 1 && split_full) tmax = fmaxf(tmax, split_min);
-          if (j >= 0) {
+    for (int t = 0; t < 8; ++t) {
+      const int e = lane + 32 * t;
+      qreg[t] = (a.exact && t < nd && e < a.d) ? __ldg(a.q + row * a.d + e) * qinv : 0.f;
+    }
+    for (int c0 = 0; c0 < total; c0 += 32) {
+      const int c = c0 + lane;
+      const float mine = (c < total) ? ap[c] : -INFINITY;
+      unsigned mask = __ballot_sync(0xffffffffu, mine >= cut && mine > -INFINITY);
+      while (mask) {
+        float sc[4]; int64_t id[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          sc[u] = -FLT_MAX; id[u] = -1;
+          if (mask) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int cc = c0 + b;
+            const int sp = cc / a.kp, p = cc - sp * a.kp;
+            const int32_t j = __ldg(a.part_i + ((size_t)sp * a.Q + row) * a.kp + p);
             id[u] = j;
             if (a.exact) {
               const float* kr = a.keys + (int64_t)j * a.d;
               float dot = 0.f;
-              for (int e = lane; e < a.d; e += 32) dot = fmaf(__ldg(qr + e) * qinv, __ldg(kr + e), dot);
-              dot = warp_sum(dot);
-              sc[u] = dot * (a.key_inv_norm ? __ldg(a.key_inv_norm + j) : 1.0f);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                const int e = lane + 32 * t;
+                if (t < nd && e < a.d) dot = fmaf(qreg[t], __ldg(kr + e), dot);
+              }
+              sc[u] = dot;
             } else {
-              sc[u] = approx;
+              sc[u] = __shfl_sync(0xffffffffu, mine, b);
             }
           }
         }
-      }
+        if (a.exact) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (id[u] >= 0 && ranks_before(sc[u], id[u], lv[a.k - 1], li[a.k - 1]))
-          warp_sorted_insert<int64_t>(lv, li, a.k, sc[u], id[u], lane);
+          for (int u = 0; u < 4; ++u)
+            if (id[u] >= 0) sc[u] = warp_sum(sc[u]) * (a.key_inv_norm ? __ldg(a.key_inv_norm + id[u]) : 1.0f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (id[u] >= 0 && ranks_before(sc[u], id[u], lv[a.k - 1], li[a.k - 1]))
+            warp_sorted_insert<int64_t>(lv, li, a.k, sc[u], id[u], lane);
+      }
     }
     const float kth = lv[a.k - 1];
     const bool certified = !a.exact || (li[a.k - 1] != INT64_MAX && kth > tmax + TC_EPS);
@@ -663,11 +724,12 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   r.idx_offset = idx_offset; r.out_scores = out_scores; r.out_idx = out_idx;
   r.fb_rows = reinterpret_cast<int32_t*>(w + p.off_fb);
   r.fb_count = reinterpret_cast<int32_t*>(w + p.off_fbn);
-  const int wpb = 8;
+  const int total_c = p.n_splits * p.kp;
+  const int wpb = (total_c <= 1024) ? 8 : 2;                    // per-warp smem: k*12 + total*4 bytes (< 48 KB per CTA)
   int64_t blocks = (Q + wpb - 1) / wpb;
-  const int64_t cap = (int64_t)sm_count() * 8;
+  const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  refine_kernel<<<(unsigned)blocks, wpb * 32, (size_t)wpb * k * 12, s>>>(r);
+  refine_kernel<<<(unsigned)blocks, wpb * 32, (size_t)wpb * (k * 12 + total_c * 4), s>>>(r);
   RAG_LAUNCH_OK("refine_kernel");
   if (mode != RAG_SIM_BF16_REFINE) return RAG_OK;
   // rows whose certificate failed are recomputed in fp32 (device-side row list; usually empty)
