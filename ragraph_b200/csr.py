@@ -76,7 +76,38 @@ class CSRGraph:
                                  deterministic=True)
 
     def spmm(self, x: Tensor, epilogue: int = 0, **kw) -> Tensor:
-        return ops.csr_spmm(self.rowptr, self.col, self.val, x, epilogue, **kw)
+        """epilogue(A @ x): one fused launch; differentiable (dX = A^T dY on the cached transpose) when an input
+        requires grad -- see autograd.py."""
+        from .autograd import spmm_epilogue
+        return spmm_epilogue(self, x, epilogue, **kw)
+
+    def row_ids(self) -> Tensor:
+        """int64 [nnz]: the row of every stored entry."""
+        counts = self.rowptr[1:] - self.rowptr[:-1]
+        return torch.repeat_interleave(torch.arange(self.n_rows, device=self.col.device), counts)
+
+    def transpose(self) -> "CSRGraph":
+        """CSR of A^T (cached).  Entries of a transposed row are ordered by original row (stable sort), so the
+        backward SpMM `dX = A^T dY` sums in a fixed order."""
+        t = getattr(self, "_transposed", None)
+        if t is None:
+            edges_t = torch.stack([self.row_ids(), self.col.to(torch.int64)], dim=1)     # [:,0] = new col, [:,1] = new row
+            t = CSRGraph.from_coo(edges_t, self.val, self.n_cols, self.n_rows, deterministic=True)
+            t._transposed = self
+            self._transposed = t
+        return t
+
+    def row_normalized(self) -> "CSRGraph":
+        """val[i,j] / sum_j val[i,j] (Propagation.py:15-16) as its own CSR handle (cached); 0/0 rows give NaN as in
+        the reference's `adj / degree`."""
+        r = getattr(self, "_row_normalized", None)
+        if r is None:
+            val = self.val if self.val is not None else torch.ones(self.nnz, dtype=torch.float32, device=self.col.device)
+            rows = self.row_ids()
+            deg = torch.zeros(self.n_rows, dtype=torch.float32, device=val.device).index_add_(0, rows, val)
+            r = CSRGraph(self.rowptr, self.col, val / deg[rows], self.n_rows, self.n_cols)
+            self._row_normalized = r
+        return r
 
 
 _dense_cache: dict = {}

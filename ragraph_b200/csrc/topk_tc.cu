@@ -203,6 +203,7 @@ struct TcArgs {
   int n_qtiles; int n_splits; int tiles_per_split; int n_tiles;
   int kp;                          // list length per (row, split)
   float* part_s; int32_t* part_i;  // [n_splits][Q][kp]
+  int swap_halves;                 // RAG_TS_SWAP=1 (diagnostic): swap the bf16 halves of every A word stored to TMEM
   int debug;                       // RAG_TC_DEBUG (profiling experiments only): 1 = epilogue skips TMEM reads, 2 = reads but skips the filter
 };
 
@@ -447,6 +448,258 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   }
 }
 
+// =====================================================================================================
+// Query-stationary variant: the query tile lives in TENSOR MEMORY as the A operand (tcgen05.mma "TS" form).
+//
+// The SS kernel above re-reads the 256-row query tile from shared memory for every key tile: per 128-key tile
+// that is 64 KB of A reads + 64 KB of B reads + 32 KB of TMA writes = 160 KB against the 1024 cycles the tensor
+// pipe needs, i.e. 156 B/clk of a 128 B/clk shared-memory port -- the MMA-only ceiling measured at 0.81 of the
+// bf16 peak.  Retrieval has a STATIONARY operand (a CTA's queries never change), so here the epilogue warps copy
+// their query rows once into TMEM (tcgen05.st, lane = row, 32-bit column j = bf16 elements 2j, 2j+1) and every
+// MMA reads A from there: shared-memory traffic drops to 96 KB per tile (94 B/clk), and the 64 KB of shared
+// memory the query tile occupied becomes pipeline depth (11 stages).
+// TMEM budget (512 columns): A = 2 row blocks x d_pad/2 columns at the top, accumulators = a ring of
+// NBUF = (512 - d_pad) / 128 buffers of 128 columns; "use" u = 2*tile + row_block takes buffer u % NBUF.
+struct __align__(8) TsBarriers {
+  uint64_t a_full;
+  uint64_t full[12];
+  uint64_t empty[12];
+  uint64_t tmem_full[3];
+  uint64_t tmem_empty[3];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+               "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+               : "memory");
+}
+
+template <int KH, int NSTAGE, int KP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t* __restrict__ q_bf, const TcArgs a) {
+  constexpr int A_COLS = 2 * KH * 32;                 // 32-bit TMEM columns of the resident query tile
+  constexpr int NBUF = (512 - A_COLS) / TC_BN;        // accumulator ring: 3 (d <= 128) or 2 (d <= 256)
+  constexpr uint32_t A_COL0 = NBUF * TC_BN;
+  static_assert(NBUF >= 2 && NBUF <= 3, "accumulator ring");
+  static_assert(NSTAGE >= 2 * KH && NSTAGE <= 12, "row-block-major MMA order holds a tile's stages for the whole tile");
+  extern __shared__ unsigned char smem_dyn[];
+  // carve: [B: NSTAGE boxes][lists: KP x 256 x (f32 + i32)][meta][pending queues][barriers]
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sB = base;
+  float* list_s = reinterpret_cast<float*>(sB + NSTAGE * TC_BOX_BYTES);    // [KP][256]
+  int32_t* list_i = reinterpret_cast<int32_t*>(list_s + KP * TC_ROWS);     // [KP][256]
+  int32_t* list_meta = list_i + KP * TC_ROWS;                              // [256]
+  float* pq_s = reinterpret_cast<float*>(list_meta + TC_ROWS);             // [TC_PQ][256] pending scores
+  int32_t* pq_i = reinterpret_cast<int32_t*>(pq_s + TC_PQ * TC_ROWS);      // [TC_PQ][256] pending indices
+  TsBarriers* bars = reinterpret_cast<TsBarriers*>(pq_i + TC_PQ * TC_ROWS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qtile = blockIdx.x % a.n_qtiles;
+  const int split = blockIdx.x / a.n_qtiles;
+  const int tile0 = split * a.tiles_per_split;
+  const int tile1 = min(tile0 + a.tiles_per_split, a.n_tiles);
+  const int n_my_tiles = max(tile1 - tile0, 0);
+
+  // ---- one-time setup ---------------------------------------------------------------------------
+  if (warp == TC_EPI_WARPS && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
+    mbar_init(&bars->a_full, TC_EPI_WARPS);
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], TC_EPI_WARPS / 2); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == TC_EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < KP * TC_ROWS; i += TC_THREADS) { list_s[i] = -INFINITY; list_i[i] = -1; }
+  for (int i = threadIdx.x; i < TC_ROWS; i += TC_THREADS) list_meta[i] = 0;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == TC_EPI_WARPS) {
+    // =============================== TMA producer: the key stream ===============================
+    if (elect_one()) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+        for (int kh = 0; kh < KH; ++kh) {
+          mbar_wait(&bars->empty[s], ph ^ 1);
+          mbar_expect_tx(&bars->full[s], TC_BOX_BYTES);
+          tma_load_2d(sB + s * TC_BOX_BYTES, &map_k, kh * 64, (tile0 + t) * TC_BN, &bars->full[s]);
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == TC_EPI_WARPS + 1) {
+    // =============================== MMA issuer (A from TMEM) ===================================
+    if (elect_one()) {
+      mbar_wait(&bars->a_full, 0);
+      tc_fence_after();
+      const uint32_t b_addr = smem_u32(sB);
+      int s = 0; uint32_t ph = 0;
+      int buf = 0; uint32_t bph = 0;
+      for (int t = 0; t < n_my_tiles; ++t) {
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+          mbar_wait(&bars->tmem_empty[buf], bph ^ 1u);
+          tc_fence_after();
+          if (a.debug == 3 && blockIdx.x == 0 && t < 512 && rb == 0) g_tc_trace[4 * t + 0] = clock64();
+          int sk = s; uint32_t phk = ph;
+          for (int kh = 0; kh < KH; ++kh) {
+            if (rb == 0) { mbar_wait(&bars->full[sk], phk); tc_fence_after(); }
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t db = umma_desc(b_addr + sk * TC_BOX_BYTES + k4 * 32);
+              tc_mma_bf16_ts(tmem_base + (uint32_t)(buf * TC_BN), tmem_base + A_COL0 + (uint32_t)((rb * KH + kh) * 32 + k4 * 8),
+                             db, TC_IDESC, (kh | k4) != 0 ? 1u : 0u);
+            }
+            if (++sk == NSTAGE) { sk = 0; phk ^= 1; }
+          }
+          tc_commit(&bars->tmem_full[buf]);                 // this row block's accumulator is complete
+          if (++buf == NBUF) { buf = 0; bph ^= 1u; }
+        }
+        for (int kh = 0; kh < KH; ++kh) {                   // smem stages reusable once all 2*KH*4 MMAs retire
+          tc_commit(&bars->empty[s]);
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+        }
+        if (a.debug == 3 && blockIdx.x == 0 && t < 512) g_tc_trace[4 * t + 1] = clock64();
+      }
+    }
+  } else if (warp < TC_EPI_WARPS) {
+    // =============================== epilogue warps ==============================================
+    const int quarter = warp & 3, rb = warp >> 2;
+    const int row = rb * 128 + quarter * 32 + lane;         // this thread's query row inside the CTA tile
+    const int64_t grow = (int64_t)qtile * TC_ROWS + row;
+    // ---- one-time: this thread's normalised bf16 query row -> TMEM (the stationary A operand) ----
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(q_bf + grow * (int64_t)(KH * 64));
+      const uint32_t a_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + A_COL0 + (uint32_t)(rb * KH * 32);
+#pragma unroll 1
+      for (int c = 0; c < KH * 2; ++c) {                    // 16 columns = 32 bf16 per step
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 x = (grow < a.Q) ? __ldg(src + c * 4 + i) : make_uint4(0u, 0u, 0u, 0u);
+          w[4 * i] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
+        }
+        if (a.swap_halves) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w[i] = __byte_perm(w[i], 0u, 0x1032);
+        }
+        tmem_st16(a_taddr + c * 16, w);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->a_full);
+    }
+    // ---- fused top-k' ------------------------------------------------------------------------------
+    float* my_s = list_s + row;                             // entry p at my_s[p * 256] (conflict free)
+    int32_t* my_i = list_i + row;
+    int32_t* my_meta = list_meta + row;
+    float* my_pqs = pq_s + row;                             // pending entry q at my_pqs[q * 256]
+    int32_t* my_pqi = pq_i + row;
+    int npend = 0;
+    float thr = -INFINITY;
+    unsigned int n_drain = 0;
+    const int64_t key_base = (int64_t)tile0 * TC_BN;
+    int buf = rb; uint32_t bph = 0;                         // use u = 2t + rb -> buffer u % NBUF, phase (u / NBUF) & 1
+    for (int t = 0; t < n_my_tiles; ++t) {
+      mbar_wait(&bars->tmem_full[buf], bph);
+      tc_fence_after();
+      if (a.debug == 3 && blockIdx.x == 0 && t < 512 && threadIdx.x == 0) g_tc_trace[4 * t + 2] = clock64();
+      const int64_t tile_key0 = key_base + (int64_t)t * TC_BN;
+      const int n_valid = (int)min((int64_t)TC_BN, a.N - tile_key0);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN);
+      auto flush = [&]() {
+        for (int q = 0; q < npend; ++q) {
+          const float sc = my_pqs[q * TC_ROWS];
+          if (sc > thr) thr = tc_list_push<KP>(my_s, my_i, my_meta, sc, my_pqi[q * TC_ROWS]);
+        }
+        npend = 0;
+      };
+      auto filter = [&](const uint32_t (&v)[32], int col0) {
+        float m1[11];
+#pragma unroll
+        for (int j = 0; j < 10; ++j)
+          m1[j] = max3(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
+        m1[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+        const float m2a = max3(m1[0], m1[1], m1[2]), m2b = max3(m1[3], m1[4], m1[5]);
+        const float m2c = max3(m1[6], m1[7], m1[8]), m2d = fmaxf(m1[9], m1[10]);
+        if (fmaxf(max3(m2a, m2b, m2c), m2d) > thr) {        // rare once the list has warmed up
+          uint32_t mask = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
+          const int room = n_valid - col0;                  // columns >= n_valid are TMA zero fill past the library end
+          if (room < 32) mask &= (room <= 0) ? 0u : ((1u << room) - 1u);
+          while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            if (npend == TC_PQ) { ++n_drain; flush(); }
+            my_pqs[npend * TC_ROWS] = select32(v, j);
+            my_pqi[npend * TC_ROWS] = (int32_t)(tile_key0 + col0 + j);
+            ++npend;
+          }
+        }
+      };
+      uint32_t va[32], vb[32];
+      const bool do_filter = (a.debug == 0 || a.debug == 3);
+      if (a.debug == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+      } else {
+        tmem_ld32(taddr, va);
+        tmem_ld_wait_regs(va);
+#pragma unroll 1
+        for (int c = 0; c < TC_BN / 32; c += 2) {
+          tmem_ld32(taddr + (c + 1) * 32, vb);
+          if (do_filter) filter(va, c * 32);
+          tmem_ld_wait_regs(vb);
+          if (c + 2 < TC_BN / 32) {
+            tmem_ld32(taddr + (c + 2) * 32, va);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+          }
+          if (do_filter) filter(vb, (c + 1) * 32);
+          if (c + 2 < TC_BN / 32) tmem_ld_wait_regs(va);
+        }
+        if (npend) { ++n_drain; flush(); }
+      }
+      buf += 2;
+      if (buf >= NBUF) { buf -= NBUF; bph ^= 1u; }
+      if (a.debug == 3 && blockIdx.x == 0 && t < 512 && threadIdx.x == 0) { g_tc_trace[4 * t + 3] = clock64(); g_tc_trace2[2 * t] = n_drain; n_drain = 0; }
+    }
+    // ---- publish this split's list --------------------------------------------------------------
+    if (grow < a.Q) {
+      float* ps = a.part_s + ((int64_t)split * a.Q + grow) * KP;
+      int32_t* pi = a.part_i + ((int64_t)split * a.Q + grow) * KP;
+#pragma unroll
+      for (int p = 0; p < KP; ++p) { ps[p] = my_s[p * TC_ROWS]; pi[p] = my_i[p * TC_ROWS]; }
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_EPI_WARPS + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---- refine: exact fp32 re-score of the candidates + certificate ------------------------------------
 struct RefineArgs {
   const float* q; const float* keys; const float* q_inv_norm; const float* key_inv_norm;
@@ -614,26 +867,37 @@ struct TcPlan {
   size_t off_qbf, off_qinv, off_ps, off_pi, off_fb, off_fbn, off_f32, total;
 };
 
-bool tc_shape_ok(int d, int k) {
+// SS kernel shapes (query tile resident in shared memory)
+static bool tc_shape_ok_ss(int d, int k) {
   if (d < 1 || k < 1) return false;
   if (d <= 128) return k <= 26;
   if (d > 192 && d <= 256) return k <= 10;        // 128 KB of resident queries leave room for 16-entry lists only
   return false;
 }
+// TS kernel shapes (query tile resident in tensor memory): any d <= 256, k' = 16 or 32 slots per (row, split)
+bool tc_shape_ok(int d, int k) { return d >= 1 && d <= 256 && k >= 1 && k <= 26; }
 
-static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k) {
+// RAG_TC_VARIANT=ss selects the older shared-memory-A kernel where it is instantiated (A/B measurements only)
+static bool tc_use_ts(int d, int k) {
+  const char* e = getenv("RAG_TC_VARIANT");
+  return !(e && e[0] == 's' && e[1] == 's' && tc_shape_ok_ss(d, k));
+}
+
+static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts) {
   TcPlan p{};
   p.d_pad = (d + 63) / 64 * 64;
-  p.kh = p.d_pad / 64;                       // 1, 2, 3 (-> 4) or 4
-  if (p.kh == 3) p.kh = 4;                   // kernel instantiations: 1, 2, 4 (a zero K half costs nothing but time)
+  p.kh = p.d_pad / 64;                       // 1..4
+  if (!ts && p.kh == 3) p.kh = 4;            // SS instantiations: 1, 2, 4
   p.kp = (k <= 10) ? 16 : 32;
-  // shared memory: A 2*KH boxes + NSTAGE boxes + lists + barriers + 1 KB alignment slack  <= 227 KB
+  // shared memory: (SS: A 2*KH boxes +) NSTAGE boxes + lists + barriers + 1 KB alignment slack  <= 227 KB
   const int list_bytes = p.kp * TC_ROWS * 8 + TC_ROWS * 4 + TC_PQ * TC_ROWS * 8;   // lists + meta + pending queues
-  const int budget = 232448 - 1024 - 256 - list_bytes - 2 * p.kh * TC_BOX_BYTES;
+  const int a_boxes = ts ? 0 : 2 * p.kh;
+  const int budget = 232448 - 1024 - 256 - list_bytes - a_boxes * TC_BOX_BYTES;
   p.nstage = budget / TC_BOX_BYTES;
-  if (p.nstage > 8) p.nstage = 8;
+  const int cap = ts ? (p.kp == 16 ? 11 : 9) : 8;
+  if (p.nstage > cap) p.nstage = cap;
   if (p.nstage < 2) p.nstage = 2;
-  p.smem = 1024 + (size_t)(2 * p.kh + p.nstage) * TC_BOX_BYTES + list_bytes + 256;
+  p.smem = 1024 + (size_t)(a_boxes + p.nstage) * TC_BOX_BYTES + list_bytes + 256;
   p.n_qtiles = (int)((Q + TC_ROWS - 1) / TC_ROWS);
   p.n_tiles = (int)((N + TC_BN - 1) / TC_BN);
   int s = sm_count() / p.n_qtiles;
@@ -657,7 +921,7 @@ bool topk_tc_available(int d, int k) { return tc_shape_ok(d, k); }
 
 size_t topk_tc_workspace(int64_t Q, int64_t N, int d, int k, int mode) {
   if (!tc_shape_ok(d, k)) return 256;
-  return tc_plan(Q, N, d, k).total;
+  return tc_plan(Q, N, d, k, true).total;   // offsets do not depend on the variant
 }
 
 template <int KH, int NSTAGE, int KP>
@@ -670,15 +934,27 @@ static int launch_filter(const CUtensorMap& mq, const CUtensorMap& mk, const TcA
   return RAG_OK;
 }
 
+template <int KH, int NSTAGE, int KP>
+static int launch_filter_ts(const CUtensorMap& mk, const uint16_t* q_bf, const TcArgs& a, const TcPlan& p, cudaStream_t s) {
+  static_assert(sizeof(TsBarriers) <= 256, "barrier block");
+  auto kern = cosine_topk_ts_kernel<KH, NSTAGE, KP>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(cosine_topk_ts_kernel)");
+  kern<<<(unsigned)(p.n_qtiles * p.n_splits), TC_THREADS, p.smem, s>>>(mk, q_bf, a);
+  RAG_LAUNCH_OK("cosine_topk_ts_kernel");
+  return RAG_OK;
+}
+
 int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const uint16_t* keys_bf16,
                 int64_t N, int d, int k, int mode, uint32_t flags, int64_t idx_offset, float* out_scores,
                 int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
   RAG_REQUIRE(!(flags & RAG_SIM_DOT), RAG_EUNSUPPORTED, "cosine_topk: the tensor-core modes implement cosine only");
   RAG_REQUIRE(tc_shape_ok(d, k), RAG_EUNSUPPORTED,
-              "cosine_topk: tensor-core modes cover d <= 128 with k <= 26 and 192 < d <= 256 with k <= 10 (d=%d k=%d)", d, k);
+              "cosine_topk: tensor-core modes cover d <= 256 with k <= 26 (d=%d k=%d)", d, k);
   RAG_REQUIRE(key_inv_norm, RAG_EINVAL, "cosine_topk: the tensor-core modes need key_inv_norm (rag_row_inv_norm_f32)");
   RAG_REQUIRE(aligned16(keys_bf16), RAG_EALIGN, "cosine_topk: keys_bf16 must be 16-byte aligned");
-  TcPlan p = tc_plan(Q, N, d, k);
+  const bool ts = tc_use_ts(d, k);
+  TcPlan p = tc_plan(Q, N, d, k, ts);
   RAG_REQUIRE(ws_bytes >= p.total, RAG_EWORKSPACE, "cosine_topk: workspace %zu < %zu bytes", ws_bytes, p.total);
   RAG_REQUIRE(ws && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, RAG_EALIGN, "cosine_topk: workspace must be 256-byte aligned");
   RAG_REQUIRE(p.smem <= (size_t)max_smem_optin(), RAG_EUNSUPPORTED, "cosine_topk: needs %zu bytes of shared memory", p.smem);
@@ -696,8 +972,6 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(fb_count)");
 
   CUtensorMap mq, mk;
-  st = make_map_bf16(&mq, q_bf, Q, p.d_pad, 128);
-  if (st) return st;
   st = make_map_bf16(&mk, keys_bf16, N, p.d_pad, TC_BN);
   if (st) return st;
 
@@ -705,16 +979,26 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   a.Q = Q; a.N = N; a.n_qtiles = p.n_qtiles; a.n_splits = p.n_splits; a.tiles_per_split = p.tiles_per_split;
   a.n_tiles = p.n_tiles; a.kp = p.kp;
   { const char* dbg = getenv("RAG_TC_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
+  { const char* sw = getenv("RAG_TS_SWAP"); a.swap_halves = sw ? atoi(sw) : 0; }
   a.part_s = reinterpret_cast<float*>(w + p.off_ps);
   a.part_i = reinterpret_cast<int32_t*>(w + p.off_pi);
-  const int kh_real = p.d_pad / 64;
-  if (kh_real == 3) return fail(RAG_EUNSUPPORTED, "cosine_topk: d in (128,192] is not instantiated on the tensor-core path");
+  if (ts) {
+#define RAG_TS_CASE(KH_, NS_, KP_) \
+  if (p.kh == KH_ && p.nstage == NS_ && p.kp == KP_) st = launch_filter_ts<KH_, NS_, KP_>(mk, q_bf, a, p, s); else
+    RAG_TS_CASE(1, 11, 16) RAG_TS_CASE(1, 9, 32) RAG_TS_CASE(2, 11, 16) RAG_TS_CASE(2, 9, 32)
+    RAG_TS_CASE(3, 11, 16) RAG_TS_CASE(3, 9, 32) RAG_TS_CASE(4, 11, 16) RAG_TS_CASE(4, 9, 32)
+    return fail(RAG_EUNSUPPORTED, "cosine_topk: no tensor-core instantiation for kh=%d nstage=%d kp=%d", p.kh, p.nstage, p.kp);
+#undef RAG_TS_CASE
+  } else {
+    st = make_map_bf16(&mq, q_bf, Q, p.d_pad, 128);
+    if (st) return st;
 #define RAG_TC_CASE(KH_, NS_, KP_) \
   if (p.kh == KH_ && p.nstage == NS_ && p.kp == KP_) st = launch_filter<KH_, NS_, KP_>(mq, mk, a, p, s); else
-  RAG_TC_CASE(1, 8, 16) RAG_TC_CASE(1, 7, 32) RAG_TC_CASE(2, 7, 16) RAG_TC_CASE(2, 5, 32)
-  RAG_TC_CASE(4, 3, 16)
-  return fail(RAG_EUNSUPPORTED, "cosine_topk: no tensor-core instantiation for kh=%d nstage=%d kp=%d", p.kh, p.nstage, p.kp);
+    RAG_TC_CASE(1, 8, 16) RAG_TC_CASE(1, 7, 32) RAG_TC_CASE(2, 7, 16) RAG_TC_CASE(2, 5, 32)
+    RAG_TC_CASE(4, 3, 16)
+    return fail(RAG_EUNSUPPORTED, "cosine_topk: no tensor-core instantiation for kh=%d nstage=%d kp=%d", p.kh, p.nstage, p.kp);
 #undef RAG_TC_CASE
+  }
   if (st) return st;
 
   RefineArgs r{};

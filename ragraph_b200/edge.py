@@ -76,15 +76,22 @@ def edge_rag_forward(all_emb: Tensor, edges: Tensor, edge_norm: Tensor, resource
     n = all_emb.shape[0]
     agg = aggregator or EdgeAggregator(n)
     g = agg.csr(edges, edge_norm)
+    train = torch.is_grad_enabled() and all_emb.requires_grad
     layer, total = all_emb, all_emb
     for _ in range(num_layers):
-        layer = g.spmm(layer)
+        layer = g.spmm(layer)               # differentiable: backward is the same kernel on the cached transpose
         total = total + layer
-    out = torch.empty_like(total)
     if key_inv_norm is None:
         key_inv_norm = ops.row_inv_norm(resource_keys)
+    queries = all_emb.detach()              # indices are not differentiable; the library carries no grad (:186-226)
+    out = torch.empty_like(queries)
     for start in range(0, n, batch_size):
         end = min(start + batch_size, n)
-        _, idx = ops.cosine_topk(all_emb[start:end], resource_keys, retrieve_num, key_inv_norm, keys_bf16, mode)
-        out[start:end] = ops.gather_reduce(resource_values, idx, L.REDUCE_MEAN, total[start:end], retrieve_weight)
+        _, idx = ops.cosine_topk(queries[start:end], resource_keys, retrieve_num, key_inv_norm, keys_bf16, mode)
+        if train:
+            out[start:end] = ops.gather_reduce(resource_values, idx, L.REDUCE_MEAN)
+        else:
+            out[start:end] = ops.gather_reduce(resource_values, idx, L.REDUCE_MEAN, total[start:end], retrieve_weight)
+    if train:                               # gradient reaches all_emb through the layer sum only (:327-328)
+        return (1 - retrieve_weight) * total + retrieve_weight * out
     return out

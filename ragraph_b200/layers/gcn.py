@@ -26,7 +26,7 @@ class GCN(nn.Module):
             seq = seq[0]
         seq_fts = self.fc(seq)
         epi = L.EPI_PRELU | (L.EPI_BIAS if self.bias is not None else 0)
-        # forward only: every RAG script runs the backbone detached (preprompt.py:62); SpMM backward is a 'next' row
-        return as_csr(adj).spmm(seq_fts.detach(), epi,
-                                bias=None if self.bias is None else self.bias.detach(),
-                                alpha=self.act.weight.detach())
+        # one fused launch under no_grad / detached inputs; with grads enabled the aggregation is the autograd SpMM
+        # (dX = A^T dY, same kernel) and bias/PReLU are differentiable torch ops (few-shot decode,
+        # RAGraph_node_fewshot/RAGraph.py:69)
+        return as_csr(adj).spmm(seq_fts, epi, bias=self.bias, alpha=self.act.weight)

@@ -71,3 +71,31 @@ def test_fake_kernels_shape_inference():
     assert s.shape == (5, 3) and i.dtype == torch.int64
     g = torch.ops.ragraph.gather_rows(keys, torch.empty(5, 3, dtype=torch.int64, device="meta"))
     assert g.shape == (5, 3, 16)
+
+
+def test_csr_transpose_and_row_normalized_host_logic():
+    """CSRGraph.transpose / row_normalized are torch index plumbing (no kernel): check them against scipy on CPU."""
+    import numpy as np
+    import scipy.sparse as sp
+    from ragraph_b200.csr import CSRGraph
+    rng = np.random.default_rng(3)
+    n, m, nnz = 50, 37, 400
+    rows = np.sort(rng.integers(0, n, nnz)); cols = rng.integers(0, m, nnz); vals = rng.random(nnz).astype(np.float32) + 0.1
+    rowptr = np.zeros(n + 1, np.int64); np.add.at(rowptr, rows + 1, 1); rowptr = np.cumsum(rowptr)
+    g = CSRGraph(torch.from_numpy(rowptr), torch.from_numpy(cols.astype(np.int32)), torch.from_numpy(vals), n, m)
+    A = sp.csr_matrix((vals, cols, rowptr), shape=(n, m))
+    t = g.transpose()
+    assert t.n_rows == m and t.n_cols == n and t.transpose() is g
+    At = sp.csr_matrix((t.val.numpy(), t.col.numpy(), t.rowptr.numpy()), shape=(m, n))
+    assert np.array_equal(At.toarray(), A.T.toarray())
+    # entries of every transposed row are ordered by original row (fixed summation order in the backward SpMM)
+    for r in range(m):
+        seg = t.col[t.rowptr[r]:t.rowptr[r + 1]].numpy()
+        assert np.all(np.diff(seg) >= 0)
+    rn = g.row_normalized()
+    dense = A.toarray(); deg = dense.sum(1, keepdims=True)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        want = dense / deg
+    got = sp.csr_matrix((rn.val.numpy(), rn.col.numpy(), rn.rowptr.numpy()), shape=(n, m)).toarray()
+    ok = deg[:, 0] > 0
+    assert np.allclose(got[ok], want[ok], rtol=1e-6)

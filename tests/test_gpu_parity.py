@@ -324,6 +324,74 @@ def test_edge_forward_golden(golden):
     assert O.rel_err(out, g["out"]) < REL
 
 
+# ------------------------------------------------------------------------------------------ autograd
+def test_spmm_backward_matches_dense_autograd():
+    """dX = A^T dY through the same kernel on the transposed CSR vs torch's dense autograd (fp64 arbiter)."""
+    torch.manual_seed(5)
+    n, m, F = 700, 500, 64
+    dense = (torch.rand(n, m, device=DEV) < 0.02).float() * torch.rand(n, m, device=DEV)
+    dense[3] = 0.0                                                  # empty row
+    g = R.CSRGraph.from_dense(dense)
+    x = torch.randn(m, F, device=DEV, requires_grad=True)
+    up = torch.randn(n, F, device=DEV)
+    y = g.spmm(x)
+    assert y.requires_grad
+    (y * up).sum().backward()
+    x64 = x.detach().double().requires_grad_(True)
+    ((dense.double() @ x64) * up.double()).sum().backward()
+    assert O.rel_err(y.detach().cpu().numpy(), (dense.double() @ x64.detach()).cpu().numpy()) < REL
+    assert O.rel_err(x.grad.cpu().numpy(), x64.grad.cpu().numpy()) < REL
+
+
+def test_spmm_epilogues_differentiable_match_fused():
+    """Training-mode (unfused, differentiable) epilogues give the same values as the fused launch, and their
+    gradients match torch autograd on the dense formulation (Propagation.py:15-25, layers/gcn.py:32-40)."""
+    torch.manual_seed(6)
+    n, F = 400, 32
+    dense = (torch.rand(n, n, device=DEV) < 0.03).float() * (torch.rand(n, n, device=DEV) + 0.1) + torch.eye(n, device=DEV)
+    g = R.CSRGraph.from_dense(dense)
+    x = torch.randn(n, F, device=DEV)
+    bias = torch.randn(F, device=DEV); alpha = torch.tensor([0.25], device=DEV)
+    for epi, kw in ((L.EPI_ROWNORM | L.EPI_RELU, {}), (L.EPI_BIAS | L.EPI_PRELU, {"bias": bias, "alpha": alpha})):
+        with torch.no_grad():
+            fused = g.spmm(x, epi, **kw)
+        xg = x.clone().requires_grad_(True)
+        kwg = {k: v.clone().requires_grad_(True) for k, v in kw.items()}
+        out = g.spmm(xg, epi, **kwg)
+        assert O.rel_err(out.detach().cpu().numpy(), fused.cpu().numpy()) < REL
+        out.square().sum().backward()
+        x64 = x.double().requires_grad_(True)
+        if epi & L.EPI_ROWNORM:
+            ref = torch.relu((dense.double() / dense.double().sum(1, keepdim=True)) @ x64)
+        else:
+            z = dense.double() @ x64 + bias.double()
+            ref = torch.where(z >= 0, z, 0.25 * z)
+        ref.square().sum().backward()
+        assert O.rel_err(xg.grad.cpu().numpy(), x64.grad.cpu().numpy()) < 1e-4
+
+
+def test_edge_forward_training_grads(golden):
+    """edge cal_loss path (modules/RAGraph.py:265-350): gradient w.r.t. the embedding table through 3 x _agg and
+    the retrieval blend equals torch autograd over the reference formulation (gather * w -> index_add)."""
+    g = golden("edge_forward")
+    w = cu(g["w"]) * 0.5 + cu(g["time_norm"]) * 0.5
+    X = cu(g["X"]).clone().requires_grad_(True)
+    edges = cu(g["edges"])
+    out = R.edge_rag_forward(X, edges, w, cu(g["keys"]), cu(g["values"]), int(g["num_layers"]),
+                             int(g["retrieve_num"]), int(g["batch_size"]), float(g["retrieve_weight"]))
+    assert O.rel_err(out.detach().cpu().numpy(), g["out"]) < REL
+    up = torch.randn_like(out)
+    (out * up).sum().backward()
+    X64 = cu(g["X"]).double().requires_grad_(True)
+    layer, total = X64, X64
+    for _ in range(int(g["num_layers"])):
+        msg = layer[edges[:, 0]] * w.double()[:, None]
+        layer = torch.zeros_like(X64).index_add(0, edges[:, 1], msg)
+        total = total + layer
+    ((1 - float(g["retrieve_weight"])) * total * up.double()).sum().backward()
+    assert O.rel_err(X.grad.cpu().numpy(), X64.grad.cpu().numpy()) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------ size-independent properties
 def test_large_properties():
     """Sizes the CPU oracle cannot finish quickly: check invariants instead."""

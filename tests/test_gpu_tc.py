@@ -7,8 +7,17 @@ from ragraph_b200 import _lib as L
 from ragraph_b200 import ops
 from oracle import ragraph_oracle as O
 
+import os
+
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 DEV = "cuda"
+
+
+@pytest.fixture(params=["ts", "ss"], autouse=True)
+def tc_variant(request, monkeypatch):
+    """ts = query tile stationary in tensor memory (default); ss = the shared-memory-A kernel (A/B reference)."""
+    monkeypatch.setenv("RAG_TC_VARIANT", request.param)
+    return request.param
 
 
 def _run(q, keys, k, mode):
@@ -22,7 +31,8 @@ def _run(q, keys, k, mode):
 
 @pytest.mark.parametrize("Q,N,d,k", [(300, 20000, 128, 10), (700, 100000, 64, 10), (1000, 50000, 256, 10),
                                      (37, 5000, 128, 20), (256, 128, 128, 4), (5, 333, 100, 3), (513, 70001, 128, 10),
-                                     (64, 3000, 32, 26)])
+                                     (64, 3000, 32, 26), (260, 30000, 160, 10), (300, 40000, 256, 20),
+                                     (1100, 60000, 128, 10)])
 def test_refine_mode_is_exact(Q, N, d, k):
     g = torch.Generator().manual_seed(Q + N + d)
     q = torch.randn(Q, d, generator=g); keys = torch.randn(N, d, generator=g)
@@ -72,8 +82,8 @@ def test_bf16_raw_mode_recall():
 
 
 def test_tc_unsupported_shapes_raise():
-    q, keys = torch.randn(8, 160, device=DEV), torch.randn(1000, 160, device=DEV)
-    assert not L.load().rag_sim_mode_supported(L.SIM_BF16_REFINE, 160, 10)
+    q, keys = torch.randn(8, 320, device=DEV), torch.randn(1000, 320, device=DEV)
+    assert not L.load().rag_sim_mode_supported(L.SIM_BF16_REFINE, 320, 10)
     with pytest.raises(L.RagError, match="RAG_EUNSUPPORTED"):
         ops.cosine_topk(q, keys, 10, key_inv_norm=ops.row_inv_norm(keys), keys_bf16=ops.rows_to_bf16(keys), mode=3)
     with pytest.raises(L.RagError, match="RAG_EINVAL"):
