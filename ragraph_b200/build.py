@@ -34,7 +34,8 @@ def _deps_mtime():
     return max(os.path.getmtime(h) for h in hdrs)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """trace=True compiles the pipeline-trace instrumentation into the tensor-core kernels (diagnostics only)."""
     os.makedirs(OBJDIR, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
     hdr_m = _deps_mtime()
@@ -47,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         s, o = job
-        cmd = [NVCC, *ARCH, *CFLAGS, "-c", s, "-o", o]
+        cmd = [NVCC, *ARCH, *CFLAGS, *(["-DRAG_TC_TRACE_BUILD=1"] if trace else []), "-c", s, "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -71,4 +72,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv or "--trace" in sys.argv, verbose="--verbose" in sys.argv, trace="--trace" in sys.argv))

@@ -43,14 +43,21 @@ constexpr int TC_ROWS = 256;          // query rows per CTA (2 row blocks of 128
 constexpr int TC_BN = 128;            // keys per tile
 constexpr int TC_BOX_BYTES = 128 * 128;   // one TMA box: 128 rows x 64 bf16
 constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;     // SS kernel: 8 epilogue warps + TMA + MMA
+constexpr int TS_THREADS = (TC_EPI_WARPS + 3) * 32;     // TS kernel: 8 epilogue warps + TMA + 2 MMA issuers
 constexpr int TC_PQ = 4;               // per-row pending-candidate queue depth (drained after the TMEM hand-back)
 constexpr float TC_EPS = 0.00390625f + 0.0009765625f;   // 2^-8 (bf16 x bf16, unit vectors) + 2^-10 slack (fp32 sums)
 constexpr unsigned long long TC_TIMEOUT_CYCLES = 20000000000ull;   // ~10 s: trap instead of hanging the GPU
 
-// profiling trace (RAG_TC_DEBUG=3): CTA 0 stamps clock64 at pipeline events of its first 512 tiles
+// profiling trace: built only with -DRAG_TC_TRACE_BUILD=1 (python -m ragraph_b200.build --trace); the production
+// kernel carries no trace registers.  CTA 0 stamps clock64 at pipeline events of a 512-tile window (RAG_TC_TRACE=1)
+#ifndef RAG_TC_TRACE_BUILD
+#define RAG_TC_TRACE_BUILD 0
+#endif
+#define TC_TRACE_ON(a) (RAG_TC_TRACE_BUILD && (a).trace)
 __device__ unsigned long long g_tc_trace[4 * 512];
-__device__ unsigned int g_tc_trace2[2 * 512];   // per tile: drains by warp 0, cycles from tmem_full to tmem_empty arrive
+__device__ unsigned int g_tc_trace2[2 * 512];
+__device__ unsigned int g_tc_trace3[16 * 256];  // MMA-thread micro-trace (TS kernel): 16 clock stamps per tile, first 256 tiles of the window   // per tile: drains by warp 0, cycles from tmem_full to tmem_empty arrive
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,14 +75,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+               : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ bool mbar_test(uint32_t addr, uint32_t parity) {     // non-blocking probe
+  uint32_t done;
+  asm volatile("{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+               : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
+  if (mbar_try(addr, parity)) return;                    // common case: no clock read on the critical path
   const unsigned long long t0 = clock64();
-  while (true) {
-    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
-                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (done) break;
+  while (!mbar_try(addr, parity)) {
     if (clock64() - t0 > TC_TIMEOUT_CYCLES) __trap();     // a broken pipeline must fail loudly, not hang
   }
 }
@@ -124,6 +140,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // v[] can be scheduled above it when another chunk's load is issued in between (software pipelining)
 __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :: "memory");
+}
+// no instruction: makes the compiler treat v[] as redefined here, so consumers stay below the preceding volatile wait
+__device__ __forceinline__ void tie_regs(uint32_t (&v)[32]) {
+  asm volatile(""
                : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
                  "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
                  "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
@@ -203,6 +228,14 @@ struct TcArgs {
   int n_qtiles; int n_splits; int tiles_per_split; int n_tiles;
   int kp;                          // list length per (row, split)
   float* part_s; int32_t* part_i;  // [n_splits][Q][kp]
+  // threshold pre-pass (TS kernel): premax = 1 runs only the first pre_tiles tiles of every split and records, per query
+  // row, the maximum score of pre_groups consecutive tile groups into gmax[(split * pre_groups + g) * Q + row]; the main
+  // pass then starts every row at thr0[row] (a proven lower bound of its final kp-th best score) instead of -inf
+  int premax; int pre_tiles; int pre_groups;
+  float* gmax; const float* thr0;
+  int trace;                       // RAG_TC_DEBUG=3 or RAG_TC_TRACE=1: CTA 0 stamps clock64 at pipeline events (g_tc_trace)
+  int trace_t0;                    // RAG_TC_TRACE_T0: first traced tile (window of 512)
+  int no_tma;                      // RAG_TC_NOTMA=1 (experiment): the producer arrives without loading keys (garbage operands)
   int swap_halves;                 // RAG_TS_SWAP=1 (diagnostic): swap the bf16 halves of every A word stored to TMEM
   int debug;                       // RAG_TC_DEBUG (profiling experiments only): 1 = epilogue skips TMEM reads, 2 = reads but skips the filter
 };
@@ -297,7 +330,7 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           for (int rb = 0; rb < 2; ++rb) {
             mbar_wait(&bars->tmem_empty[b][rb], use_parity ^ 1u);
             tc_fence_after();
-            if (a.debug == 3 && blockIdx.x == 0 && t < 512 && rb == 0) g_tc_trace[4 * t + 0] = clock64();
+            if (TC_TRACE_ON(a) && blockIdx.x == 0 && (unsigned)(t - a.trace_t0) < 512u && rb == 0) g_tc_trace[4 * (t - a.trace_t0) + 0] = clock64();
             int sk = s; uint32_t phk = ph;
             for (int kh = 0; kh < KH; ++kh) {
               if (rb == 0) { mbar_wait(&bars->full[sk], phk); tc_fence_after(); }
@@ -339,7 +372,7 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           tc_commit(&bars->tmem_full[b][0]);
           tc_commit(&bars->tmem_full[b][1]);
         }
-        if (a.debug == 3 && blockIdx.x == 0 && t < 512) g_tc_trace[4 * t + 1] = clock64();
+        if (TC_TRACE_ON(a) && blockIdx.x == 0 && (unsigned)(t - a.trace_t0) < 512u) g_tc_trace[4 * (t - a.trace_t0) + 1] = clock64();
       }
     }
   } else if (warp < TC_EPI_WARPS) {
@@ -359,7 +392,7 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       const int b = t & 1;
       mbar_wait(&bars->tmem_full[b][rb], ((uint32_t)t >> 1) & 1u);
       tc_fence_after();
-      if (a.debug == 3 && blockIdx.x == 0 && t < 512 && threadIdx.x == 0) g_tc_trace[4 * t + 2] = clock64();
+      if (TC_TRACE_ON(a) && blockIdx.x == 0 && (unsigned)(t - a.trace_t0) < 512u && threadIdx.x == 0) g_tc_trace[4 * (t - a.trace_t0) + 2] = clock64();
       const int64_t tile_key0 = key_base + (int64_t)t * TC_BN;
       const int n_valid = (int)min((int64_t)TC_BN, a.N - tile_key0);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((b * 2 + rb) * TC_BN);
@@ -400,7 +433,7 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         }
       };
       uint32_t va[32], vb[32];
-      const bool do_filter = (a.debug == 0 || a.debug == 3);
+      const bool do_filter = (a.debug == 0);
       if (a.debug == 1) {
         tc_fence_before();
         __syncwarp();
@@ -427,7 +460,7 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         }
         if (npend) { ++n_drain; flush(); }
       }
-      if (a.debug == 3 && blockIdx.x == 0 && t < 512 && threadIdx.x == 0) { g_tc_trace[4 * t + 3] = clock64(); g_tc_trace2[2 * t] = n_drain; n_drain = 0; }
+      if (TC_TRACE_ON(a) && blockIdx.x == 0 && (unsigned)(t - a.trace_t0) < 512u && threadIdx.x == 0) { g_tc_trace[4 * (t - a.trace_t0) + 3] = clock64(); g_tc_trace2[2 * (t - a.trace_t0)] = n_drain; n_drain = 0; }
     }
     // ---- publish this split's list --------------------------------------------------------------
     const int64_t grow = (int64_t)qtile * TC_ROWS + row;
@@ -460,14 +493,19 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 // memory the query tile occupied becomes pipeline depth (11 stages).
 // TMEM budget (512 columns): A = 2 row blocks x d_pad/2 columns at the top, accumulators = a ring of
 // NBUF = (512 - d_pad) / 128 buffers of 128 columns; "use" u = 2*tile + row_block takes buffer u % NBUF.
+// Accumulator hand-off barriers are per (buffer, row block): with an odd ring a buffer alternates between the two
+// row blocks, and a parity wait is only safe when ONE party consumes every completion of a barrier in order (a
+// waiter that arrives a full phase early would otherwise see the stale parity of the previous-but-one completion --
+// possible once two issuer warps run skewed).
 struct __align__(8) TsBarriers {
   uint64_t a_full;
   uint64_t full[12];
   uint64_t empty[12];
-  uint64_t tmem_full[3];
-  uint64_t tmem_empty[3];
+  uint64_t tmem_full[3][2];
+  uint64_t tmem_empty[3][2];
   uint32_t tmem_base;
 };
+constexpr int TS_BAR_BYTES = 512;
 
 __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -482,46 +520,181 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
                : "memory");
 }
 
-template <int KH, int NSTAGE, int KP>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// ---- selection state of the TS kernel ---------------------------------------------------------------
+// Per (query row, key split): a SORTED list of the KP best (score, key) seen so far plus an append buffer of KP pending
+// candidates, both in shared memory with entry p of row r at [p * TS_LSTRIDE + r] (stride 257: a whole warp reading ONE
+// row is bank-conflict free).
+//  * Fast path, registers only: each lane (= query row) reduces its 128 scores of the tile to four chunk maxima,
+//    compares with its threshold (thr = the row's KP-th best at its last compaction, or the pre-pass bound) and the
+//    warp votes once per tile.
+//  * A hit ((lane, 32-score chunk) with a maximum above thr) costs the tile loop only a copy of the chunk into the
+//    warp's hit QUEUE (static register indices, independent stores).  A lone warp runs dependent code at ~6 cycles per
+//    instruction (measured), so anything serial done here delays the warp's next TMEM drain and, through the
+//    accumulator ring, the tensor pipe.
+//  * Queued hits are served when the warp would otherwise wait for its next accumulator: all 32 lanes take one score
+//    each, compare with the owner row's current threshold, and the candidates append themselves at ballot-derived
+//    slots -- no per-lane serial scan, no dynamic register indexing.
+//  * When a buffer fills, the warp compacts that row together: every lane ranks one (KP = 16) or two (KP = 32) of the
+//    2*KP entries against all others (rank = number of entries that precede it; ties broken by position, so ranks are
+//    a permutation), entries ranked below KP are stored back at slot = rank and the new threshold is the entry ranked
+//    KP-1.  A frozen threshold admits candidates at the rate it had when it was set, so a row is compacted about once
+//    per doubling of the keys seen, instead of one replace-min list update per candidate.
+constexpr int TS_LSTRIDE = TC_ROWS + 1;
+constexpr int TS_QN = 16;                 // hit-queue entries per epilogue warp
+constexpr int TS_QSTRIDE = 36;            // 32 scores + first key index + (owner lane | valid columns << 8), 16 B aligned
+constexpr int TS_QUEUE_BYTES = TC_EPI_WARPS * TS_QN * TS_QSTRIDE * 4;
+
+template <int KP>
+__device__ __forceinline__ float ts_compact_row(float* ls, int32_t* li, float* ps, int32_t* pi, int row, int npend, int lane) {
+  // Every lane reads all 2*KP scores of the row straight from shared memory (broadcast loads: independent, pipelined)
+  // instead of pulling them one shuffle at a time -- the shuffle version spent ~60 cycles per entry on latency.
+  constexpr unsigned FULL = 0xffffffffu;
+  if constexpr (KP == 16) {
+    const bool is_list = lane < 16;
+    const int slot = lane & 15;
+    const bool valid = is_list || slot < npend;
+    const float s = valid ? (is_list ? ls : ps)[slot * TS_LSTRIDE + row] : -INFINITY;
+    const int32_t id = valid ? (is_list ? li : pi)[slot * TS_LSTRIDE + row] : -1;
+    int rank = 0;
+#pragma unroll 8
+    for (int m = 0; m < 16; ++m) {                          // positions 0..15: the sorted list
+      const float a = ls[m * TS_LSTRIDE + row];
+      rank += (a > s || (a == s && m < lane)) ? 1 : 0;
+    }
+#pragma unroll 8
+    for (int m = 0; m < 16; ++m) {                          // positions 16..31: the append buffer
+      const float a = (m < npend) ? ps[m * TS_LSTRIDE + row] : -INFINITY;
+      rank += (a > s || (a == s && 16 + m < lane)) ? 1 : 0;
+    }
+    __syncwarp();                                           // all reads of the row happen before any write
+    if (rank < 16) { ls[rank * TS_LSTRIDE + row] = s; li[rank * TS_LSTRIDE + row] = id; }
+    __syncwarp();
+    return ls[15 * TS_LSTRIDE + row];                       // the new KP-th best
+  } else {
+    static_assert(KP == 32, "list lengths: 16 or 32");
+    const float s0 = ls[lane * TS_LSTRIDE + row];                       // list entry `lane`     (position lane)
+    const int32_t i0 = li[lane * TS_LSTRIDE + row];
+    const bool v1 = lane < npend;
+    const float s1 = v1 ? ps[lane * TS_LSTRIDE + row] : -INFINITY;      // pending entry `lane`  (position 32 + lane)
+    const int32_t i1 = v1 ? pi[lane * TS_LSTRIDE + row] : -1;
+    int r0 = 0, r1 = 0;
+#pragma unroll 8
+    for (int m = 0; m < 32; ++m) {
+      const float a0 = ls[m * TS_LSTRIDE + row], a1 = (m < npend) ? ps[m * TS_LSTRIDE + row] : -INFINITY;
+      r0 += ((a0 > s0 || (a0 == s0 && m < lane)) ? 1 : 0) + ((a1 > s0) ? 1 : 0);
+      r1 += ((a0 >= s1) ? 1 : 0) + ((a1 > s1 || (a1 == s1 && m < lane)) ? 1 : 0);
+    }
+    __syncwarp();
+    if (r0 < 32) { ls[r0 * TS_LSTRIDE + row] = s0; li[r0 * TS_LSTRIDE + row] = i0; }
+    if (r1 < 32) { ls[r1 * TS_LSTRIDE + row] = s1; li[r1 * TS_LSTRIDE + row] = i1; }
+    __syncwarp();
+    return ls[31 * TS_LSTRIDE + row];
+  }
+}
+
+// Serve one queued hit (all 32 lanes): lane j takes score j of the 32-score chunk, compares it with the owner row's
+// current threshold, and the candidates append themselves at ballot-derived slots of the owner's buffer; a full buffer
+// is compacted on the spot.  Returns the owner's new (threshold, pending count); `owner` = the owner lane.
+struct TsServed { float thr; int np; int owner; };
+template <int KP>
+__device__ __forceinline__ TsServed ts_serve_entry(const float* ev, float* ls, int32_t* li, float* ps, int32_t* pi, int wrow0,
+                                                   float thr, int npend, int lane) {
+  const int key0 = __float_as_int(ev[32]);
+  const int meta = __float_as_int(ev[33]);
+  const int L = meta & 31, nv = meta >> 8;
+  const float val = ev[lane];
+  float thr_l = __shfl_sync(0xffffffffu, thr, L);
+  int np = __shfl_sync(0xffffffffu, npend, L);
+  bool cand = val > thr_l && lane < nv;                     // columns >= nv are TMA zero fill past the library end
+  const int orow = wrow0 + L;
+  while (true) {
+    const unsigned cm = __ballot_sync(0xffffffffu, cand);
+    if (cm == 0) break;
+    const int pos = np + __popc(cm & ((1u << lane) - 1u));
+    const bool fit = cand && pos < KP;
+    if (fit) {
+      ps[pos * TS_LSTRIDE + orow] = val;
+      pi[pos * TS_LSTRIDE + orow] = key0 + lane;
+    }
+    np = min(np + __popc(cm), KP);
+    cand = cand && !fit;
+    if (__ballot_sync(0xffffffffu, cand) == 0) break;
+    __syncwarp();                                           // buffer full with candidates left: compact the row, go on
+    thr_l = ts_compact_row<KP>(ls, li, ps, pi, orow, KP, lane);
+    np = 0;
+    cand = cand && val > thr_l;
+  }
+  return TsServed{thr_l, np, L};
+}
+__device__ __forceinline__ float chunk_max32(const uint32_t (&v)[32]) {
+  float m1[11];
+#pragma unroll
+  for (int j = 0; j < 10; ++j)
+    m1[j] = max3(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
+  m1[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+  const float m2a = max3(m1[0], m1[1], m1[2]), m2b = max3(m1[3], m1[4], m1[5]);
+  const float m2c = max3(m1[6], m1[7], m1[8]), m2d = fmaxf(m1[9], m1[10]);
+  return fmaxf(max3(m2a, m2b, m2c), m2d);
+}
+// one queue entry: 8 x 128-bit stores of the chunk (static register indices) + one 64-bit header store
+__device__ __forceinline__ void queue_put(float* entry, const uint32_t (&v)[32], int key0, int meta) {
+  uint4* e4 = reinterpret_cast<uint4*>(entry);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) e4[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  *reinterpret_cast<int2*>(entry + 32) = make_int2(key0, meta);
+}
+
+// Epilogue: a warp pulls its whole 32 x 128 accumulator slice into registers (4 x tcgen05.ld.x32, one wait) and hands
+// the TMEM buffer back BEFORE it filters, so the MMA issuers never wait on selection work.
+// PRE = true: threshold pre-pass instantiation (group maxima only, see TcArgs::premax)
+template <int KH, int NSTAGE, int KP, bool PRE>
+__global__ void __launch_bounds__(TS_THREADS, 1)
 cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t* __restrict__ q_bf, const TcArgs a) {
   constexpr int A_COLS = 2 * KH * 32;                 // 32-bit TMEM columns of the resident query tile
   constexpr int NBUF = (512 - A_COLS) / TC_BN;        // accumulator ring: 3 (d <= 128) or 2 (d <= 256)
   constexpr uint32_t A_COL0 = NBUF * TC_BN;
   static_assert(NBUF >= 2 && NBUF <= 3, "accumulator ring");
+  // issuer warps: 2 with the ring of 3; with NBUF = 2 (one buffer per row block, d > 128) consecutive tiles of a row
+  // block are serialised through ONE barrier, which only a single in-order waiter may follow by parity -- and a tile
+  // is 2048+ tensor cycles there, so one issuer keeps up
+  constexpr int NISS = (NBUF == 3) ? 2 : 1;
   static_assert(NSTAGE >= 2 * KH && NSTAGE <= 12, "row-block-major MMA order holds a tile's stages for the whole tile");
-  extern __shared__ unsigned char smem_dyn[];
-  // carve: [B: NSTAGE boxes][lists: KP x 256 x (f32 + i32)][meta][pending queues][barriers]
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  unsigned char* sB = base;
-  float* list_s = reinterpret_cast<float*>(sB + NSTAGE * TC_BOX_BYTES);    // [KP][256]
-  int32_t* list_i = reinterpret_cast<int32_t*>(list_s + KP * TC_ROWS);     // [KP][256]
-  int32_t* list_meta = list_i + KP * TC_ROWS;                              // [256]
-  float* pq_s = reinterpret_cast<float*>(list_meta + TC_ROWS);             // [TC_PQ][256] pending scores
-  int32_t* pq_i = reinterpret_cast<int32_t*>(pq_s + TC_PQ * TC_ROWS);      // [TC_PQ][256] pending indices
-  TsBarriers* bars = reinterpret_cast<TsBarriers*>(pq_i + TC_PQ * TC_ROWS);
+  // Offsets are taken from the extern array itself (no integer round trip), so every list / queue access below stays
+  // in the shared address space (LDS/STS, not generic LD/ST).  The dynamic window starts 1 KB-aligned when the kernel
+  // has no static shared memory; checked once below.
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  // carve: [B: NSTAGE boxes][sorted lists: KP x 257 x (f32 + i32)][append buffers: same][warp hit queues][barriers]
+  unsigned char* sB = smem_dyn;
+  float* list_s = reinterpret_cast<float*>(smem_dyn + NSTAGE * TC_BOX_BYTES);
+  int32_t* list_i = reinterpret_cast<int32_t*>(list_s + KP * TS_LSTRIDE);
+  float* pq_s = reinterpret_cast<float*>(list_i + KP * TS_LSTRIDE);
+  int32_t* pq_i = reinterpret_cast<int32_t*>(pq_s + KP * TS_LSTRIDE);
+  float* queue = reinterpret_cast<float*>(pq_i + KP * TS_LSTRIDE);        // [8 warps][TS_QN][TS_QSTRIDE]
+  constexpr int BAR_OFF = (NSTAGE * TC_BOX_BYTES + 4 * KP * TS_LSTRIDE * 4 + TS_QUEUE_BYTES + 15) / 16 * 16;
+  TsBarriers* bars = reinterpret_cast<TsBarriers*>(smem_dyn + BAR_OFF);
+  if (threadIdx.x == 0 && (smem_u32(smem_dyn) & 1023u) != 0) __trap();     // TMA SWIZZLE_128B boxes need 1 KB alignment
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qtile = blockIdx.x % a.n_qtiles;
   const int split = blockIdx.x / a.n_qtiles;
   const int tile0 = split * a.tiles_per_split;
   const int tile1 = min(tile0 + a.tiles_per_split, a.n_tiles);
-  const int n_my_tiles = max(tile1 - tile0, 0);
+  const int n_my_tiles = PRE ? min(max(tile1 - tile0, 0), a.pre_tiles) : max(tile1 - tile0, 0);
 
   // ---- one-time setup ---------------------------------------------------------------------------
   if (warp == TC_EPI_WARPS && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
     mbar_init(&bars->a_full, TC_EPI_WARPS);
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    for (int b = 0; b < NBUF; ++b) { mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], TC_EPI_WARPS / 2); }
+    for (int b = 0; b < NBUF; ++b)
+      for (int r = 0; r < 2; ++r) { mbar_init(&bars->tmem_full[b][r], 1); mbar_init(&bars->tmem_empty[b][r], TC_EPI_WARPS / 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_EPI_WARPS + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < KP * TC_ROWS; i += TC_THREADS) { list_s[i] = -INFINITY; list_i[i] = -1; }
-  for (int i = threadIdx.x; i < TC_ROWS; i += TC_THREADS) list_meta[i] = 0;
+  for (int i = threadIdx.x; i < KP * TS_LSTRIDE; i += TS_THREADS) { list_s[i] = -INFINITY; list_i[i] = -1; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -534,45 +707,83 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
       for (int t = 0; t < n_my_tiles; ++t) {
         for (int kh = 0; kh < KH; ++kh) {
           mbar_wait(&bars->empty[s], ph ^ 1);
-          mbar_expect_tx(&bars->full[s], TC_BOX_BYTES);
-          tma_load_2d(sB + s * TC_BOX_BYTES, &map_k, kh * 64, (tile0 + t) * TC_BN, &bars->full[s]);
+          if (a.no_tma) { mbar_arrive(&bars->full[s]); }
+          else {
+            mbar_expect_tx(&bars->full[s], TC_BOX_BYTES);
+            tma_load_2d(sB + s * TC_BOX_BYTES, &map_k, kh * 64, (tile0 + t) * TC_BN, &bars->full[s]);
+          }
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == TC_EPI_WARPS + 1) {
-    // =============================== MMA issuer (A from TMEM) ===================================
-    if (elect_one()) {
+  } else if (warp >= TC_EPI_WARPS + 1) {
+    // =============================== MMA issuers (A from TMEM) ==================================
+    // The issuing thread's own latencies (four mbarrier waits, fences and four commits per tile, ~1300 cycles
+    // measured) exceed the 1024 cycles the tensor pipe needs for a d=128 tile, so ONE issuer leaves the pipe idle a
+    // quarter of the time.  Two issuer warps take alternate key tiles (mw = 0: even, 1: odd); each walks the stage
+    // ring and the accumulator ring in steps of two tiles.  tcgen05.commit tracks the MMAs of the executing thread,
+    // so every barrier is still completed by exactly one commit.
+    const int mw = warp - (TC_EPI_WARPS + 1);
+    if (mw < NISS && elect_one()) {
       mbar_wait(&bars->a_full, 0);
       tc_fence_after();
       const uint32_t b_addr = smem_u32(sB);
-      int s = 0; uint32_t ph = 0;
-      int buf = 0; uint32_t bph = 0;
-      for (int t = 0; t < n_my_tiles; ++t) {
-#pragma unroll
-        for (int rb = 0; rb < 2; ++rb) {
-          mbar_wait(&bars->tmem_empty[buf], bph ^ 1u);
-          tc_fence_after();
-          if (a.debug == 3 && blockIdx.x == 0 && t < 512 && rb == 0) g_tc_trace[4 * t + 0] = clock64();
+      int s = mw * KH; uint32_t ph = 0;
+      while (s >= NSTAGE) { s -= NSTAGE; ph ^= 1; }
+      for (int t = mw; t < n_my_tiles; t += NISS) {
+        const bool tr3 = TC_TRACE_ON(a) && blockIdx.x == 0 && (unsigned)(t - a.trace_t0) < 256u;
+        unsigned int* t3 = g_tc_trace3 + 16 * (tr3 ? (t - a.trace_t0) : 0);
+        if (tr3) t3[0] = (unsigned int)clock64();
+        // The tile's key boxes land long before its accumulators are free: take those waits FIRST, so that the critical
+        // hand-off (epilogue releases a buffer -> first MMA of the next use enters the pipe) is one barrier wake-up plus
+        // the MMA issue, not three wake-ups.
+        {
           int sk = s; uint32_t phk = ph;
           for (int kh = 0; kh < KH; ++kh) {
-            if (rb == 0) { mbar_wait(&bars->full[sk], phk); tc_fence_after(); }
+            mbar_wait(&bars->full[sk], phk);
+            if (++sk == NSTAGE) { sk = 0; phk ^= 1; }
+          }
+          if (tr3) t3[2] = (unsigned int)clock64();
+        }
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+          // use u = 2t + rb takes buffer u % NBUF; its previous user was use u - NBUF (row block (u - NBUF) & 1,
+          // that row block's k'-th visit of the buffer): wait until its epilogue has drained it
+          const uint32_t u = 2u * (uint32_t)t + (uint32_t)rb;
+          const uint32_t buf = (NBUF == 2) ? (u & 1u) : (u % 3u);
+          if (u >= (uint32_t)NBUF) {
+            const uint32_t up = u - NBUF, tp = up >> 1;
+            mbar_wait(&bars->tmem_empty[buf][up & 1u], ((NBUF == 2) ? tp : tp / 3u) & 1u);
+          }
+          tc_fence_after();
+          if (tr3) t3[rb == 0 ? 1 : 7] = (unsigned int)clock64();
+          if (TC_TRACE_ON(a) && blockIdx.x == 0 && (unsigned)(t - a.trace_t0) < 512u && rb == 0) g_tc_trace[4 * (t - a.trace_t0) + 0] = clock64();
+          int sk = s;
+          for (int kh = 0; kh < KH; ++kh) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               const uint64_t db = umma_desc(b_addr + sk * TC_BOX_BYTES + k4 * 32);
               tc_mma_bf16_ts(tmem_base + (uint32_t)(buf * TC_BN), tmem_base + A_COL0 + (uint32_t)((rb * KH + kh) * 32 + k4 * 8),
                              db, TC_IDESC, (kh | k4) != 0 ? 1u : 0u);
             }
-            if (++sk == NSTAGE) { sk = 0; phk ^= 1; }
+            if (tr3 && rb == 0 && kh < 2) t3[3 + 2 * kh] = (unsigned int)clock64();
+            if (++sk == NSTAGE) sk = 0;
           }
-          tc_commit(&bars->tmem_full[buf]);                 // this row block's accumulator is complete
-          if (++buf == NBUF) { buf = 0; bph ^= 1u; }
+          if (tr3 && rb == 1) t3[8] = (unsigned int)clock64();
+          tc_commit(&bars->tmem_full[buf][rb]);             // this row block's accumulator is complete
+          if (tr3) t3[rb == 0 ? 6 : 9] = (unsigned int)clock64();
         }
         for (int kh = 0; kh < KH; ++kh) {                   // smem stages reusable once all 2*KH*4 MMAs retire
           tc_commit(&bars->empty[s]);
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
-        if (a.debug == 3 && blockIdx.x == 0 && t < 512) g_tc_trace[4 * t + 1] = clock64();
+        if (tr3) t3[10] = (unsigned int)clock64();
+        if (TC_TRACE_ON(a) && blockIdx.x == 0 && (unsigned)(t - a.trace_t0) < 512u) g_tc_trace[4 * (t - a.trace_t0) + 1] = clock64();
+        // hop over the other issuer's tile: KH stages
+        if (NISS == 2) {
+          s += KH;
+          if (s >= NSTAGE) { s -= NSTAGE; ph ^= 1; }
+        }
       }
     }
   } else if (warp < TC_EPI_WARPS) {
@@ -604,90 +815,161 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
       if (lane == 0) mbar_arrive(&bars->a_full);
     }
     // ---- fused top-k' ------------------------------------------------------------------------------
-    float* my_s = list_s + row;                             // entry p at my_s[p * 256] (conflict free)
-    int32_t* my_i = list_i + row;
-    int32_t* my_meta = list_meta + row;
-    float* my_pqs = pq_s + row;                             // pending entry q at my_pqs[q * 256]
-    int32_t* my_pqi = pq_i + row;
-    int npend = 0;
-    float thr = -INFINITY;
-    unsigned int n_drain = 0;
-    const int64_t key_base = (int64_t)tile0 * TC_BN;
-    int buf = rb; uint32_t bph = 0;                         // use u = 2t + rb -> buffer u % NBUF, phase (u / NBUF) & 1
-    for (int t = 0; t < n_my_tiles; ++t) {
-      mbar_wait(&bars->tmem_full[buf], bph);
+    const int wrow0 = rb * 128 + quarter * 32;              // first row of this warp (lane L owns row wrow0 + L)
+    int npend = 0;                                          // candidates in this row's append buffer
+    // KP-th best score at the last compaction of this row; starts at the pre-pass bound (one notch lower, so that keys
+    // tying with the bound are still taken) or -inf
+    float thr = (!PRE && a.thr0 && grow < a.Q) ? a.thr0[grow] : -INFINITY;
+    if (thr > -INFINITY) thr = (thr > 0.f) ? thr * (1.0f - 1e-6f) : thr * (1.0f + 1e-6f) - 1e-30f;
+    // pre-pass state: running maximum of the current tile group
+    float gm = -INFINITY;
+    int gi = 0;
+    const int g_tiles = PRE ? (n_my_tiles + a.pre_groups - 1) / a.pre_groups : 0;
+    int g_end = g_tiles;
+    const int key_base = tile0 * TC_BN;                     // 32-bit: a shard holds < 2^31 keys (checked by the C ABI)
+    // ---- this warp's hit queue: (lane, chunk) hits wait here until the warp has nothing better to do ----
+    float* q_mine = queue + warp * (TS_QN * TS_QSTRIDE);
+    unsigned qhead = 0, qtail = 0;                          // warp-uniform counters; slot = counter % TS_QN
+    // all lanes: serve the oldest queued hit (ts_serve_entry)
+    auto process_one = [&]() {
+      const TsServed r = ts_serve_entry<KP>(q_mine + (qhead % TS_QN) * TS_QSTRIDE, list_s, list_i, pq_s, pq_i, wrow0, thr, npend, lane);
+      if (lane == r.owner) { npend = r.np; thr = r.thr; }
+      ++qhead;
+      __syncwarp();
+    };
+    for (int t = 0; t <= n_my_tiles; ++t) {
+      // use u = 2t + rb -> buffer u % NBUF; this row block's (t / 3)-th visit of it (ring of 3), t-th (ring of 2)
+      const uint32_t u = 2u * (uint32_t)t + (uint32_t)rb;
+      const uint32_t buf = (NBUF == 2) ? (u & 1u) : (u % 3u);
+      const uint32_t full_par = ((NBUF == 2) ? (uint32_t)t : (uint32_t)t / 3u) & 1u;
+      // idle time is selection time: while the next accumulator is not ready, work off queued hits; the extra pass
+      // t == n_my_tiles drains what is left (one call site keeps the kernel small)
+      if (qhead != qtail) {
+        const uint32_t full_addr = smem_u32(&bars->tmem_full[buf][rb]);
+        while (qhead != qtail && (t == n_my_tiles || !__any_sync(0xffffffffu, mbar_test(full_addr, full_par)))) process_one();
+      }
+      if (t == n_my_tiles) break;
+      mbar_wait(&bars->tmem_full[buf][rb], full_par);
       tc_fence_after();
-      if (a.debug == 3 && blockIdx.x == 0 && t < 512 && threadIdx.x == 0) g_tc_trace[4 * t + 2] = clock64();
-      const int64_t tile_key0 = key_base + (int64_t)t * TC_BN;
-      const int n_valid = (int)min((int64_t)TC_BN, a.N - tile_key0);
+      if (TC_TRACE_ON(a) && blockIdx.x == 0 && (unsigned)(t - a.trace_t0) < 512u && threadIdx.x == 0) g_tc_trace[4 * (t - a.trace_t0) + 2] = clock64();
+      const int tile_key0 = key_base + t * TC_BN;
+      const int n_valid = min(TC_BN, (int)a.N - tile_key0);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN);
-      auto flush = [&]() {
-        for (int q = 0; q < npend; ++q) {
-          const float sc = my_pqs[q * TC_ROWS];
-          if (sc > thr) thr = tc_list_push<KP>(my_s, my_i, my_meta, sc, my_pqi[q * TC_ROWS]);
-        }
-        npend = 0;
-      };
-      auto filter = [&](const uint32_t (&v)[32], int col0) {
-        float m1[11];
-#pragma unroll
-        for (int j = 0; j < 10; ++j)
-          m1[j] = max3(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
-        m1[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
-        const float m2a = max3(m1[0], m1[1], m1[2]), m2b = max3(m1[3], m1[4], m1[5]);
-        const float m2c = max3(m1[6], m1[7], m1[8]), m2d = fmaxf(m1[9], m1[10]);
-        if (fmaxf(max3(m2a, m2b, m2c), m2d) > thr) {        // rare once the list has warmed up
-          uint32_t mask = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
-          const int room = n_valid - col0;                  // columns >= n_valid are TMA zero fill past the library end
-          if (room < 32) mask &= (room <= 0) ? 0u : ((1u << room) - 1u);
-          while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            if (npend == TC_PQ) { ++n_drain; flush(); }
-            my_pqs[npend * TC_ROWS] = select32(v, j);
-            my_pqi[npend * TC_ROWS] = (int32_t)(tile_key0 + col0 + j);
-            ++npend;
-          }
-        }
-      };
-      uint32_t va[32], vb[32];
-      const bool do_filter = (a.debug == 0 || a.debug == 3);
+      bool hit = false;
       if (a.debug == 1) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+        if (lane == 0) mbar_arrive(&bars->tmem_empty[buf][rb]);
       } else {
-        tmem_ld32(taddr, va);
-        tmem_ld_wait_regs(va);
-#pragma unroll 1
-        for (int c = 0; c < TC_BN / 32; c += 2) {
-          tmem_ld32(taddr + (c + 1) * 32, vb);
-          if (do_filter) filter(va, c * 32);
-          tmem_ld_wait_regs(vb);
-          if (c + 2 < TC_BN / 32) {
-            tmem_ld32(taddr + (c + 2) * 32, va);
-          } else {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+        // Three of the four 32-column chunks are loaded at once; the fourth reuses the first chunk's registers once that
+        // chunk has been reduced (and, on a hit, queued): 96 score registers live instead of 128, which is what keeps
+        // this kernel free of local-memory traffic at 352 threads (168 registers per thread).
+        uint32_t va[32], vb[32], vc[32];
+        tmem_ld32(taddr, va); tmem_ld32(taddr + 32, vb); tmem_ld32(taddr + 64, vc);
+        tmem_ld_wait();
+        tie_regs(va); tie_regs(vb); tie_regs(vc);
+        auto release = [&]() {                              // hand the TMEM buffer back to the MMA issuers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->tmem_empty[buf][rb]);
+        };
+        if constexpr (PRE) {
+          // pre-pass: group maxima only (no lists, no slow path); a tile that runs past the library end is skipped
+          const float c0 = chunk_max32(va);
+          tmem_ld32(taddr + 96, va);
+          const float c1 = chunk_max32(vb), c2 = chunk_max32(vc);
+          tmem_ld_wait();
+          tie_regs(va);
+          release();
+          const float c3 = chunk_max32(va);
+          if (n_valid == TC_BN) gm = fmaxf(gm, fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)));
+          if (t + 1 == g_end || t + 1 == n_my_tiles) {
+            if (grow < a.Q) a.gmax[((int64_t)split * a.pre_groups + gi) * a.Q + grow] = gm;
+            gm = -INFINITY; ++gi; g_end += g_tiles;
           }
-          if (do_filter) filter(vb, (c + 1) * 32);
-          if (c + 2 < TC_BN / 32) tmem_ld_wait_regs(va);
+        } else if (a.debug == 2) {
+          tmem_ld32(taddr + 96, va);
+          tmem_ld_wait();
+          tie_regs(va);
+          release();
+        } else {
+          // A hit costs the tile loop only the copy of its 32-score chunk into the queue (8 x 128-bit stores with static
+          // register indices + a header); everything serial happens later in process_one.  `m` = lanes whose chunk
+          // maximum beats their threshold; slots follow from ballot ranks.  If the queue lacks room (dense phases only:
+          // no pre-pass bound, tiny libraries) the hit lanes go in half a warp at a time, serving queued hits first.
+          auto enqueue = [&](const uint32_t (&v)[32], unsigned m, int c) {
+            const int key0 = tile_key0 + c * 32;
+            const int meta = lane | (max(min(32, n_valid - c * 32), 0) << 8);
+            const int n = __popc(m);
+            if (__builtin_expect(qtail - qhead + (unsigned)n <= (unsigned)TS_QN, 1)) {
+              if ((m >> lane) & 1u) queue_put(q_mine + ((qtail + __popc(m & ((1u << lane) - 1u))) % TS_QN) * TS_QSTRIDE, v, key0, meta);
+              qtail += n;
+              __syncwarp();
+            } else {
+#pragma unroll 1
+              for (int half = 0; half < 2; ++half) {
+                const unsigned mh = m & (half ? 0xffff0000u : 0x0000ffffu);
+                const int nh = __popc(mh);
+                while (qtail - qhead + (unsigned)nh > (unsigned)TS_QN) process_one();
+                if ((mh >> lane) & 1u) queue_put(q_mine + ((qtail + __popc(mh & ((1u << lane) - 1u))) % TS_QN) * TS_QSTRIDE, v, key0, meta);
+                qtail += nh;
+                __syncwarp();
+              }
+            }
+          };
+          // fast path (registers only): chunk maxima against the row threshold, one warp vote for the first chunk (its
+          // registers are about to be reused) and one for the other three
+          const float c0 = chunk_max32(va);
+          const bool h0 = c0 > thr;
+          if (__any_sync(0xffffffffu, h0)) enqueue(va, __ballot_sync(0xffffffffu, h0), 0);
+          tmem_ld32(taddr + 96, va);
+          const float c1 = chunk_max32(vb), c2 = chunk_max32(vc);
+          tmem_ld_wait();
+          tie_regs(va);
+          release();
+          const float c3 = chunk_max32(va);
+          const bool h1 = c1 > thr, h2 = c2 > thr, h3 = c3 > thr;
+          hit = h0 || h1 || h2 || h3;
+          if (__any_sync(0xffffffffu, h1 || h2 || h3)) {
+            const unsigned b1 = __ballot_sync(0xffffffffu, h1), b2 = __ballot_sync(0xffffffffu, h2), b3 = __ballot_sync(0xffffffffu, h3);
+#pragma unroll 1
+            for (int c = 1; c < 4; ++c) {
+              const unsigned m = (c == 1) ? b1 : (c == 2) ? b2 : b3;
+              if (m == 0) continue;
+              if (c == 1) enqueue(vb, m, 1);
+              else if (c == 2) enqueue(vc, m, 2);
+              else enqueue(va, m, 3);
+            }
+          }
         }
-        if (npend) { ++n_drain; flush(); }
       }
-      buf += 2;
-      if (buf >= NBUF) { buf -= NBUF; bph ^= 1u; }
-      if (a.debug == 3 && blockIdx.x == 0 && t < 512 && threadIdx.x == 0) { g_tc_trace[4 * t + 3] = clock64(); g_tc_trace2[2 * t] = n_drain; n_drain = 0; }
+      if (TC_TRACE_ON(a) && blockIdx.x == 0 && (unsigned)(t - a.trace_t0) < 512u && warp == 0) {
+        const unsigned hb = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) {
+          g_tc_trace[4 * (t - a.trace_t0) + 3] = clock64();
+          g_tc_trace2[2 * (t - a.trace_t0)] = qtail - qhead; g_tc_trace2[2 * (t - a.trace_t0) + 1] = __popc(hb);
+        }
+      }
     }
-    // ---- publish this split's list --------------------------------------------------------------
-    if (grow < a.Q) {
+    if constexpr (PRE) {
+      for (; gi < a.pre_groups; ++gi)
+        if (grow < a.Q) a.gmax[((int64_t)split * a.pre_groups + gi) * a.Q + grow] = -INFINITY;
+    }
+    // ---- fold what is still pending, publish this split's list (sorted: score desc) ---------------------
+    if constexpr (!PRE) {
+      unsigned todo = __ballot_sync(0xffffffffu, npend > 0);
+      while (todo) {
+        const int L = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int np = __shfl_sync(0xffffffffu, npend, L);
+        ts_compact_row<KP>(list_s, list_i, pq_s, pq_i, wrow0 + L, np, lane);
+      }
+    }
+    if (!PRE && grow < a.Q) {
       float* ps = a.part_s + ((int64_t)split * a.Q + grow) * KP;
       int32_t* pi = a.part_i + ((int64_t)split * a.Q + grow) * KP;
 #pragma unroll
-      for (int p = 0; p < KP; ++p) { ps[p] = my_s[p * TC_ROWS]; pi[p] = my_i[p * TC_ROWS]; }
+      for (int p = 0; p < KP; ++p) { ps[p] = list_s[p * TS_LSTRIDE + row]; pi[p] = list_i[p * TS_LSTRIDE + row]; }
     }
   }
 
@@ -700,6 +982,38 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
   }
 }
 
+// ---- pre-pass threshold: thr0[row] = kp-th largest of the row's G group maxima ---------------------------
+// Each group maximum is the bf16 score of a distinct key of this shard, so at least kp keys score >= thr0: the final
+// kp-th best score of the row (over the whole shard, hence over the union of the split lists) is >= thr0.
+__global__ void __launch_bounds__(256) sample_threshold_kernel(const float* __restrict__ gmax, int G, int64_t Q, int kp,
+                                                               float* __restrict__ thr0) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= Q) return;
+  float v[8];                                                 // G <= 256
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { const int g = lane + 32 * t; v[t] = (g < G) ? __ldg(gmax + (int64_t)g * Q + row) : -INFINITY; }
+  float kth = -INFINITY;
+  for (int it = 0; it < kp; ++it) {                           // remove the current maximum (one instance) kp times
+    float m = v[0];
+#pragma unroll
+    for (int t = 1; t < 8; ++t) m = fmaxf(m, v[t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    kth = m;
+    if (m == -INFINITY) break;
+    int mine = -1;
+#pragma unroll
+    for (int t = 7; t >= 0; --t) mine = (v[t] == m) ? t : mine;
+    const unsigned who = __ballot_sync(0xffffffffu, mine >= 0);
+    if (lane == __ffs(who) - 1) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) if (t == mine) v[t] = -INFINITY;
+    }
+  }
+  if (lane == 0) thr0[row] = kth;
+}
+
 // ---- refine: exact fp32 re-score of the candidates + certificate ------------------------------------
 struct RefineArgs {
   const float* q; const float* keys; const float* q_inv_norm; const float* key_inv_norm;
@@ -709,6 +1023,7 @@ struct RefineArgs {
   int64_t idx_offset;
   float* out_scores; int64_t* out_idx;
   int32_t* fb_rows; int32_t* fb_count;   // uncertified rows (exact only)
+  const float* thr0;                     // nullable: pre-pass bound; keys never listed score <= thr0[row] (bf16)
 };
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -756,6 +1071,7 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
       if (in && full) tmax = fmaxf(tmax, mn);
     }
     tmax = warp_max(tmax);
+    if (a.thr0) tmax = fmaxf(tmax, __ldg(a.thr0 + row));
     __syncwarp();
     // ---- pass 2 ------------------------------------------------------------------------------------
     float prev = INFINITY;
@@ -864,7 +1180,8 @@ static int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int d_
 struct TcPlan {
   int kh, kp, nstage, n_qtiles, n_splits, tiles_per_split, n_tiles, d_pad;
   size_t smem;
-  size_t off_qbf, off_qinv, off_ps, off_pi, off_fb, off_fbn, off_f32, total;
+  size_t off_qbf, off_qinv, off_ps, off_pi, off_fb, off_fbn, off_gmax, off_thr0, off_f32, total;
+  int pre_tiles, pre_groups;          // threshold pre-pass (0 tiles = off)
 };
 
 // SS kernel shapes (query tile resident in shared memory)
@@ -874,8 +1191,9 @@ static bool tc_shape_ok_ss(int d, int k) {
   if (d > 192 && d <= 256) return k <= 10;        // 128 KB of resident queries leave room for 16-entry lists only
   return false;
 }
-// TS kernel shapes (query tile resident in tensor memory): any d <= 256, k' = 16 or 32 slots per (row, split)
-bool tc_shape_ok(int d, int k) { return d >= 1 && d <= 256 && k >= 1 && k <= 26; }
+// TS kernel shapes (query tile resident in tensor memory): d <= 256; k' = 16 slots per (row, split) for k <= 10,
+// 32 for k <= 26 (d <= 128 only: 128 KB of lists + append buffers leave 4 pipeline stages, d > 128 needs 8)
+bool tc_shape_ok(int d, int k) { return d >= 1 && d <= 256 && k >= 1 && (k <= 10 || (k <= 26 && d <= 128)); }
 
 // RAG_TC_VARIANT=ss selects the older shared-memory-A kernel where it is instantiated (A/B measurements only)
 static bool tc_use_ts(int d, int k) {
@@ -890,14 +1208,17 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts) {
   if (!ts && p.kh == 3) p.kh = 4;            // SS instantiations: 1, 2, 4
   p.kp = (k <= 10) ? 16 : 32;
   // shared memory: (SS: A 2*KH boxes +) NSTAGE boxes + lists + barriers + 1 KB alignment slack  <= 227 KB
-  const int list_bytes = p.kp * TC_ROWS * 8 + TC_ROWS * 4 + TC_PQ * TC_ROWS * 8;   // lists + meta + pending queues
+  // SS: lists + meta + pending queues; TS: sorted lists + append buffers (stride 257) + 16 B alignment slack
+  const int list_bytes = ts ? 2 * p.kp * TS_LSTRIDE * 8 + TS_QUEUE_BYTES + 16 : p.kp * TC_ROWS * 8 + TC_ROWS * 4 + TC_PQ * TC_ROWS * 8;
   const int a_boxes = ts ? 0 : 2 * p.kh;
-  const int budget = 232448 - 1024 - 256 - list_bytes - a_boxes * TC_BOX_BYTES;
+  const int bar_bytes = ts ? TS_BAR_BYTES : 256;
+  const int slack = ts ? 0 : 1024;           // SS aligns its window by hand; TS declares the 1 KB alignment
+  const int budget = 232448 - slack - bar_bytes - list_bytes - a_boxes * TC_BOX_BYTES;
   p.nstage = budget / TC_BOX_BYTES;
-  const int cap = ts ? (p.kp == 16 ? 11 : 9) : 8;
+  const int cap = ts ? (p.kp == 16 ? 9 : 4) : 8;
   if (p.nstage > cap) p.nstage = cap;
   if (p.nstage < 2) p.nstage = 2;
-  p.smem = 1024 + (size_t)(a_boxes + p.nstage) * TC_BOX_BYTES + list_bytes + 256;
+  p.smem = slack + (size_t)(a_boxes + p.nstage) * TC_BOX_BYTES + list_bytes + bar_bytes;
   p.n_qtiles = (int)((Q + TC_ROWS - 1) / TC_ROWS);
   p.n_tiles = (int)((N + TC_BN - 1) / TC_BN);
   int s = sm_count() / p.n_qtiles;
@@ -912,6 +1233,18 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts) {
   p.off_pi = off; off += align_up((size_t)p.n_splits * Q * p.kp * 4, 256);
   p.off_fb = off; off += align_up((size_t)Q * 4, 256);
   p.off_fbn = off; off += 256;
+  // threshold pre-pass (TS kernel): 1/64 of every split, worthwhile once a split has >= 1024 tiles; G = n_splits * groups
+  // group maxima per row, G >= 2 * kp so that the kp-th largest of them sits near the middle of their distribution
+  p.pre_tiles = 0; p.pre_groups = 0;
+  int pre_min = 1024;
+  { const char* e = getenv("RAG_TC_PREPASS_MIN_TILES"); if (e && atoi(e) >= 64) pre_min = atoi(e); }   // tests lower it
+  if (ts && p.tiles_per_split >= pre_min) {
+    int g = (2 * p.kp + p.n_splits - 1) / p.n_splits;
+    if (g < 1) g = 1;
+    if ((int64_t)g * p.n_splits <= 256 && g <= p.tiles_per_split / 64) { p.pre_tiles = p.tiles_per_split / 64; p.pre_groups = g; }
+  }
+  p.off_gmax = off; off += align_up((size_t)p.pre_groups * p.n_splits * Q * 4, 256);
+  p.off_thr0 = off; off += align_up((size_t)Q * 4, 256);
   p.off_f32 = off; off += topk_f32_rows_workspace(Q, N, d, k);
   p.total = off;
   return p;
@@ -934,13 +1267,13 @@ static int launch_filter(const CUtensorMap& mq, const CUtensorMap& mk, const TcA
   return RAG_OK;
 }
 
-template <int KH, int NSTAGE, int KP>
+template <int KH, int NSTAGE, int KP, bool PRE>
 static int launch_filter_ts(const CUtensorMap& mk, const uint16_t* q_bf, const TcArgs& a, const TcPlan& p, cudaStream_t s) {
-  static_assert(sizeof(TsBarriers) <= 256, "barrier block");
-  auto kern = cosine_topk_ts_kernel<KH, NSTAGE, KP>;
+  static_assert(sizeof(TsBarriers) <= TS_BAR_BYTES, "barrier block");
+  auto kern = cosine_topk_ts_kernel<KH, NSTAGE, KP, PRE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(cosine_topk_ts_kernel)");
-  kern<<<(unsigned)(p.n_qtiles * p.n_splits), TC_THREADS, p.smem, s>>>(mk, q_bf, a);
+  kern<<<(unsigned)(p.n_qtiles * p.n_splits), TS_THREADS, p.smem, s>>>(mk, q_bf, a);
   RAG_LAUNCH_OK("cosine_topk_ts_kernel");
   return RAG_OK;
 }
@@ -950,7 +1283,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
                 int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
   RAG_REQUIRE(!(flags & RAG_SIM_DOT), RAG_EUNSUPPORTED, "cosine_topk: the tensor-core modes implement cosine only");
   RAG_REQUIRE(tc_shape_ok(d, k), RAG_EUNSUPPORTED,
-              "cosine_topk: tensor-core modes cover d <= 256 with k <= 26 (d=%d k=%d)", d, k);
+              "cosine_topk: tensor-core modes cover d <= 128 with k <= 26 and d <= 256 with k <= 10 (d=%d k=%d)", d, k);
   RAG_REQUIRE(key_inv_norm, RAG_EINVAL, "cosine_topk: the tensor-core modes need key_inv_norm (rag_row_inv_norm_f32)");
   RAG_REQUIRE(aligned16(keys_bf16), RAG_EALIGN, "cosine_topk: keys_bf16 must be 16-byte aligned");
   const bool ts = tc_use_ts(d, k);
@@ -979,16 +1312,37 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   a.Q = Q; a.N = N; a.n_qtiles = p.n_qtiles; a.n_splits = p.n_splits; a.tiles_per_split = p.tiles_per_split;
   a.n_tiles = p.n_tiles; a.kp = p.kp;
   { const char* dbg = getenv("RAG_TC_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
+  { const char* tr = getenv("RAG_TC_TRACE"); a.trace = (tr && atoi(tr)) ? 1 : 0; if (a.debug == 3) { a.debug = 0; a.trace = 1; } }
+  { const char* t0 = getenv("RAG_TC_TRACE_T0"); a.trace_t0 = t0 ? atoi(t0) : 0; }
+  { const char* nt = getenv("RAG_TC_NOTMA"); a.no_tma = nt ? atoi(nt) : 0; }
   { const char* sw = getenv("RAG_TS_SWAP"); a.swap_halves = sw ? atoi(sw) : 0; }
   a.part_s = reinterpret_cast<float*>(w + p.off_ps);
   a.part_i = reinterpret_cast<int32_t*>(w + p.off_pi);
   if (ts) {
+    auto run_ts = [&](const TcArgs& ta) -> int {
 #define RAG_TS_CASE(KH_, NS_, KP_) \
-  if (p.kh == KH_ && p.nstage == NS_ && p.kp == KP_) st = launch_filter_ts<KH_, NS_, KP_>(mk, q_bf, a, p, s); else
-    RAG_TS_CASE(1, 11, 16) RAG_TS_CASE(1, 9, 32) RAG_TS_CASE(2, 11, 16) RAG_TS_CASE(2, 9, 32)
-    RAG_TS_CASE(3, 11, 16) RAG_TS_CASE(3, 9, 32) RAG_TS_CASE(4, 11, 16) RAG_TS_CASE(4, 9, 32)
-    return fail(RAG_EUNSUPPORTED, "cosine_topk: no tensor-core instantiation for kh=%d nstage=%d kp=%d", p.kh, p.nstage, p.kp);
+  if (p.kh == KH_ && p.nstage == NS_ && p.kp == KP_) \
+    return ta.premax ? launch_filter_ts<KH_, NS_, KP_, true>(mk, q_bf, ta, p, s) : launch_filter_ts<KH_, NS_, KP_, false>(mk, q_bf, ta, p, s);
+      RAG_TS_CASE(1, 9, 16) RAG_TS_CASE(2, 9, 16) RAG_TS_CASE(3, 9, 16) RAG_TS_CASE(4, 9, 16)
+      RAG_TS_CASE(1, 4, 32) RAG_TS_CASE(2, 4, 32)
 #undef RAG_TS_CASE
+      return fail(RAG_EUNSUPPORTED, "cosine_topk: no tensor-core instantiation for kh=%d nstage=%d kp=%d", p.kh, p.nstage, p.kp);
+    };
+    const char* pp = getenv("RAG_TC_PREPASS");
+    if (p.pre_tiles > 0 && !(pp && pp[0] == '0') && a.debug == 0) {
+      // threshold pre-pass over the first 1/64 of every split (group maxima only), then the per-row bound
+      TcArgs pre = a;
+      pre.premax = 1; pre.pre_tiles = p.pre_tiles; pre.pre_groups = p.pre_groups;
+      pre.gmax = reinterpret_cast<float*>(w + p.off_gmax);
+      pre.trace = 0;
+      st = run_ts(pre);
+      if (st) return st;
+      float* thr0 = reinterpret_cast<float*>(w + p.off_thr0);
+      sample_threshold_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, s>>>(pre.gmax, p.pre_groups * p.n_splits, Q, p.kp, thr0);
+      RAG_LAUNCH_OK("sample_threshold_kernel");
+      a.thr0 = thr0;
+    }
+    st = run_ts(a);
   } else {
     st = make_map_bf16(&mq, q_bf, Q, p.d_pad, 128);
     if (st) return st;
@@ -1008,6 +1362,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   r.idx_offset = idx_offset; r.out_scores = out_scores; r.out_idx = out_idx;
   r.fb_rows = reinterpret_cast<int32_t*>(w + p.off_fb);
   r.fb_count = reinterpret_cast<int32_t*>(w + p.off_fbn);
+  r.thr0 = a.thr0;
   const int total_c = p.n_splits * p.kp;
   const int wpb = (total_c <= 1024) ? 8 : 2;                    // per-warp smem: k*12 + total*4 bytes (< 48 KB per CTA)
   int64_t blocks = (Q + wpb - 1) / wpb;
@@ -1023,9 +1378,10 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
 
 }  // namespace rag
 
-// diagnostics: copy the RAG_TC_DEBUG=3 pipeline trace (4 x 512 clock64 stamps + 2 x 512 uint32) to the host (20 KB)
+// diagnostics: copy the pipeline trace (4 x 512 clock64 stamps + 2 x 512 uint32 + 16 x 256 uint32) to the host (36 KB)
 extern "C" RAG_API int rag_tc_trace_read(unsigned long long* host_out) {
   cudaError_t e = cudaMemcpyFromSymbol(host_out, rag::g_tc_trace, sizeof(unsigned long long) * 4 * 512);
   if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host_out + 4 * 512, rag::g_tc_trace2, sizeof(unsigned int) * 2 * 512);
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host_out + 4 * 512 + 512, rag::g_tc_trace3, sizeof(unsigned int) * 16 * 256);
   return e == cudaSuccess ? RAG_OK : rag::cuda_fail(e, "rag_tc_trace_read");
 }

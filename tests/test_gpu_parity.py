@@ -221,11 +221,19 @@ def test_gcn_layer_golden(golden):
     layer = R.GCN(24, 16, 'prelu').to(DEV)
     with torch.no_grad():
         layer.fc.weight.copy_(cu(g["weight"])); layer.bias.copy_(cu(g["bias"])); layer.act.weight.copy_(cu(g["alpha"]))
-    out = layer((cu(g["seq"]), cu(g["adj"]).unsqueeze(0))).cpu().numpy()
+    with torch.no_grad():                                           # one fused launch (aggregation + bias + PReLU)
+        out = layer((cu(g["seq"]), cu(g["adj"]).unsqueeze(0))).cpu().numpy()
     assert np.max(np.abs(out - g["out"])) < 2e-5 * max(1.0, np.abs(g["out"]).max())   # includes cuBLAS XW
     sp = cu(g["adj"]).to_sparse()
-    out_sp = layer((cu(g["seq"]), sp), sparse=True).cpu().numpy()
+    with torch.no_grad():
+        out_sp = layer((cu(g["seq"]), sp), sparse=True).cpu().numpy()
     assert np.max(np.abs(out_sp - g["out"])) < 2e-5 * max(1.0, np.abs(g["out"]).max())
+    # training mode: same values through the differentiable path, gradients reach W, b and alpha
+    out_tr = layer((cu(g["seq"]), cu(g["adj"]).unsqueeze(0)))
+    assert out_tr.requires_grad
+    assert np.max(np.abs(out_tr.detach().cpu().numpy() - g["out"])) < 2e-5 * max(1.0, np.abs(g["out"]).max())
+    out_tr.sum().backward()
+    assert layer.fc.weight.grad is not None and layer.bias.grad is not None and layer.act.weight.grad is not None
 
 
 def test_edge_agg_golden(golden):

@@ -31,7 +31,7 @@ def _run(q, keys, k, mode):
 
 @pytest.mark.parametrize("Q,N,d,k", [(300, 20000, 128, 10), (700, 100000, 64, 10), (1000, 50000, 256, 10),
                                      (37, 5000, 128, 20), (256, 128, 128, 4), (5, 333, 100, 3), (513, 70001, 128, 10),
-                                     (64, 3000, 32, 26), (260, 30000, 160, 10), (300, 40000, 256, 20),
+                                     (64, 3000, 32, 26), (260, 30000, 160, 10), (300, 40000, 256, 7),
                                      (1100, 60000, 128, 10)])
 def test_refine_mode_is_exact(Q, N, d, k):
     g = torch.Generator().manual_seed(Q + N + d)
@@ -99,3 +99,32 @@ def test_large_refine_equals_fp32():
     s0, i0 = ops.cosine_topk(q, keys, k, key_inv_norm=inv)
     assert float((s3 - s0).abs().max()) < 2e-6
     assert float((i3 == i0).float().mean()) > 0.9999
+
+
+@pytest.mark.parametrize("min_tiles", [64, 1024])
+def test_prepass_threshold_keeps_exactness(min_tiles, monkeypatch, tc_variant):
+    """The threshold pre-pass (group maxima over 1/64 of every split -> per-row lower bound of the k'-th best score)
+    must not change results: duplicates of the best match (ties AT the bound), zero rows, and queries whose whole top-k
+    sits inside the sampled prefix."""
+    if tc_variant != "ts":
+        pytest.skip("pre-pass exists in the ts kernel only")
+    monkeypatch.setenv("RAG_TC_PREPASS_MIN_TILES", str(min_tiles))
+    torch.manual_seed(11)
+    Q, d, k = 4096, 128, 10
+    N = 1_300_000 if min_tiles == 1024 else 120_000
+    keys = torch.randn(N, d, device=DEV); q = torch.randn(Q, d, device=DEV)
+    q[:64] = keys[:64] + 0.01 * torch.randn(64, d, device=DEV)         # best matches inside the sampled prefix of split 0
+    keys[1000:1020] = keys[5]                                          # 20 exact duplicates of a key that query 5 matches
+    keys[N - 30:N - 10] = q[100] * 3.0                                 # 20 identical best matches for query 100 (cos = 1)
+    q[7] = 0.0; keys[9] = 0.0
+    inv = ops.row_inv_norm(keys); shadow = ops.rows_to_bf16(keys, True)
+    s3, i3 = ops.cosine_topk(q, keys, k, key_inv_norm=inv, keys_bf16=shadow, mode=L.SIM_BF16_REFINE)
+    monkeypatch.setenv("RAG_TC_PREPASS", "0")
+    s3n, i3n = ops.cosine_topk(q, keys, k, key_inv_norm=inv, keys_bf16=shadow, mode=L.SIM_BF16_REFINE)
+    s0, i0 = ops.cosine_topk(q, keys, k, key_inv_norm=inv)             # fp32 CUDA-core path
+    assert torch.equal(s3, s3n) and torch.equal(i3, i3n)
+    assert float((s3 - s0).abs().max()) < 2e-6
+    same = (i3 == i0).all(dim=1)
+    assert float(same.float().mean()) > 0.99
+    for r in torch.nonzero(~same).flatten().tolist():                  # any difference must be a tie within 1e-6
+        assert float((s3[r].sort().values - s0[r].sort().values).abs().max()) < 1e-6

@@ -28,16 +28,17 @@ for a, b in ev:
 torch.cuda.synchronize()
 ms = sorted(a.elapsed_time(b) for a, b in ev)
 med = ms[len(ms) // 2]
-print(f"RAG_TC_DEBUG={os.environ.get('RAG_TC_DEBUG','0')} N={N} d={d} Q={Q} mode={mode}: median {med:.3f} ms  min {ms[0]:.3f}  "
+print(f"variant={os.environ.get('RAG_TC_VARIANT','ts')} RAG_TC_DEBUG={os.environ.get('RAG_TC_DEBUG','0')} N={N} d={d} Q={Q} mode={mode}: median {med:.3f} ms  min {ms[0]:.3f}  "
       f"{2*Q*N*d/med/1e9:.1f} TFLOP/s  {Q/med*1e3:.0f} q/s")
-if os.environ.get("RAG_TC_DEBUG") == "3":
+if os.environ.get("RAG_TC_DEBUG") == "3" or os.environ.get("RAG_TC_TRACE") == "1":
     import ctypes, numpy as np
     lib = L.load()
-    buf = (ctypes.c_ulonglong * (2048 + 512))()
+    buf = (ctypes.c_ulonglong * (2048 + 512 + 2048))()
     lib.rag_tc_trace_read.argtypes = [ctypes.c_void_p]
     lib.rag_tc_trace_read(buf)
     tr = np.array(buf[:2048], dtype=np.int64).reshape(512, 4)
-    tr2 = np.frombuffer(np.array(buf[2048:], dtype=np.uint64).tobytes(), dtype=np.uint32).reshape(512, 2)
+    tr2 = np.frombuffer(np.array(buf[2048:2560], dtype=np.uint64).tobytes(), dtype=np.uint32).reshape(512, 2)
+    tr3 = np.frombuffer(np.array(buf[2560:], dtype=np.uint64).tobytes(), dtype=np.uint32).reshape(256, 16).astype(np.int64)
     t0 = tr[0, 0]
     print("tile: mma_start mma_issued | epi_start epi_done   (cycles since first)   d(mma_start) d(epi_done)")
     for t in list(range(0, 12)) + list(range(400, 412)):
@@ -45,8 +46,18 @@ if os.environ.get("RAG_TC_DEBUG") == "3":
         dm = tr[t, 0] - tr[t - 1, 0] if t else 0
         de = tr[t, 3] - tr[t - 1, 3] if t else 0
         print(f"{t:4d}: {r[0]:8d} {r[1]:8d} | {r[2]:8d} {r[3]:8d}    {dm:6d} {de:6d}   epi_len={tr[t,3]-tr[t,2]}  full_lat={tr[t,2]-tr[t,1]}  drains={tr2[t,0]}  tmem_hold={tr2[t,1]}")
-    print("drains per tile (100..500):", float(tr2[100:500, 0].mean()), " mean tmem_hold:", float(tr2[100:500, 1].mean()),
-          " mean epi_len for drains==0:", float(np.mean([(tr[t,3]-tr[t,2]) for t in range(100,500) if tr2[t,0]==0] or [0])),
-          " ==1:", float(np.mean([(tr[t,3]-tr[t,2]) for t in range(100,500) if tr2[t,0]==1] or [0])),
-          " ==2:", float(np.mean([(tr[t,3]-tr[t,2]) for t in range(100,500) if tr2[t,0]==2] or [0])))
-    print("mean period (tiles 100..500):", (tr[500, 0] - tr[100, 0]) / 400.0, " mean epi_len:", float(np.mean(tr[100:500, 3] - tr[100:500, 2])))
+    hits = tr2[100:500, 1]
+    el = (tr[100:500, 3] - tr[100:500, 2])
+    per = np.diff(tr[100:501, 0])
+    print(f"window t0={os.environ.get('RAG_TC_TRACE_T0','0')}: mean period {per.mean():.1f} (median {np.median(per):.0f}, p90 {np.percentile(per,90):.0f})  "
+          f"issue {np.mean(tr[100:500,1]-tr[100:500,0]):.0f}")
+    for h in (0, 1, 2, 3):
+        sel = hits == h if h < 3 else hits >= 3
+        if sel.any():
+            print(f"  warp-0 lanes on the slow path = {h}{'+' if h == 3 else ''}: {sel.mean()*100:.1f}% of tiles, epi_len mean {el[sel].mean():.0f} median {np.median(el[sel]):.0f}, "
+                  f"period mean {per[sel].mean():.0f}")
+    names = ["top", "W_e0", "fulls", "mma0", "-", "mma1", "commit0", "W_e1", "mma_rb1", "commit1", "empties"]
+    seg = (tr3[100:250, 1:11] - tr3[100:250, 0:10]) & 0xffffffff
+    nxt = (tr3[101:251, 0] - tr3[100:250, 10]) & 0xffffffff
+    print("MMA-thread micro-trace, mean cycles per segment (tiles 100..250): " +
+          "  ".join(f"{n}={seg[:, i].mean():.0f}" for i, n in enumerate(names[1:])) + f"  loop={nxt.mean():.0f}  total={(seg.sum(1) + nxt).mean():.0f}")

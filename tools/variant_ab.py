@@ -48,8 +48,9 @@ def run(N, d):
         os.environ.pop("RAG_TC_DEBUG", None)
         res[variant] = ops.cosine_topk(q, keys, k, key_inv_norm=inv, keys_bf16=shadow, mode=3)
         print(json.dumps(out), flush=True)
-    same = bool(torch.equal(res["ss"][1], res["ts"][1])) and bool(torch.equal(res["ss"][0], res["ts"][0]))
+    same = all(bool(torch.equal(res["ss"][j], res["ts"][j])) for j in (0, 1))
     print(json.dumps({"N": N, "d": d, "ss_equals_ts_mode3": same}), flush=True)
+    os.environ.pop("RAG_TC_VARIANT", None)
 
 
 if __name__ == "__main__":
