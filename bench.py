@@ -31,6 +31,15 @@ SPMM_N, SPMM_NNZ, SPMM_F = 2_449_029, 61_859_140, 256
 METRIC = "retrieval queries/sec (top-10, 100M keys) + SpMM GB/s"
 
 
+def _ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from a committed `ncu --set full` capture of exactly this
+    kernel and size (profiles/ncu_traffic.json, written from the .ncu-rep by tools/ncu_summary.py); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(key)
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -299,8 +308,11 @@ def main():
     flops = 2.0 * Q_BATCH * (hi - lo) * DIM
     tf_ach = flops / (kern_ms * 1e-3) / 1e12
     roof = {"bound": "tensor", "achieved": tf_ach, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": tf_ach / peaks["bf16"],
-            "traffic": None, "kernel": {0: "cosine_topk_f32_kernel (CUDA-core fp32)", 2: "cosine_topk_tc_kernel (tcgen05 bf16)",
-                                        3: "cosine_topk_tc_kernel (tcgen05 bf16) + fp32 refine"}.get(mode, str(mode)),
+            "traffic": _ncu_traffic(f"cosine_topk_ts_kernel:N={hi - lo}:d={DIM}:Q={Q_BATCH}") if mode in (2, 3) else None,
+            "kernel": {0: "cosine_topk_f32_kernel (CUDA-core fp32)",
+                       2: "cosine_topk_ts_kernel (tcgen05 bf16, query tile stationary in TMEM) + threshold pre-pass",
+                       3: "cosine_topk_ts_kernel (tcgen05 bf16, query tile stationary in TMEM) + threshold pre-pass + fp32 refine"
+                       }.get(mode, str(mode)),
             "kernel_ms": kern_ms, "peak_source": peaks["src"] + " bf16 burst (cuBLAS 8192^3)",
             "algorithmic": "2*Q*N_local*d flop per launch"}
 
@@ -364,7 +376,8 @@ def bench_spmm(dev, args, peaks):
             "config": {"workload": f"CSR SpMM ogbn-products-shaped synthetic: n={SPMM_N} nnz={SPMM_NNZ} F={SPMM_F} fp32, "
                                    f"Chung-Lu power law, max degree {max_deg}", "l2": "X (2.5 GB) larger than L2"},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                         "traffic": None, "kernel": "csr_spmm_kernel<32,2>", "algorithmic_bytes": alg,
+                         "traffic": _ncu_traffic(f"csr_spmm_kernel:n={SPMM_N}:nnz={SPMM_NNZ}:F={SPMM_F}"),
+                         "kernel": "csr_spmm_kernel<32,2>", "algorithmic_bytes": alg,
                          "compulsory_bytes": SPMM_NNZ * 8 + (SPMM_N + 1) * 8 + 2 * SPMM_N * SPMM_F * 4,
                          "peak_source": peaks["src"] + " copy bandwidth"},
             "gpu_launches": int(L.launch_count() - l0)}

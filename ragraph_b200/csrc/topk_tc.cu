@@ -233,6 +233,7 @@ struct TcArgs {
   // pass then starts every row at thr0[row] (a proven lower bound of its final kp-th best score) instead of -inf
   int premax; int pre_tiles; int pre_groups;
   float* gmax; const float* thr0;
+  float* overflow;                 // TS kernel: [CTAs][8 warps][32 lanes][128] scores parked when a warp's hit queue overflows
   int trace;                       // RAG_TC_DEBUG=3 or RAG_TC_TRACE=1: CTA 0 stamps clock64 at pipeline events (g_tc_trace)
   int trace_t0;                    // RAG_TC_TRACE_T0: first traced tile (window of 512)
   int no_tma;                      // RAG_TC_NOTMA=1 (experiment): the producer arrives without loading keys (garbage operands)
@@ -597,10 +598,8 @@ __device__ __forceinline__ float ts_compact_row(float* ls, int32_t* li, float* p
 // is compacted on the spot.  Returns the owner's new (threshold, pending count); `owner` = the owner lane.
 struct TsServed { float thr; int np; int owner; };
 template <int KP>
-__device__ __forceinline__ TsServed ts_serve_entry(const float* ev, float* ls, int32_t* li, float* ps, int32_t* pi, int wrow0,
-                                                   float thr, int npend, int lane) {
-  const int key0 = __float_as_int(ev[32]);
-  const int meta = __float_as_int(ev[33]);
+__device__ __forceinline__ TsServed ts_serve_entry(const float* ev, int key0, int meta, float* ls, int32_t* li, float* ps,
+                                                   int32_t* pi, int wrow0, float thr, int npend, int lane) {
   const int L = meta & 31, nv = meta >> 8;
   const float val = ev[lane];
   float thr_l = __shfl_sync(0xffffffffu, thr, L);
@@ -832,7 +831,9 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
     unsigned qhead = 0, qtail = 0;                          // warp-uniform counters; slot = counter % TS_QN
     // all lanes: serve the oldest queued hit (ts_serve_entry)
     auto process_one = [&]() {
-      const TsServed r = ts_serve_entry<KP>(q_mine + (qhead % TS_QN) * TS_QSTRIDE, list_s, list_i, pq_s, pq_i, wrow0, thr, npend, lane);
+      const float* ev = q_mine + (qhead % TS_QN) * TS_QSTRIDE;
+      const TsServed r = ts_serve_entry<KP>(ev, __float_as_int(ev[32]), __float_as_int(ev[33]), list_s, list_i, pq_s, pq_i, wrow0,
+                                            thr, npend, lane);
       if (lane == r.owner) { npend = r.np; thr = r.thr; }
       ++qhead;
       __syncwarp();
@@ -861,84 +862,71 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->tmem_empty[buf][rb]);
       } else {
-        // Three of the four 32-column chunks are loaded at once; the fourth reuses the first chunk's registers once that
-        // chunk has been reduced (and, on a hit, queued): 96 score registers live instead of 128, which is what keeps
-        // this kernel free of local-memory traffic at 352 threads (168 registers per thread).
-        uint32_t va[32], vb[32], vc[32];
-        tmem_ld32(taddr, va); tmem_ld32(taddr + 32, vb); tmem_ld32(taddr + 64, vc);
+        // The warp pulls its whole 32 x 128 slice into registers and hands the TMEM buffer back BEFORE it looks at a
+        // single score: the MMA issuers wait for this release, and every cycle between "accumulator complete" and
+        // "buffer free" comes out of the one tile of slack the 3-deep accumulator ring provides.
+        uint32_t va[32], vb[32], vc[32], vd[32];
+        tmem_ld32(taddr, va); tmem_ld32(taddr + 32, vb); tmem_ld32(taddr + 64, vc); tmem_ld32(taddr + 96, vd);
         tmem_ld_wait();
-        tie_regs(va); tie_regs(vb); tie_regs(vc);
-        auto release = [&]() {                              // hand the TMEM buffer back to the MMA issuers
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->tmem_empty[buf][rb]);
-        };
+        tie_regs(va); tie_regs(vb); tie_regs(vc); tie_regs(vd);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->tmem_empty[buf][rb]);
         if constexpr (PRE) {
           // pre-pass: group maxima only (no lists, no slow path); a tile that runs past the library end is skipped
-          const float c0 = chunk_max32(va);
-          tmem_ld32(taddr + 96, va);
-          const float c1 = chunk_max32(vb), c2 = chunk_max32(vc);
-          tmem_ld_wait();
-          tie_regs(va);
-          release();
-          const float c3 = chunk_max32(va);
+          const float c0 = chunk_max32(va), c1 = chunk_max32(vb), c2 = chunk_max32(vc), c3 = chunk_max32(vd);
           if (n_valid == TC_BN) gm = fmaxf(gm, fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)));
           if (t + 1 == g_end || t + 1 == n_my_tiles) {
             if (grow < a.Q) a.gmax[((int64_t)split * a.pre_groups + gi) * a.Q + grow] = gm;
             gm = -INFINITY; ++gi; g_end += g_tiles;
           }
-        } else if (a.debug == 2) {
-          tmem_ld32(taddr + 96, va);
-          tmem_ld_wait();
-          tie_regs(va);
-          release();
-        } else {
-          // A hit costs the tile loop only the copy of its 32-score chunk into the queue (8 x 128-bit stores with static
-          // register indices + a header); everything serial happens later in process_one.  `m` = lanes whose chunk
-          // maximum beats their threshold; slots follow from ballot ranks.  If the queue lacks room (dense phases only:
-          // no pre-pass bound, tiny libraries) the hit lanes go in half a warp at a time, serving queued hits first.
-          auto enqueue = [&](const uint32_t (&v)[32], unsigned m, int c) {
-            const int key0 = tile_key0 + c * 32;
-            const int meta = lane | (max(min(32, n_valid - c * 32), 0) << 8);
-            const int n = __popc(m);
-            if (__builtin_expect(qtail - qhead + (unsigned)n <= (unsigned)TS_QN, 1)) {
-              if ((m >> lane) & 1u) queue_put(q_mine + ((qtail + __popc(m & ((1u << lane) - 1u))) % TS_QN) * TS_QSTRIDE, v, key0, meta);
-              qtail += n;
+        } else if (a.debug == 0) {
+          // fast path (registers only): four chunk maxima against the row threshold, ONE warp vote per tile
+          const float c0 = chunk_max32(va), c1 = chunk_max32(vb), c2 = chunk_max32(vc), c3 = chunk_max32(vd);
+          const bool h0 = c0 > thr, h1 = c1 > thr, h2 = c2 > thr, h3 = c3 > thr;
+          hit = h0 || h1 || h2 || h3;
+          if (__any_sync(0xffffffffu, hit)) {
+            // A hit costs the tile loop only the copy of its 32-score chunk into the queue (8 x 128-bit stores with static
+            // register indices + a header) at the slot its ballot rank says; everything serial happens in process_one.
+            const unsigned b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
+            const unsigned b2 = __ballot_sync(0xffffffffu, h2), b3 = __ballot_sync(0xffffffffu, h3);
+            const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
+            const int nv3 = max(n_valid - 96, 0);           // only the library's last tile can be short
+            if (__builtin_expect(qtail - qhead + (unsigned)(n0 + n1 + n2 + n3) <= (unsigned)TS_QN, 1)) {
+              const unsigned lt = (1u << lane) - 1u;
+              if (h0) queue_put(q_mine + ((qtail + __popc(b0 & lt)) % TS_QN) * TS_QSTRIDE, va, tile_key0, lane | (min(32, n_valid) << 8));
+              if (h1) queue_put(q_mine + ((qtail + n0 + __popc(b1 & lt)) % TS_QN) * TS_QSTRIDE, vb, tile_key0 + 32, lane | (max(min(32, n_valid - 32), 0) << 8));
+              if (h2) queue_put(q_mine + ((qtail + n0 + n1 + __popc(b2 & lt)) % TS_QN) * TS_QSTRIDE, vc, tile_key0 + 64, lane | (max(min(32, n_valid - 64), 0) << 8));
+              if (h3) queue_put(q_mine + ((qtail + n0 + n1 + n2 + __popc(b3 & lt)) % TS_QN) * TS_QSTRIDE, vd, tile_key0 + 96, lane | (min(32, nv3) << 8));
+              qtail += n0 + n1 + n2 + n3;
               __syncwarp();
             } else {
-#pragma unroll 1
-              for (int half = 0; half < 2; ++half) {
-                const unsigned mh = m & (half ? 0xffff0000u : 0x0000ffffu);
-                const int nh = __popc(mh);
-                while (qtail - qhead + (unsigned)nh > (unsigned)TS_QN) process_one();
-                if ((mh >> lane) & 1u) queue_put(q_mine + ((qtail + __popc(mh & ((1u << lane) - 1u))) % TS_QN) * TS_QSTRIDE, v, key0, meta);
-                qtail += nh;
-                __syncwarp();
+              // Queue overflow (dense phases only: no pre-pass bound yet, tiny or adversarial libraries).  Every lane
+              // parks its four chunks in this warp's private global-memory area -- after that no score register is live
+              // and the hits are served straight from the area, one (lane, chunk) at a time.
+              float* ov = a.overflow + ((size_t)blockIdx.x * TC_EPI_WARPS + warp) * (32 * TC_BN);
+              uint4* mine = reinterpret_cast<uint4*>(ov + lane * TC_BN);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                mine[j] = make_uint4(va[4 * j], va[4 * j + 1], va[4 * j + 2], va[4 * j + 3]);
+                mine[8 + j] = make_uint4(vb[4 * j], vb[4 * j + 1], vb[4 * j + 2], vb[4 * j + 3]);
+                mine[16 + j] = make_uint4(vc[4 * j], vc[4 * j + 1], vc[4 * j + 2], vc[4 * j + 3]);
+                mine[24 + j] = make_uint4(vd[4 * j], vd[4 * j + 1], vd[4 * j + 2], vd[4 * j + 3]);
               }
-            }
-          };
-          // fast path (registers only): chunk maxima against the row threshold, one warp vote for the first chunk (its
-          // registers are about to be reused) and one for the other three
-          const float c0 = chunk_max32(va);
-          const bool h0 = c0 > thr;
-          if (__any_sync(0xffffffffu, h0)) enqueue(va, __ballot_sync(0xffffffffu, h0), 0);
-          tmem_ld32(taddr + 96, va);
-          const float c1 = chunk_max32(vb), c2 = chunk_max32(vc);
-          tmem_ld_wait();
-          tie_regs(va);
-          release();
-          const float c3 = chunk_max32(va);
-          const bool h1 = c1 > thr, h2 = c2 > thr, h3 = c3 > thr;
-          hit = h0 || h1 || h2 || h3;
-          if (__any_sync(0xffffffffu, h1 || h2 || h3)) {
-            const unsigned b1 = __ballot_sync(0xffffffffu, h1), b2 = __ballot_sync(0xffffffffu, h2), b3 = __ballot_sync(0xffffffffu, h3);
+              __syncwarp();
 #pragma unroll 1
-            for (int c = 1; c < 4; ++c) {
-              const unsigned m = (c == 1) ? b1 : (c == 2) ? b2 : b3;
-              if (m == 0) continue;
-              if (c == 1) enqueue(vb, m, 1);
-              else if (c == 2) enqueue(vc, m, 2);
-              else enqueue(va, m, 3);
+              for (int c = 0; c < 4; ++c) {
+                unsigned m = (c == 0) ? b0 : (c == 1) ? b1 : (c == 2) ? b2 : b3;
+                const int nvc = max(min(32, n_valid - c * 32), 0);
+                while (m) {
+                  const int L = __ffs(m) - 1;
+                  m &= m - 1;
+                  const TsServed r = ts_serve_entry<KP>(ov + L * TC_BN + c * 32, tile_key0 + c * 32, L | (nvc << 8), list_s, list_i,
+                                                        pq_s, pq_i, wrow0, thr, npend, lane);
+                  if (lane == r.owner) { npend = r.np; thr = r.thr; }
+                  __syncwarp();
+                }
+              }
             }
           }
         }
@@ -1180,7 +1168,7 @@ static int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int d_
 struct TcPlan {
   int kh, kp, nstage, n_qtiles, n_splits, tiles_per_split, n_tiles, d_pad;
   size_t smem;
-  size_t off_qbf, off_qinv, off_ps, off_pi, off_fb, off_fbn, off_gmax, off_thr0, off_f32, total;
+  size_t off_qbf, off_qinv, off_ps, off_pi, off_fb, off_fbn, off_gmax, off_thr0, off_ovf, off_f32, total;
   int pre_tiles, pre_groups;          // threshold pre-pass (0 tiles = off)
 };
 
@@ -1241,10 +1229,13 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts) {
   if (ts && p.tiles_per_split >= pre_min) {
     int g = (2 * p.kp + p.n_splits - 1) / p.n_splits;
     if (g < 1) g = 1;
-    if ((int64_t)g * p.n_splits <= 256 && g <= p.tiles_per_split / 64) { p.pre_tiles = p.tiles_per_split / 64; p.pre_groups = g; }
+    int div = 64;
+    { const char* e = getenv("RAG_TC_PREPASS_DIV"); if (e && atoi(e) >= 4) div = atoi(e); }                    // experiments
+    if ((int64_t)g * p.n_splits <= 256 && g <= p.tiles_per_split / div) { p.pre_tiles = p.tiles_per_split / div; p.pre_groups = g; }
   }
   p.off_gmax = off; off += align_up((size_t)p.pre_groups * p.n_splits * Q * 4, 256);
   p.off_thr0 = off; off += align_up((size_t)Q * 4, 256);
+  p.off_ovf = off; off += ts ? align_up((size_t)p.n_qtiles * p.n_splits * TC_EPI_WARPS * 32 * TC_BN * 4, 256) : 0;
   p.off_f32 = off; off += topk_f32_rows_workspace(Q, N, d, k);
   p.total = off;
   return p;
@@ -1318,6 +1309,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   { const char* sw = getenv("RAG_TS_SWAP"); a.swap_halves = sw ? atoi(sw) : 0; }
   a.part_s = reinterpret_cast<float*>(w + p.off_ps);
   a.part_i = reinterpret_cast<int32_t*>(w + p.off_pi);
+  a.overflow = reinterpret_cast<float*>(w + p.off_ovf);
   if (ts) {
     auto run_ts = [&](const TcArgs& ta) -> int {
 #define RAG_TS_CASE(KH_, NS_, KP_) \
