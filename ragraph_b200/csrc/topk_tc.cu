@@ -1183,10 +1183,18 @@ static bool tc_shape_ok_ss(int d, int k) {
 // 32 for k <= 26 (d <= 128 only: 128 KB of lists + append buffers leave 4 pipeline stages, d > 128 needs 8)
 bool tc_shape_ok(int d, int k) { return d >= 1 && d <= 256 && k >= 1 && (k <= 10 || (k <= 26 && d <= 128)); }
 
-// RAG_TC_VARIANT=ss selects the older shared-memory-A kernel where it is instantiated (A/B measurements only)
-static bool tc_use_ts(int d, int k) {
+// Which filter kernel runs.  Measured on B200 (profiles/r1_midsize_ab.jsonl, r1_variant_ab_v4.jsonl): the query-stationary
+// TS kernel wins once a CTA streams many key tiles (12.5 M keys x 4096 queries: parity; 100 M: +6 %), because its hit
+// handling is built for the sparse steady state behind the pre-pass bound; short streams are one long warm-up phase, where
+// the SS kernel's lane-parallel list updates are 2-3x faster.  Default: TS from 8192 tiles per CTA, and for the shapes SS
+// does not instantiate.  RAG_TC_VARIANT=ss|ts forces one (A/B measurements, tests).
+constexpr int TS_MIN_TILES_PER_SPLIT = 8192;
+static bool tc_use_ts(int d, int k, int tiles_per_split) {
+  const bool ss_ok = tc_shape_ok_ss(d, k);
   const char* e = getenv("RAG_TC_VARIANT");
-  return !(e && e[0] == 's' && e[1] == 's' && tc_shape_ok_ss(d, k));
+  if (e && e[0] == 's' && e[1] == 's') return !ss_ok;
+  if (e && e[0] == 't' && e[1] == 's') return true;
+  return !ss_ok || tiles_per_split >= TS_MIN_TILES_PER_SPLIT;
 }
 
 static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts) {
@@ -1277,7 +1285,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
               "cosine_topk: tensor-core modes cover d <= 128 with k <= 26 and d <= 256 with k <= 10 (d=%d k=%d)", d, k);
   RAG_REQUIRE(key_inv_norm, RAG_EINVAL, "cosine_topk: the tensor-core modes need key_inv_norm (rag_row_inv_norm_f32)");
   RAG_REQUIRE(aligned16(keys_bf16), RAG_EALIGN, "cosine_topk: keys_bf16 must be 16-byte aligned");
-  const bool ts = tc_use_ts(d, k);
+  const bool ts = tc_use_ts(d, k, tc_plan(Q, N, d, k, true).tiles_per_split);
   TcPlan p = tc_plan(Q, N, d, k, ts);
   RAG_REQUIRE(ws_bytes >= p.total, RAG_EWORKSPACE, "cosine_topk: workspace %zu < %zu bytes", ws_bytes, p.total);
   RAG_REQUIRE(ws && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, RAG_EALIGN, "cosine_topk: workspace must be 256-byte aligned");

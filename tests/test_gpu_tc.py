@@ -13,10 +13,14 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 DEV = "cuda"
 
 
-@pytest.fixture(params=["ts", "ss"], autouse=True)
+@pytest.fixture(params=["ts", "ss", "auto"], autouse=True)
 def tc_variant(request, monkeypatch):
-    """ts = query tile stationary in tensor memory (default); ss = the shared-memory-A kernel (A/B reference)."""
-    monkeypatch.setenv("RAG_TC_VARIANT", request.param)
+    """ts = query tile stationary in tensor memory (long key streams); ss = query tile in shared memory (short streams);
+    auto = the library's own choice by stream length."""
+    if request.param == "auto":
+        monkeypatch.delenv("RAG_TC_VARIANT", raising=False)
+    else:
+        monkeypatch.setenv("RAG_TC_VARIANT", request.param)
     return request.param
 
 
