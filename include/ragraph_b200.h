@@ -110,6 +110,17 @@ RAG_API int rag_cosine_topk_f32(const float* q, int64_t Q, const float* keys, co
                         uint32_t flags, int64_t idx_offset, float* out_scores, int64_t* out_idx,
                         void* workspace, size_t workspace_bytes, rag_stream_t stream);
 
+/* Top-k with per-query exclusion lists, fp32 path: query row r never returns the key indices
+ * mask_col[mask_rowptr[r] .. mask_rowptr[r+1]) (global indices, i.e. including idx_offset; any order).  With
+ * RAG_SIM_DOT this is the edge variant's evaluation ranking -- rating = U @ I^T on the GPU, history items set to
+ * -inf, torch.topk(max(k)) on the CPU (RAGraph_edge/utils/metrics.py:48-53, 96-118) -- as ONE launch without the
+ * [B, n_items] rating matrix or its device-to-host copy.  Rows with fewer than k admissible keys are padded with
+ * index -1 / score -FLT_MAX.  Workspace: rag_cosine_topk_workspace(Q, N, d, k, RAG_SIM_FP32). */
+RAG_API int rag_topk_masked_f32(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, int64_t N,
+                        int32_t d, int32_t k, uint32_t flags, const int64_t* mask_rowptr, const int64_t* mask_col,
+                        int64_t idx_offset, float* out_scores, int64_t* out_idx, void* workspace,
+                        size_t workspace_bytes, rag_stream_t stream);
+
 /* weighted two-metric variant (RAGraph_node_fewshot/ragraph_utils/ToyGraphBase.py:47-79):
  * score = w_a * cos(qa, ka) + w_b * cos(qb, kb), fp32 path only. */
 RAG_API size_t rag_cosine2_topk_workspace(int64_t Q, int64_t N, int32_t da, int32_t db, int32_t k);

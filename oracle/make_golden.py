@@ -240,7 +240,26 @@ def gen_edge():
           out=torch.cat([ur, ir], 0))
 
 
+def gen_edge_eval():
+    """Evaluation ranking (utils/metrics.py:96-118, 210-214): rating = U @ I^T, history items set to -1e8, torch.topk."""
+    from utils.metrics import Metric
+    from modules.LightGCN import LightGCN
+    g = torch.Generator().manual_seed(2718)
+    B, ni, d, k = 40, 300, 16, 20
+    U = torch.randn(B, d, generator=g); I = torch.randn(ni, d, generator=g)
+    hist = {u: torch.randperm(ni, generator=g)[: int(torch.randint(0, 60, (1,), generator=g))].tolist() for u in range(B)}
+    m = object.__new__(Metric)
+    with torch.no_grad():
+        pred = LightGCN.rating(None, U, I).cpu()
+    pred = m._mask_history_pos(pred, list(range(B)), hist)
+    top_s, top_i = torch.topk(pred, k=k)
+    rowptr = torch.zeros(B + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(torch.tensor([len(hist[u]) for u in range(B)]), 0)
+    cols = torch.tensor([x for u in range(B) for x in hist[u]], dtype=torch.int64)
+    _save("edge_eval", U=U, I=I, hist_rowptr=rowptr, hist_items=cols, k=k, top_scores=top_s, top_items=top_i)
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
     _install_stubs()
-    gen_node(); gen_graph(); gen_node_fewshot(); gen_edge()
+    gen_node(); gen_graph(); gen_node_fewshot(); gen_edge(); gen_edge_eval()

@@ -238,6 +238,17 @@ def edge_forward(all_emb, edges, edge_norm, resource_keys, resource_values, num_
 # ----------------------------------------------------------------------------------------
 # multi-GPU restatement (new functionality, C1): merge of per-shard candidates
 # ----------------------------------------------------------------------------------------
+def rating_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, hist_rowptr, hist_items, k: int):
+    """Evaluation ranking, RAGraph_edge/utils/metrics.py:110-117 + 210-214: rating = user_emb @ item_emb.T
+    (LightGCN.rating, modules/LightGCN.py:115-116), every history item of a user set to -1e8, torch.topk(k)."""
+    pred = torch.matmul(user_emb, item_emb.t()).clone()
+    rp = [int(x) for x in hist_rowptr]
+    for i in range(pred.shape[0]):
+        pos_list = [int(x) for x in hist_items[rp[i]:rp[i + 1]]]
+        pred[i, pos_list] = -1e8
+    return torch.topk(pred, k=k)
+
+
 def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k: int):
     """scores/idx: [R, Q, k_r] per-shard candidates (idx already global).  Returns the
     global top-k with the deterministic order the product uses: score desc, index asc."""

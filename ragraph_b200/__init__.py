@@ -6,13 +6,13 @@ calling any op needs the built library and CUDA tensors (no CPU fallback).
 """
 from . import _lib, ops
 from .csr import CSRGraph, as_csr
-from .edge import EdgeAggregator, edge_rag_forward, scatter_add, scatter_sum
+from .edge import EdgeAggregator, edge_rag_forward, rating_topk, scatter_add, scatter_sum
 from .layers import GCN
 from .ragraph_utils import Propagation, SimilarityFunctions, TaskDecoder, ToyGraphBase
 from .RAGraph import RAGraph
 from .sharded import ShardedRetriever, owner_of, shard_bounds
 
-__all__ = ["_lib", "ops", "CSRGraph", "as_csr", "EdgeAggregator", "edge_rag_forward", "scatter_add", "scatter_sum",
+__all__ = ["_lib", "ops", "CSRGraph", "as_csr", "EdgeAggregator", "edge_rag_forward", "rating_topk", "scatter_add", "scatter_sum",
            "GCN", "Propagation", "SimilarityFunctions", "TaskDecoder", "ToyGraphBase", "RAGraph",
            "ShardedRetriever", "owner_of", "shard_bounds"]
 __version__ = "0.1.0"

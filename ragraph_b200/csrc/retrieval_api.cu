@@ -6,7 +6,7 @@ namespace rag {
 size_t topk_f32_workspace(int64_t Q, int64_t N, int d, int k);
 int topk_f32_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, int64_t N, int d, int k,
                  uint32_t flags, int64_t idx_offset, float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes,
-                 cudaStream_t s);
+                 cudaStream_t s, const int64_t* mask_rowptr = nullptr, const int64_t* mask_col = nullptr);
 // topk_tc.cu (tcgen05 filter + fp32 refine)
 size_t topk_tc_workspace(int64_t Q, int64_t N, int d, int k, int mode);
 bool topk_tc_available(int d, int k);
@@ -80,6 +80,18 @@ extern "C" int rag_cosine_topk_f32(const float* q, int64_t Q, const float* keys,
     default:
       return rag::fail(RAG_EINVAL, "cosine_topk: unknown mode %d", mode);
   }
+}
+
+extern "C" int rag_topk_masked_f32(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, int64_t N,
+                                   int32_t d, int32_t k, uint32_t flags, const int64_t* mask_rowptr,
+                                   const int64_t* mask_col, int64_t idx_offset, float* out_scores, int64_t* out_idx,
+                                   void* workspace, size_t workspace_bytes, rag_stream_t stream) {
+  int st = check_topk_args("topk_masked", q, Q, keys, N, d, k, out_scores, out_idx);
+  if (st || Q == 0) return st;
+  RAG_REQUIRE((mask_rowptr == nullptr) == (mask_col == nullptr) || mask_rowptr, RAG_EINVAL,
+              "topk_masked: mask_col without mask_rowptr");
+  return rag::topk_f32_run(q, Q, keys, key_inv_norm, N, d, k, flags, idx_offset, out_scores, out_idx, workspace,
+                           workspace_bytes, (cudaStream_t)stream, mask_rowptr, mask_rowptr ? mask_col : nullptr);
 }
 
 extern "C" size_t rag_cosine2_topk_workspace(int64_t Q, int64_t N, int32_t da, int32_t db, int32_t k) {

@@ -35,6 +35,9 @@ struct TopkArgs {
   float* dense_out;                               // MATERIALIZE: [Q, N]
   const int32_t* row_map;                         // optional: compact row r -> query row row_map[r]
   const int32_t* n_rows_dev;                      // optional: device-side count of rows in row_map
+  // optional exclusion lists (edge evaluation: a user's history items never rank, utils/metrics.py:48-53,113-115):
+  // query row r must not return the (global) key indices mask_col[mask_rowptr[r] .. mask_rowptr[r+1])
+  const int64_t* mask_rowptr; const int64_t* mask_col;
 };
 
 template <bool MATERIALIZE>
@@ -196,8 +199,18 @@ __global__ void __launch_bounds__(TK_THREADS, 2) cosine_topk_f32_kernel(const To
             m &= m - 1;
             const float sv = __shfl_sync(0xffffffffu, s, src);
             if (sv > t) {                         // t may have risen since the ballot
-              warp_sorted_insert<int32_t>(rv, ri, k, sv, (int32_t)(n0 - key_lo + c0 + src), lane);
-              t = rv[k - 1];
+              bool excluded = false;
+              if (a.mask_rowptr && q0 + row < Qeff) {         // only candidates pay for the membership test
+                const int64_t qr = a.row_map ? (int64_t)__ldg(a.row_map + q0 + row) : q0 + row;
+                const int64_t key = a.idx_offset + n0 + c0 + src;
+                const int64_t mlo = __ldg(a.mask_rowptr + qr), mhi = __ldg(a.mask_rowptr + qr + 1);
+                for (int64_t m0 = mlo; m0 < mhi && !excluded; m0 += 32)
+                  excluded = __any_sync(0xffffffffu, m0 + lane < mhi && __ldg(a.mask_col + m0 + lane) == key);
+              }
+              if (!excluded) {
+                warp_sorted_insert<int32_t>(rv, ri, k, sv, (int32_t)(n0 - key_lo + c0 + src), lane);
+                t = rv[k - 1];
+              }
             }
           }
         }
@@ -324,8 +337,10 @@ size_t topk_f32_workspace(int64_t Q, int64_t N, int d, int k) { return tk_plan(Q
 static int topk_f32_core(const float* q, int64_t Q, const float* keys, const float* key_inv_norm,
                          const float* q_inv_norm, int64_t N, int d, int k, int64_t idx_offset, const TkPlan& p,
                          unsigned char* w, const int32_t* row_map, const int32_t* n_rows_dev, float* out_scores,
-                         int64_t* out_idx, cudaStream_t s) {
+                         int64_t* out_idx, cudaStream_t s, const int64_t* mask_rowptr = nullptr,
+                         const int64_t* mask_col = nullptr) {
   TopkArgs a{};
+  a.mask_rowptr = mask_rowptr; a.mask_col = mask_col;
   a.q = q; a.Q = Q; a.keys = keys; a.key_inv_norm = key_inv_norm; a.q_inv_norm = q_inv_norm;
   a.N = N; a.d = d; a.k = k; a.keys_per_split = p.keys_per_split; a.n_splits = p.n_splits;
   a.idx_offset = idx_offset; a.row_map = row_map; a.n_rows_dev = n_rows_dev;
@@ -348,7 +363,7 @@ static int topk_f32_core(const float* q, int64_t Q, const float* keys, const flo
 
 int topk_f32_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, int64_t N, int d, int k,
                  uint32_t flags, int64_t idx_offset, float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes,
-                 cudaStream_t s) {
+                 cudaStream_t s, const int64_t* mask_rowptr, const int64_t* mask_col) {
   const bool dot = (flags & RAG_SIM_DOT) != 0;
   const bool need_kinv = !dot && key_inv_norm == nullptr;
   TkPlan p = tk_plan(Q, N, d, k, need_kinv);
@@ -367,7 +382,7 @@ int topk_f32_run(const float* q, int64_t Q, const float* keys, const float* key_
     }
   }
   return topk_f32_core(q, Q, keys, dot ? nullptr : (need_kinv ? kinv : key_inv_norm), dot ? nullptr : qinv, N, d, k,
-                       idx_offset, p, w, nullptr, nullptr, out_scores, out_idx, s);
+                       idx_offset, p, w, nullptr, nullptr, out_scores, out_idx, s, mask_rowptr, mask_col);
 }
 
 // fp32 path over a device-side list of rows (the tensor-core refine's uncertified rows).  The grid covers the

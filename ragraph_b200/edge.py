@@ -1,6 +1,7 @@
 """Mirror of the edge (link-prediction) variant's pieces of the hot path.
 
 scatter_sum / scatter_add : RAGraph_edge/modules/utils.py:17-38
+rating_topk               : RAGraph_edge/utils/metrics.py:48-53,96-118 (evaluation ranking)
 _agg                      : RAGraph_edge/modules/RAGraph.py:232-240
 retrieve loop + blend     : RAGraph_edge/modules/RAGraph.py:279-328
 """
@@ -95,3 +96,11 @@ def edge_rag_forward(all_emb: Tensor, edges: Tensor, edge_norm: Tensor, resource
     if train:                               # gradient reaches all_emb through the layer sum only (:327-328)
         return (1 - retrieve_weight) * total + retrieve_weight * out
     return out
+
+
+def rating_topk(user_emb: Tensor, item_emb: Tensor, k: int, hist_rowptr: Tensor, hist_items: Tensor) -> Tensor:
+    """Evaluation ranking of RAGraph_edge/utils/metrics.py:96-118 in one launch: top-k items by user . item, a user's
+    history items excluded (Metric._mask_history_pos sets them to -inf, :48-53).  hist_rowptr int64[B+1] / hist_items
+    int64[nnz] hold the batch users' history lists back to back.  Returns item indices int64 [B, k] like
+    ``torch.topk(batch_pred, k)[1]``; the [B, n_items] rating matrix and its .cpu() copy never exist."""
+    return ops.topk_masked(user_emb, item_emb, k, hist_rowptr, hist_items, L.SIM_DOT)[1]

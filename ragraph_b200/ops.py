@@ -134,6 +134,36 @@ def _(q, keys, k, key_inv_norm=None, keys_bf16=None, mode=0, flags=0, idx_offset
     return q.new_empty((q.shape[0], k)), q.new_empty((q.shape[0], k), dtype=torch.int64)
 
 
+@torch.library.custom_op("ragraph::topk_masked", mutates_args=())
+def topk_masked(q: Tensor, keys: Tensor, k: int, mask_rowptr: Tensor, mask_col: Tensor, flags: int = 0,
+                key_inv_norm: Optional[Tensor] = None, idx_offset: int = 0) -> Tuple[Tensor, Tensor]:
+    """Fused similarity + top-k where query row r never returns the key indices mask_col[mask_rowptr[r]:mask_rowptr[r+1]]
+    (int64 CSR of exclusions).  flags=SIM_DOT: plain dot product (edge evaluation ranking)."""
+    _need_cuda(q, keys, mask_rowptr, mask_col, key_inv_norm)
+    q, keys = _f32c(q, "topk_masked"), _f32c(keys, "topk_masked")
+    if q.dim() != 2 or keys.dim() != 2 or q.shape[1] != keys.shape[1]:
+        raise RuntimeError(f"topk_masked: shapes {tuple(q.shape)} vs {tuple(keys.shape)}")
+    Q, N, d = q.shape[0], keys.shape[0], q.shape[1]
+    if mask_rowptr.dtype != torch.int64 or mask_col.dtype != torch.int64 or mask_rowptr.numel() != Q + 1:
+        raise RuntimeError("topk_masked: mask_rowptr int64[Q+1] and mask_col int64[nnz] expected")
+    mask_rowptr, mask_col = mask_rowptr.contiguous(), mask_col.contiguous()
+    if key_inv_norm is not None:
+        key_inv_norm = _f32c(key_inv_norm, "key_inv_norm")
+    scores = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+    lib = L.load()
+    ws = _workspace(lib.rag_cosine_topk_workspace(Q, N, d, k, L.SIM_FP32), q.device)
+    with torch.cuda.device(q.device):
+        L.check(lib.rag_topk_masked_f32(_p(q), Q, _p(keys), _p(key_inv_norm), N, d, k, flags, _p(mask_rowptr), _p(mask_col),
+                                        idx_offset, _p(scores), _p(idx), _p(ws), ws.numel(), _stream()), "topk_masked")
+    return scores, idx
+
+
+@topk_masked.register_fake
+def _(q, keys, k, mask_rowptr, mask_col, flags=0, key_inv_norm=None, idx_offset=0):
+    return q.new_empty((q.shape[0], k)), q.new_empty((q.shape[0], k), dtype=torch.int64)
+
+
 @torch.library.custom_op("ragraph::cosine2_topk", mutates_args=())
 def cosine2_topk(qa: Tensor, ka: Tensor, w_a: float, qb: Tensor, kb: Tensor, w_b: float,
                  k: int) -> Tuple[Tensor, Tensor]:

@@ -47,6 +47,7 @@ class ToyGraphBase:
         self._keys = self._values = self._labels = self._positions = None
         self._inv_norm = self._keys_bf16 = None
         self._derived_rows = 0                # rows [0, _derived_rows) of inv_norm / bf16 shadow are valid
+        self.shard_lo = 0                     # global index of local row 0 (key-row sharded libraries)
         self._reserve(capacity)
 
     # ---- store ---------------------------------------------------------------------------
@@ -113,6 +114,72 @@ class ToyGraphBase:
 
     def __len__(self) -> int:
         return self._n
+
+    # ---- persistence (the reference rebuilds its library from the dataset at every construction,
+    #      ToyGraphBase.py:35-38 / RAGraph.py:27-28, and never saves it) ------------------------------------------
+    _FILES = (("keys", "_keys"), ("values", "_values"), ("labels", "_labels"), ("positions", "_positions"))
+
+    def save(self, path: str, chunk_rows: int = 1 << 20) -> None:
+        """Write the rows in use as raw little-endian arrays (<path>/keys.bin, values.bin, labels.bin[, positions.bin])
+        plus meta.json.  Streams device -> pinned host -> file in chunks, so a 100 M-row library needs no host copy of
+        itself.  Derived arrays (inverse norms, bf16 shadow) are not stored: they are one kernel pass on load."""
+        import json
+        import os
+        os.makedirs(path, exist_ok=True)
+        meta = {"format": "ragraph_b200.toygraphbase/1", "rows": self._n, "emb_size": self.emb_size,
+                "num_class": self.num_class, "variant": self.variant, "label_dtype": str(self._label_dtype).split(".")[-1],
+                "retrieve_num": self.retrieve_num, "noise_retrieve_num": self.noise_retrieve_num,
+                "structure_weight": self.structure_weight, "semantic_weight": self.semantic_weight,
+                "noise_std": self.noise_std, "toy_graph_hop": self.toy_graph_hop, "num_anchors": self.num_anchors,
+                "arrays": {}}
+        for name, attr in self._FILES:
+            t = getattr(self, attr)
+            if t is None:
+                continue
+            meta["arrays"][name] = {"dtype": str(t.dtype).split(".")[-1], "cols": int(t.shape[1])}
+            with open(os.path.join(path, name + ".bin"), "wb") as f:
+                for a in range(0, self._n, chunk_rows):
+                    b = min(self._n, a + chunk_rows)
+                    f.write(t[a:b].contiguous().cpu().numpy().tobytes())
+        with open(os.path.join(path, "meta.json"), "w") as f:
+            json.dump(meta, f, indent=1)
+
+    @classmethod
+    def load(cls, path: str, device=None, rows: Optional[Tuple[int, int]] = None, pretrain_model=None,
+             mode: Optional[int] = None, chunk_rows: int = 1 << 20) -> "ToyGraphBase":
+        """Rebuild a store from ``save()`` output.  ``rows=(lo, hi)`` loads only that row range -- one shard of a
+        key-row sharded library (``shard_bounds``); ``shard_lo`` is set so returned indices stay global."""
+        import json
+        import os
+        import numpy as np
+        with open(os.path.join(path, "meta.json")) as f:
+            meta = json.load(f)
+        if meta.get("format") != "ragraph_b200.toygraphbase/1":
+            raise RuntimeError(f"{path}: not a ragraph_b200 library (format {meta.get('format')!r})")
+        n_all = int(meta["rows"])
+        lo, hi = (0, n_all) if rows is None else (int(rows[0]), int(rows[1]))
+        if not (0 <= lo <= hi <= n_all):
+            raise RuntimeError(f"rows {rows} outside the stored library of {n_all} rows")
+        st = cls(pretrain_model, int(meta["num_class"]), int(meta["emb_size"]), int(meta["toy_graph_hop"]) + 1, device=device,
+                 variant=meta["variant"], capacity=max(hi - lo, 1), mode=mode, label_dtype=getattr(torch, meta["label_dtype"]))
+        for key in ("retrieve_num", "noise_retrieve_num", "structure_weight", "semantic_weight", "noise_std", "num_anchors"):
+            setattr(st, key, meta[key])
+        for name, attr in cls._FILES:
+            info = meta["arrays"].get(name)
+            dst = getattr(st, attr)
+            if info is None or dst is None:
+                continue
+            dt = getattr(torch, info["dtype"])
+            cols = int(info["cols"])
+            if dst.dtype != dt or dst.shape[1] != cols:
+                raise RuntimeError(f"{path}/{name}.bin: stored {info} does not match the store layout")
+            src = np.memmap(os.path.join(path, name + ".bin"), mode="r", dtype=np.dtype(info["dtype"]), shape=(n_all, cols))
+            for a in range(lo, hi, chunk_rows):
+                b = min(hi, a + chunk_rows)
+                dst[a - lo:b - lo].copy_(torch.from_numpy(np.ascontiguousarray(src[a:b])), non_blocking=False)
+        st._n = hi - lo
+        st.shard_lo = lo
+        return st
 
     def show(self):
         print('resource_keys', self.resource_keys.shape)

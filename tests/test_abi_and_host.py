@@ -99,3 +99,35 @@ def test_csr_transpose_and_row_normalized_host_logic():
     got = sp.csr_matrix((rn.val.numpy(), rn.col.numpy(), rn.rowptr.numpy()), shape=(n, m)).toarray()
     ok = deg[:, 0] > 0
     assert np.allclose(got[ok], want[ok], rtol=1e-6)
+
+
+def test_library_save_load_roundtrip_and_shards(tmp_path):
+    """ToyGraphBase.save / load is host I/O plus tensor copies: bit-exact round trip, int64 labels,
+    position codes of the few-shot variant, and loading one key-row shard with its global offset."""
+    from ragraph_b200 import ToyGraphBase
+    g = torch.Generator().manual_seed(4)
+    n, d, C = 1000, 24, 5
+    for variant, ldt in (("node", torch.float32), ("node_fewshot", torch.int64)):
+        st = ToyGraphBase(None, C, d, 3, device="cpu", variant=variant, capacity=16, label_dtype=ldt)
+        keys, vals = torch.randn(n, d, generator=g), torch.randn(n, d, generator=g)
+        vals[3, 0] = -0.0
+        labs = torch.nn.functional.one_hot(torch.randint(0, C, (n,), generator=g), C).to(ldt)
+        pos = torch.rand(n, 10, generator=g) if variant == "node_fewshot" else None
+        st.add_entries(keys[:600], vals[:600], labs[:600], None if pos is None else pos[:600])
+        st.add_entries(keys[600:], vals[600:], labs[600:], None if pos is None else pos[600:])
+        st.retrieve_num = 7
+        p = str(tmp_path / variant)
+        st.save(p, chunk_rows=333)
+        back = ToyGraphBase.load(p, device="cpu", chunk_rows=100)
+        assert len(back) == n and back.variant == variant and back.retrieve_num == 7 and back.shard_lo == 0
+        assert back.resource_labels.dtype == ldt
+        for a, b in ((back.resource_keys, keys), (back.resource_values, vals), (back.resource_labels, labs)):
+            assert torch.equal(a.view(torch.uint8).reshape(-1) if a.dtype.is_floating_point else a.reshape(-1),
+                               b.view(torch.uint8).reshape(-1) if b.dtype.is_floating_point else b.reshape(-1))
+        if pos is not None:
+            assert torch.equal(back.resource_positions, pos)
+        lo, hi = shard_bounds(n, 3, 1)
+        part = ToyGraphBase.load(p, device="cpu", rows=(lo, hi))
+        assert len(part) == hi - lo and part.shard_lo == lo and torch.equal(part.resource_keys, keys[lo:hi])
+    with pytest.raises(RuntimeError, match="outside"):
+        ToyGraphBase.load(p, device="cpu", rows=(10, n + 1))

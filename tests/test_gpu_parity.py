@@ -332,6 +332,45 @@ def test_edge_forward_golden(golden):
     assert O.rel_err(out, g["out"]) < REL
 
 
+# ------------------------------------------------------------------------------------------ edge evaluation ranking (8f rank 4)
+def test_edge_eval_ranking_golden(golden):
+    """rating + history mask + top-k (utils/metrics.py:110-117, 210-214) as one launch vs the reference's own output."""
+    g = golden("edge_eval")
+    k = int(g["k"])
+    items = R.rating_topk(cu(g["U"]), cu(g["I"]), k, cu(g["hist_rowptr"]), cu(g["hist_items"])).cpu().numpy()
+    S64 = g["U"].astype(np.float64) @ g["I"].astype(np.float64).T
+    rp = g["hist_rowptr"]
+    for r in range(S64.shape[0]):
+        S64[r, g["hist_items"][rp[r]:rp[r + 1]]] = -1e8
+        assert not set(items[r]) & set(g["hist_items"][rp[r]:rp[r + 1]].tolist())      # history never ranks
+    ok, bad = O.topk_sets_match(items, S64, k)
+    assert ok, bad[:5]
+    assert (items == g["top_items"]).mean() > 0.99                                      # same order barring fp32 ties
+    s, i = ops.topk_masked(cu(g["U"]), cu(g["I"]), k, cu(g["hist_rowptr"]), cu(g["hist_items"]), L.SIM_DOT)
+    assert np.max(np.abs(s.cpu().numpy() - np.take_along_axis(S64, i.cpu().numpy(), 1))) < 1e-5
+
+
+def test_topk_masked_edge_cases():
+    torch.manual_seed(8)
+    Q, N, d, k = 70, 5000, 32, 10
+    q, keys = torch.randn(Q, d, device=DEV), torch.randn(N, d, device=DEV)
+    # row 0: no exclusions; row 1: excludes its entire unmasked top-k; row 2: excludes everything but 4 keys (padding)
+    s0, i0 = ops.cosine_topk(q, keys, k)
+    lists = [torch.empty(0, dtype=torch.int64, device=DEV), i0[1].clone(),
+             torch.arange(4, N, device=DEV)] + [torch.randint(0, N, (37,), device=DEV) for _ in range(Q - 3)]
+    rowptr = torch.zeros(Q + 1, dtype=torch.int64, device=DEV)
+    rowptr[1:] = torch.cumsum(torch.tensor([len(x) for x in lists], device=DEV), 0)
+    s, i = ops.topk_masked(q, keys, k, rowptr, torch.cat(lists))
+    assert torch.equal(i[0], i0[0]) and torch.equal(s[0], s0[0])
+    assert not set(i[1].tolist()) & set(i0[1].tolist())
+    assert sorted(i[2][:4].tolist()) == [0, 1, 2, 3] and (i[2][4:] == -1).all()
+    S = torch.nn.functional.normalize(q.double(), dim=-1) @ torch.nn.functional.normalize(keys.double(), dim=-1).T
+    for r in range(3, Q):
+        S[r, lists[r]] = -float("inf")
+    ok, bad = O.topk_sets_match(i[3:].cpu().numpy(), S[3:].cpu().numpy(), k)
+    assert ok, bad[:5]
+
+
 # ------------------------------------------------------------------------------------------ autograd (SURVEY 8f rank 1)
 def test_spmm_backward_matches_dense_autograd():
     """dX = A^T dY through the same kernel on the transposed CSR vs torch's dense autograd (fp64 arbiter)."""

@@ -100,3 +100,9 @@ def test_merge_topk_matches_single_shard():
         parts_s.append(s); parts_i.append(i + lo)
     ms, mi = O.merge_topk(torch.stack(parts_s), torch.stack(parts_i), 5)
     assert torch.equal(ms, ref_s) and torch.equal(mi, ref_i)
+
+
+def test_edge_eval_ranking(golden):
+    g = golden("edge_eval")
+    s, i = O.rating_topk(T(g["U"]), T(g["I"]), g["hist_rowptr"], g["hist_items"], int(g["k"]))
+    assert np.array_equal(i.numpy(), g["top_items"]) and np.array_equal(s.numpy(), g["top_scores"])
