@@ -249,6 +249,31 @@ def rating_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, hist_rowptr, his
     return torch.topk(pred, k=k)
 
 
+def process_tu_arrays(xs, edge_indices, num_node_attributes: int):
+    """process_tu_dataset on plain arrays (RAGraph_node/ragraph_utils/utility.py:30-72): dense block-diagonal adjacency
+    via scipy coo -> todense per graph, then normalize_adj(adj + I).todense() (utils/process.py:208-215), float32."""
+    import scipy.sparse as sp
+    features = rawlabels = adjacency = None
+    for g, (x, e_ind) in enumerate(zip(xs, edge_indices)):
+        x = np.asarray(x); e_ind = np.asarray(e_ind)
+        f, l = x[:, :num_node_attributes], x[:, num_node_attributes:]
+        coo = sp.coo_matrix((np.ones(e_ind.shape[1]), (e_ind[0, :], e_ind[1, :])), shape=(x.shape[0], x.shape[0]))
+        tmpadj = coo.todense()
+        if g == 0:
+            features, rawlabels, adjacency = f, l, tmpadj
+        else:
+            features = np.vstack((features, f)); rawlabels = np.vstack((rawlabels, l))
+            zero = np.zeros((adjacency.shape[0], x.shape[0]))
+            adjacency = np.vstack((np.column_stack((adjacency, zero)), np.column_stack((zero.T, tmpadj))))
+    adj = sp.coo_matrix(sp.csr_matrix(adjacency) + sp.eye(adjacency.shape[0]))
+    rowsum = np.array(adj.sum(1))
+    d_inv_sqrt = np.power(rowsum, -0.5).flatten()
+    d_inv_sqrt[np.isinf(d_inv_sqrt)] = 0.
+    d = sp.diags(d_inv_sqrt)
+    adj = adj.dot(d).transpose().dot(d).tocoo().todense()
+    return torch.FloatTensor(np.asarray(features)), torch.FloatTensor(np.asarray(adj)), torch.FloatTensor(np.asarray(rawlabels))
+
+
 def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k: int):
     """scores/idx: [R, Q, k_r] per-shard candidates (idx already global).  Returns the
     global top-k with the deterministic order the product uses: score desc, index asc."""

@@ -11,8 +11,9 @@ from .layers import GCN
 from .ragraph_utils import Propagation, SimilarityFunctions, TaskDecoder, ToyGraphBase
 from .RAGraph import RAGraph
 from .sharded import ShardedRetriever, owner_of, shard_bounds
+from .utility import normalized_adjacency_csr, process_graph_batch
 
 __all__ = ["_lib", "ops", "CSRGraph", "as_csr", "EdgeAggregator", "edge_rag_forward", "rating_topk", "scatter_add", "scatter_sum",
            "GCN", "Propagation", "SimilarityFunctions", "TaskDecoder", "ToyGraphBase", "RAGraph",
-           "ShardedRetriever", "owner_of", "shard_bounds"]
+           "ShardedRetriever", "owner_of", "shard_bounds", "normalized_adjacency_csr", "process_graph_batch"]
 __version__ = "0.1.0"

@@ -204,10 +204,29 @@ class ToyGraphBase:
                 raise RuntimeError("node_fewshot retrieval needs search_positions (position-aware codes)")
             return ops.cosine2_topk(search_positions, self.resource_positions, self.structure_weight,
                                     search_keys, self.resource_keys, self.semantic_weight, k)
+        if k > L.RAG_MAX_K:
+            return self._topk_large(search_keys, k)
         mode = self._pick_mode(search_keys.shape[0], k)
         self._refresh_derived(mode != L.SIM_FP32)
         return ops.cosine_topk(search_keys, self.resource_keys, k, self._inv_norm[:self._n],
                                self._keys_bf16 if mode != L.SIM_FP32 else None, mode)
+
+    def _topk_large(self, search_keys: Tensor, k: int, budget_bytes: int = 1 << 30) -> Tuple[Tensor, Tensor]:
+        """k > RAG_MAX_K (the edge variant's vanilla configs ask for retrieve_num = 100000, i.e. most of the library,
+        RAGraph_edge/modules/RAGraph.py:57,73): outside the fused kernels.  The scores of a query chunk are materialised
+        by the CUDA similarity kernel ([chunk, N] fp32 bounded by ``budget_bytes``) and selected with torch.topk -- a
+        library call on a path that degenerates to "average almost everything"; k is clamped to the library size like
+        a user of the reference would have to."""
+        k = min(k, self._n)
+        Q = search_keys.shape[0]
+        chunk = max(1, min(Q, budget_bytes // max(4 * self._n, 1)))
+        scores = torch.empty((Q, k), dtype=torch.float32, device=search_keys.device)
+        idx = torch.empty((Q, k), dtype=torch.int64, device=search_keys.device)
+        for a in range(0, Q, chunk):
+            b = min(Q, a + chunk)
+            s = ops.cosine_similarity(search_keys[a:b], self.resource_keys)
+            scores[a:b], idx[a:b] = torch.topk(s, k, dim=1, largest=True, sorted=True)
+        return scores, idx
 
     def retrieve(self, search_keys: Tensor, search_adj, add_noise: bool, search_positions: Optional[Tensor] = None):
         """Same contract as the reference: returns (rag_embeddings[Q,k',d], rag_labels[Q,k',C]).

@@ -131,3 +131,27 @@ def test_library_save_load_roundtrip_and_shards(tmp_path):
         assert len(part) == hi - lo and part.shard_lo == lo and torch.equal(part.resource_keys, keys[lo:hi])
     with pytest.raises(RuntimeError, match="outside"):
         ToyGraphBase.load(p, device="cpu", rows=(10, n + 1))
+
+
+def test_process_graph_batch_matches_reference_dense_adjacency():
+    """CSR-direct preprocessing vs the oracle restatement of process_tu_dataset + normalize_adj:
+    asymmetric edges, duplicate edges, an isolated node, several graphs."""
+    import numpy as np
+    from oracle import ragraph_oracle as O
+    from ragraph_b200 import process_graph_batch
+    g = torch.Generator().manual_seed(12)
+    xs, eis = [], []
+    for n, E in ((7, 15), (1, 0), (12, 40), (5, 6)):
+        xs.append(torch.rand(n, 9, generator=g))
+        e = torch.randint(0, n, (2, E), generator=g)
+        if E >= 6:
+            e[:, 1] = e[:, 0]                                   # duplicate edge -> multiplicity 2
+        eis.append(e)
+    feats, csr, labs = process_graph_batch(xs, eis, 6)
+    rf, radj, rl = O.process_tu_arrays([x.numpy() for x in xs], [e.numpy() for e in eis], 6)
+    assert torch.equal(feats, rf) and torch.equal(labs, rl)
+    dense = torch.zeros(csr.n_rows, csr.n_cols)
+    rows = csr.row_ids()
+    dense[rows, csr.col.long()] = csr.val
+    assert torch.equal(dense != 0, radj != 0)
+    assert float((dense - radj).abs().max()) <= 1e-7

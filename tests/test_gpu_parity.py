@@ -332,6 +332,24 @@ def test_edge_forward_golden(golden):
     assert O.rel_err(out, g["out"]) < REL
 
 
+def test_topk_beyond_fused_k():
+    """k > RAG_MAX_K (edge vanilla configs, modules/RAGraph.py:57,73) takes the materialising path; k > N is clamped."""
+    torch.manual_seed(2)
+    N, d, Q = 3000, 64, 50
+    base = R.ToyGraphBase(None, 3, d, 3, device=DEV, capacity=N)
+    keys = torch.randn(N, d, device=DEV)
+    base.add_entries(keys, torch.randn(N, d, device=DEV), torch.zeros(N, 3, device=DEV))
+    q = torch.randn(Q, d, device=DEV)
+    s, i = base.topk(q, 500)
+    ref_s, ref_i = O.topk(O.cosine_similarity(q.cpu(), keys.cpu()), 500)
+    assert float((s.cpu() - ref_s).abs().max()) < 1e-5
+    S64 = O.cosine_similarity_f64(q.cpu().numpy(), keys.cpu().numpy())
+    ok, bad = O.topk_sets_match(i.cpu().numpy(), S64, 500)
+    assert ok, bad[:5]
+    s2, i2 = base.topk(q, 100000)
+    assert i2.shape == (Q, N) and torch.equal(i2.sort(dim=1).values, torch.arange(N, device=DEV).expand(Q, N))
+
+
 # ------------------------------------------------------------------------------------------ edge evaluation ranking (8f rank 4)
 def test_edge_eval_ranking_golden(golden):
     """rating + history mask + top-k (utils/metrics.py:110-117, 210-214) as one launch vs the reference's own output."""
