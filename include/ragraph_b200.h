@@ -212,6 +212,33 @@ RAG_API int rag_dense_count_rows(const float* adj, int64_t n_rows, int64_t n_col
 RAG_API int rag_dense_fill_csr(const float* adj, int64_t n_rows, int64_t n_cols, const int64_t* rowptr,
                        int32_t* col, float* val, rag_stream_t stream);
 
+/* ---- K10 / 8f-4: per-destination softmax over edge scalars ------------------------------ */
+/* out[e] = mix_a * base[e] + mix_b * softmax_{e' : index[e'] == index[e]}((src[e] - lo) / span), COO order.
+ * Replaces the min-max rescale + torch_scatter.scatter_softmax(edge_times, dst, dim_size) of
+ * RAGraph_edge/modules/RAGraph.py:250-263 and, with base = edge_norm and mix_a = mix_b = 0.5, the mix of :267.
+ * base nullable (then out = mix_b * softmax).  lo = 0, span = 1 gives torch_scatter.scatter_softmax itself.
+ * range_dev nullable: DEVICE float[2] = { min(src), max_step }; when given, lo = range_dev[0] and span =
+ * range_dev[1] - range_dev[0] are read on the device (the reference's tensor-valued min/max, no host sync).
+ * Entries whose index is outside [0, n_groups) get softmax 0.  The group sums use fp32 atomics: like the
+ * reference's kernel the summation order is not fixed (parity ~1e-6 relative). */
+RAG_API size_t rag_scatter_softmax_workspace(int64_t n_groups);
+RAG_API int rag_scatter_softmax_f32(const float* src, const int64_t* index, int64_t E, int64_t n_groups, float lo,
+                            float span, const float* range_dev, const float* base, float mix_a, float mix_b, float* out,
+                            void* workspace, size_t workspace_bytes, rag_stream_t stream);
+
+/* ---- a9: downstream prompt + class-prototype scores (downprompt.py) ---------------------- */
+/* out[n,d] = act(w[d] * x[n,d]); act 0 = identity (RAGraph_graph/downprompt.py:197-209), 1 = ELU
+ * (RAGraph_node/downprompt.py:118-130).  out may alias x. */
+RAG_API int rag_prompt_act_f32(const float* x, int64_t n, int32_t d, const float* w, int32_t act, float* out,
+                       rag_stream_t stream);
+/* out[n,C]: cosine of every (optionally prompted: act(w * x), w nullable) row against the C <= 32 class
+ * prototypes proto[C,d], torch.cosine_similarity semantics (each norm clamped at eps, default 1e-8), then
+ * mode 0 = raw scores, 1 = softmax over classes (RAGraph_node/downprompt.py:36-46), 2 = log_softmax
+ * (RAGraph_graph/downprompt.py:41-56 `predict`).  Replaces the reference's per-(row, class) Python loop. */
+RAG_API int rag_prototype_scores_f32(const float* x, int64_t n, int32_t d, const float* w, int32_t act,
+                             const float* proto, int32_t C, float eps, int32_t mode, float* out,
+                             rag_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -235,7 +235,7 @@ def gen_edge():
     with torch.no_grad():
         time_norm = fw._relative_edge_time_encoding(edges, times)
         ur, ir = RAGraph.forward(fw, edges, w, times)
-    _save("edge_forward", X=X, edges=edges, w=w, time_norm=time_norm, keys=keys, values=values,
+    _save("edge_forward", X=X, edges=edges, w=w, times=times, time_norm=time_norm, keys=keys, values=values,
           num_layers=args.num_layers, batch_size=32, retrieve_num=10, retrieve_weight=0.3,
           out=torch.cat([ur, ir], 0))
 
@@ -259,7 +259,136 @@ def gen_edge_eval():
     _save("edge_eval", U=U, I=I, hist_rowptr=rowptr, hist_items=cols, k=k, top_scores=top_s, top_items=top_i)
 
 
+def _fewshot_forward(variant, graph_level, seed, rw, lw, hop):
+    """Unmodified RAGraph.forward of a few-shot variant on a shim (RAGraph_node_fewshot/RAGraph.py:47-83,
+    RAGraph_graph_fewshot/RAGraph.py:46-91); encode returns fixed embeddings, decode is the variant's own GCN layer."""
+    _enter_variant(variant)
+    if graph_level:
+        # RAGraph_graph_fewshot/ragraph_utils/__init__.py:7 imports a module that is not in the repo, and
+        # FewShotBase (:2) is not on the forward path: stub the missing names, nothing of them is called
+        fu = types.ModuleType("ragraph_utils.fewshot_utility")
+        for nm in ("fewshot_predict_labels_by_mean", "fewshot_mean_logits", "fewshot_predict_logits", "fewshot_predict_labels"):
+            setattr(fu, nm, None)
+        sys.modules["ragraph_utils.fewshot_utility"] = fu
+    import importlib
+    from ragraph_utils.ToyGraphBase import ToyGraphBase
+    from layers.gcn import GCN
+    RAG = importlib.import_module("RAGraph").RAGraph
+    g = torch.Generator().manual_seed(seed)
+    nq, N, d, C = 26, 350, 32, (3 if not graph_level else 2)
+    adj = _sym_norm_adj(nq, 0.12, g)
+    emb_q = torch.randn(nq, d, generator=g)
+    keys = torch.nn.functional.normalize(torch.randn(N, d, generator=g), dim=-1)
+    values = torch.randn(N, d, generator=g)
+    labels = torch.nn.functional.one_hot(torch.randint(0, C, (N,), generator=g), C).float()
+    logits_table = torch.randn(C, C, generator=g)
+    torch.manual_seed(seed)
+    dec = GCN(d, C, 'prelu')
+    with torch.no_grad():
+        dec.bias.copy_(torch.randn(C, generator=g) * 0.1)
+
+    class _PM:
+        def encode(self, features, a):
+            return emb_q
+
+        def decode(self, hidden, a):
+            return dec((hidden, a))
+
+    base = object.__new__(ToyGraphBase)
+    base.retrieve_num, base.noise_retrieve_num = (5, 1) if not graph_level else (min(3, C + 1), 1)
+    base.resource_keys, base.resource_values, base.resource_labels = keys, values, labels
+    extra = {}
+    if not graph_level:
+        from ragraph_utils.PositionAwareEncoder import PositionAwareEncoder
+        base.num_anchors, base.dis_q = 10, 10
+        base.structure_weight, base.semantic_weight = 0.001, 0.999
+        base.resource_positions = torch.rand(N, 10, generator=g)
+        extra["positions"] = base.resource_positions
+    shim = object.__new__(RAG)
+    torch.nn.Module.__init__(shim)
+    shim.pretrain_model, shim.toy_graph_base = _PM(), base
+    shim.retrieve_weight, shim.label_weight, shim.finetune = rw, lw, True
+    shim.noise_finetune, shim.query_graph_hop = False, hop
+    shim.eval()
+    with torch.no_grad():
+        torch.manual_seed(seed + 1)                      # PositionAwareEncoder draws random anchors
+        out = shim.forward(None, adj, logits_table)
+        shim.finetune = False
+        torch.manual_seed(seed + 1)
+        vanilla = shim.forward(None, adj, logits_table)
+        if not graph_level:
+            torch.manual_seed(seed + 1)
+            extra["search_positions"] = PositionAwareEncoder.encode_position_aware_code(adj, 10, 10)
+    _save("fewshot_forward_" + ("graph" if graph_level else "node"), emb_q=emb_q, adj=adj, keys=keys, values=values,
+          labels=labels, mean_fewshot_logits=logits_table, dec_weight=dec.fc.weight.detach(), dec_bias=dec.bias.detach(),
+          dec_alpha=dec.act.weight.detach(), retrieve_num=base.retrieve_num, retrieve_weight=rw, label_weight=lw,
+          hop=hop, out=out, vanilla=vanilla, **extra)
+
+
+def gen_fewshot_forward():
+    _fewshot_forward("RAGraph_node_fewshot", False, 515, 0.5, 0.5, 3)
+    _fewshot_forward("RAGraph_graph_fewshot", True, 616, 0.3, 0.8, 1)
+
+
+def gen_downprompt():
+    """Downstream prompt heads (section 8 row a9).  The reference allocates its class-slot scratch with
+    torch.FloatTensor(...) -- UNINITIALISED memory -- and averages over it (RAGraph_node/downprompt.py:61,77;
+    RAGraph_graph/downprompt.py:60,93,102): its output is defined only when the unwritten slots are zero.  For the
+    duration of these calls torch.FloatTensor(sizes...) is patched to return zero-filled storage; nothing else of the
+    reference is touched."""
+    real_ft = torch.FloatTensor
+
+    def zero_ft(*a, **k):
+        if a and all(isinstance(x, int) for x in a):
+            return torch.zeros(*a)
+        return real_ft(*a, **k)
+
+    g = torch.Generator().manual_seed(8128)
+    try:
+        torch.FloatTensor = zero_ft
+        # ---- node variant: ELU(weight * emb), prototypes over n//2 slots, softmax of cosines
+        _enter_variant("RAGraph_node")
+        import importlib
+        dpn = importlib.import_module("downprompt")
+        n, d, C = 60, 24, 3
+        feature = torch.randn(1, n, d, generator=g)
+        labels = torch.randint(0, C, (n,), generator=g)
+        labels[:5] = torch.tensor([0, 1, 2, 0, 1])
+        seq = torch.randn(n, d, generator=g)
+        seq[7] = 0.0                                      # zero row: cosine eps clamp
+        p = torch.zeros(1, d)
+        torch.manual_seed(3)
+        m = dpn.downprompt(p, p, p, d, C, feature, labels)
+        with torch.no_grad():
+            ave0 = m.ave.clone()
+            prompted = m.downprompt(seq)
+            probs_eval = m.forward(seq, train=0)
+            probs_train = m.forward(seq, train=1)
+            ave1 = m.ave.clone()
+        _save("downprompt_node", feature=feature, labels=labels, seq=seq, weight=m.downprompt.weight.detach(),
+              ave_init=ave0, prompted=prompted, probs_eval=probs_eval, probs_train=probs_train, ave_train=ave1)
+
+        # ---- graph variant: weight * emb, per-graph sum readout, prototypes over n slots, log_softmax of cosines
+        _enter_variant("RAGraph_graph")
+        dpg = importlib.import_module("downprompt")
+        sizes = torch.tensor([5, 1, 9, 3, 12, 7, 2, 6])
+        nn_, C = int(sizes.sum()), 6
+        seq = torch.randn(nn_, d, generator=g)
+        torch.manual_seed(4)
+        mg = dpg.downprompt(p, p, p, d, C)
+        glabels = torch.tensor([0, 5, 2, 2, 1, 3, 4, 0])
+        with torch.no_grad():
+            gemb = mg.forward(seq, sizes)
+            ave = dpg.averageemb(glabels, gemb, C)
+            logp = dpg.predict(sizes.shape[0], C, gemb, ave)
+        _save("downprompt_graph", seq=seq, graph_sizes=sizes, weight=mg.downprompt.weight.detach(), graph_emb=gemb,
+              graph_labels=glabels, ave=ave, log_probs=logp)
+    finally:
+        torch.FloatTensor = real_ft
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
     _install_stubs()
     gen_node(); gen_graph(); gen_node_fewshot(); gen_edge(); gen_edge_eval()
+    gen_fewshot_forward(); gen_downprompt()

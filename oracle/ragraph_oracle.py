@@ -236,6 +236,105 @@ def edge_forward(all_emb, edges, edge_norm, resource_keys, resource_values, num_
 
 
 # ----------------------------------------------------------------------------------------
+# K10  edge time encoding (scatter_softmax is third-party torch_scatter 2.1.2, absent here:
+#      restated from its documented semantics -- softmax over the entries sharing an index)
+# ----------------------------------------------------------------------------------------
+def scatter_softmax(src: torch.Tensor, index: torch.Tensor, dim_size=None) -> torch.Tensor:
+    """torch_scatter.scatter_softmax(src, index, dim_size=...) as called at
+    RAGraph_edge/modules/RAGraph.py:261 (1-D src, 1-D index): exp(src - groupmax) / groupsum."""
+    n = int(dim_size) if dim_size is not None else int(index.max()) + 1
+    mx = torch.full((n,), -float("inf"), dtype=src.dtype).scatter_reduce(0, index, src, reduce="amax", include_self=True)
+    e = torch.exp(src - mx[index])
+    den = torch.zeros(n, dtype=src.dtype).scatter_add_(0, index, e)
+    return e / den[index]
+
+
+def relative_edge_time_encoding(edges: torch.Tensor, edge_times: torch.Tensor, num_nodes: int, max_step=None):
+    """RAGraph_edge/modules/RAGraph.py:250-263: min-max rescale to [0,1], softmax per destination node."""
+    edge_times = edge_times.float()
+    if max_step is None:
+        max_step = edge_times.max()
+    edge_times = (edge_times - edge_times.min()) / (max_step - edge_times.min())
+    return scatter_softmax(edge_times, edges[:, 1], dim_size=num_nodes)
+
+
+def edge_time_mix(edge_norm: torch.Tensor, time_norm: torch.Tensor) -> torch.Tensor:
+    """RAGraph_edge/modules/RAGraph.py:267."""
+    return edge_norm * 1 / 2 + time_norm * 1 / 2
+
+
+# ----------------------------------------------------------------------------------------
+# a9  downstream prompt (downprompt.py)
+# ----------------------------------------------------------------------------------------
+def downstream_prompt(graph_embedding: torch.Tensor, weight: torch.Tensor, elu: bool) -> torch.Tensor:
+    """RAGraph_node/downprompt.py:118-130 (weight * emb, then ELU) / RAGraph_graph/downprompt.py:197-209 (no ELU)."""
+    out = weight * graph_embedding
+    return F.elu(out) if elu else out
+
+
+def average_emb(labels: torch.Tensor, rawret: torch.Tensor, nb_class: int, slots: int) -> torch.Tensor:
+    """RAGraph_node/downprompt.py:59-79 (nb_class 3, slots = n // 2) / RAGraph_graph/downprompt.py:59-94 (slots = n):
+    rows of class c are packed into scratch[c, 0:cnt_c], then torch.mean over the slot axis.  The reference allocates
+    the scratch uninitialised (torch.FloatTensor(...)); its result is defined only if the unwritten slots are zero,
+    which is what is restated (and what oracle/make_golden.py pins by zero-filling that allocation)."""
+    retlabel = torch.zeros(nb_class, slots, rawret.shape[1])
+    cnt = [0] * nb_class
+    for x in range(rawret.shape[0]):
+        c = int(labels[x].item())
+        if 0 <= c < nb_class:
+            retlabel[c][cnt[c]] = rawret[x]
+            cnt[c] += 1
+    return torch.mean(retlabel, dim=1)
+
+
+def prototype_scores(rawret: torch.Tensor, ave: torch.Tensor, mode: str = "raw") -> torch.Tensor:
+    """RAGraph_node/downprompt.py:36-46 (softmax) / RAGraph_graph/downprompt.py:41-56 (log_softmax): one
+    torch.cosine_similarity(rawret[x], ave[c], dim=0) per (row, class)."""
+    ret = torch.empty(rawret.shape[0], ave.shape[0])
+    for x in range(rawret.shape[0]):
+        for c in range(ave.shape[0]):
+            ret[x][c] = torch.cosine_similarity(rawret[x], ave[c], dim=0)
+    if mode == "softmax":
+        return F.softmax(ret, dim=1)
+    if mode == "log_softmax":
+        return F.log_softmax(ret, dim=1)
+    return ret
+
+
+def split_and_batchify_graph_feats(batched_graph_feats: torch.Tensor, graph_sizes: torch.Tensor) -> torch.Tensor:
+    """RAGraph_graph/downprompt.py:98-112: per-graph sum over consecutive row blocks."""
+    cnt = 0
+    result = torch.zeros(graph_sizes.shape[0], batched_graph_feats.shape[1])
+    for i in range(graph_sizes.shape[0]):
+        n_i = int(graph_sizes[i].item())
+        result[i] = torch.sum(batched_graph_feats[cnt:cnt + n_i, :], dim=0)
+        cnt += n_i
+    return result
+
+
+# ----------------------------------------------------------------------------------------
+# a7  few-shot fusion (labels -> class id -> mean few-shot logits; decode = second GCN layer)
+# ----------------------------------------------------------------------------------------
+def fuse_fewshot(pretrain_emb, adj, rag_embeddings, rag_labels, mean_fewshot_logits, decode_params,
+                 retrieve_weight, label_weight, hop, finetune=True, graph_level=False):
+    """RAGraph_node_fewshot/RAGraph.py:47-83 (graph_level=False) and RAGraph_graph_fewshot/RAGraph.py:46-91
+    (graph_level=True: every node of the single query graph retrieves, the blended logits are averaged over nodes).
+    decode_params = (weight, bias, prelu_alpha) of the second GCN layer (models/gcnlayers.py `decode`)."""
+    rag_logits = mean_fewshot_logits[torch.argmax(rag_labels, dim=-1)]
+    rag_logits = torch.mean(rag_logits, dim=1)
+    if not finetune:
+        return rag_logits
+    rag_embedding = torch.sum(rag_embeddings, dim=1)
+    query_embeddings = aggregate_k_hop_features(adj, pretrain_emb, hop)
+    hidden = query_embeddings * (1 - retrieve_weight) + rag_embedding * retrieve_weight
+    decode_logits = gcn_layer(hidden, adj, *decode_params)
+    label_logits = decode_logits * (1 - label_weight) + rag_logits * label_weight
+    if graph_level:
+        label_logits = label_logits.mean(dim=0).unsqueeze(0)
+    return label_logits
+
+
+# ----------------------------------------------------------------------------------------
 # multi-GPU restatement (new functionality, C1): merge of per-shard candidates
 # ----------------------------------------------------------------------------------------
 def rating_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, hist_rowptr, hist_items, k: int):

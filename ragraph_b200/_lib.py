@@ -18,6 +18,8 @@ SIM_FP32, SIM_BF16, SIM_BF16_REFINE = 0, 2, 3
 SIM_DOT = 1
 EPI_ROWNORM, EPI_BIAS, EPI_RELU, EPI_PRELU, EPI_BLEND, EPI_ACCUM = 1, 2, 4, 8, 16, 32
 REDUCE_SUM, REDUCE_MEAN = 0, 1
+ACT_NONE, ACT_ELU = 0, 1
+SCORES_RAW, SCORES_SOFTMAX, SCORES_LOG_SOFTMAX = 0, 1, 2
 
 _p, _i64, _i32, _u32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_float, C.c_size_t
 
@@ -49,6 +51,10 @@ SIGNATURES = {
     "rag_coo_fill_csr": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p]),
     "rag_dense_count_rows": (C.c_int, [_p, _i64, _i64, _p, _p]),
     "rag_dense_fill_csr": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p]),
+    "rag_scatter_softmax_workspace": (_sz, [_i64]),
+    "rag_scatter_softmax_f32": (C.c_int, [_p, _p, _i64, _i64, _f32, _f32, _p, _p, _f32, _f32, _p, _p, _sz, _p]),
+    "rag_prompt_act_f32": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _p]),
+    "rag_prototype_scores_f32": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _i32, _f32, _i32, _p, _p]),
 }
 
 _lock = threading.Lock()

@@ -3,6 +3,7 @@
 scatter_sum / scatter_add : RAGraph_edge/modules/utils.py:17-38
 rating_topk               : RAGraph_edge/utils/metrics.py:48-53,96-118 (evaluation ranking)
 _agg                      : RAGraph_edge/modules/RAGraph.py:232-240
+time encoding             : RAGraph_edge/modules/RAGraph.py:250-263,266-267 (scatter_softmax over destination nodes)
 retrieve loop + blend     : RAGraph_edge/modules/RAGraph.py:279-328
 """
 from __future__ import annotations
@@ -39,6 +40,29 @@ def scatter_add(src, index, dim=-1, out=None, dim_size=None):
     return scatter_sum(src, index, dim, out, dim_size)
 
 
+def scatter_softmax(src: Tensor, index: Tensor, dim: int = 0, dim_size: Optional[int] = None) -> Tensor:
+    """torch_scatter.scatter_softmax for the form the hot path uses (1-D src, 1-D index): softmax over the entries
+    that share an index, result in the caller's order."""
+    if src.dim() != 1 or index.dim() != 1 or dim not in (0, -1):
+        raise NotImplementedError("scatter_softmax: only 1-D src / index (edge scalars grouped by destination node)")
+    if dim_size is None:
+        dim_size = int(index.max()) + 1 if index.numel() else 0
+    return ops.scatter_softmax(src.float(), index, int(dim_size))
+
+
+def relative_edge_time_encoding(edges: Tensor, edge_times: Tensor, num_nodes: int, max_step=None,
+                                edge_norm: Optional[Tensor] = None) -> Tensor:
+    """`_relative_edge_time_encoding` (modules/RAGraph.py:250-263): edge times min-max rescaled to [0,1], then a
+    softmax per destination node (edges[:,1]).  The rescale runs inside the kernel; with ``edge_norm`` given the
+    result is already the mixed edge weight of :267, ``edge_norm * 1/2 + time_norm * 1/2``."""
+    t = edge_times.float()
+    hi = t.max() if max_step is None else torch.as_tensor(max_step, dtype=torch.float32, device=t.device)
+    rng = torch.stack([t.min(), hi.reshape(())])          # stays on the device: no host sync for the min / max
+    if edge_norm is None:
+        return ops.scatter_softmax(t, edges[:, 1].contiguous(), num_nodes, range_dev=rng)
+    return ops.scatter_softmax(t, edges[:, 1].contiguous(), num_nodes, 0.0, 1.0, edge_norm, 0.5, 0.5, rng)
+
+
 class EdgeAggregator:
     """`_agg(all_emb, edges, edge_norm)` with the CSR built once per (edges, edge_norm) pair.
     Y[dst] = sum_e w_e * X[src_e]  (src = edges[:,0], dst = edges[:,1])."""
@@ -69,12 +93,16 @@ def edge_rag_forward(all_emb: Tensor, edges: Tensor, edge_norm: Tensor, resource
                      resource_values: Tensor, num_layers: int = 3, retrieve_num: int = 10, batch_size: int = 4096,
                      retrieve_weight: float = 0.3, key_inv_norm: Optional[Tensor] = None,
                      keys_bf16: Optional[Tensor] = None, mode: int = L.SIM_FP32,
-                     aggregator: Optional[EdgeAggregator] = None) -> Tensor:
-    """modules/RAGraph.py:279-328 without LoRA/gating/noise: LightGCN layer sum + retrieval blend.
+                     aggregator: Optional[EdgeAggregator] = None, edge_times: Optional[Tensor] = None,
+                     max_time_step=None) -> Tensor:
+    """modules/RAGraph.py:265-328 without LoRA/gating/noise: (time-aware edge weights when ``edge_times`` is given,
+    :266-267) + LightGCN layer sum + retrieval blend.
     res = (1-w) * (X0 + A X0 + A^2 X0 + A^3 X0) + w * mean_k values[topk(cos(X0, keys))].
     The layer sum rides in the SpMM epilogue (RAG_EPI_ACCUM); per 4096-query batch the retrieve is one fused
     similarity+top-k launch and the mean + convex blend one gather_reduce launch."""
     n = all_emb.shape[0]
+    if edge_times is not None:
+        edge_norm = relative_edge_time_encoding(edges, edge_times, n, max_time_step, edge_norm)
     agg = aggregator or EdgeAggregator(n)
     g = agg.csr(edges, edge_norm)
     train = torch.is_grad_enabled() and all_emb.requires_grad

@@ -363,5 +363,89 @@ def csr_from_dense(adj: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     return rowptr, col, val
 
 
+# ----------------------------------------------------------------------------- edge time encoding (K10)
+@torch.library.custom_op("ragraph::scatter_softmax", mutates_args=())
+def scatter_softmax(src: Tensor, index: Tensor, dim_size: int, lo: float = 0.0, span: float = 1.0,
+                    base: Optional[Tensor] = None, mix_a: float = 0.0, mix_b: float = 1.0,
+                    range_dev: Optional[Tensor] = None) -> Tensor:
+    """mix_a * base + mix_b * softmax over the entries sharing an index of (src - lo) / span; [E] in COO order.
+    Defaults = torch_scatter.scatter_softmax(src, index, dim_size=dim_size).  range_dev = device float32 [2]
+    {min, max_step}: lo / span are then read on the device (no host sync)."""
+    _need_cuda(src, index, base, range_dev)
+    if range_dev is not None:
+        range_dev = _f32c(range_dev, "range_dev")
+        if range_dev.numel() != 2:
+            raise RuntimeError("scatter_softmax: range_dev must hold {min, max_step}")
+    src = _f32c(src, "scatter_softmax")
+    if index.dtype != torch.int64 or index.dim() != 1 or src.dim() != 1 or index.numel() != src.numel():
+        raise RuntimeError("scatter_softmax: src f32 [E] and index int64 [E] expected")
+    index = index.contiguous()
+    if base is not None:
+        base = _f32c(base, "base")
+        if base.shape != src.shape:
+            raise RuntimeError("scatter_softmax: base must be [E]")
+    out = torch.empty_like(src)
+    lib = L.load()
+    ws = _workspace(lib.rag_scatter_softmax_workspace(dim_size), src.device)
+    if src.numel():
+        with torch.cuda.device(src.device):
+            L.check(lib.rag_scatter_softmax_f32(_p(src), _p(index), src.numel(), dim_size, lo, span, _p(range_dev), _p(base),
+                                                mix_a, mix_b, _p(out), _p(ws), ws.numel(), _stream()), "scatter_softmax")
+    return out
+
+
+@scatter_softmax.register_fake
+def _(src, index, dim_size, lo=0.0, span=1.0, base=None, mix_a=0.0, mix_b=1.0, range_dev=None):
+    return torch.empty_like(src)
+
+
+# ----------------------------------------------------------------------------- downstream prompt (a9)
+@torch.library.custom_op("ragraph::prompt_act", mutates_args=())
+def prompt_act(x: Tensor, w: Tensor, act: int = 0) -> Tensor:
+    """act(w * x): w [d] or [1,d]; act 0 identity, 1 ELU."""
+    _need_cuda(x, w)
+    x, w = _f32c(x, "prompt_act"), _f32c(w, "prompt_act").reshape(-1)
+    if x.dim() != 2 or w.numel() != x.shape[1]:
+        raise RuntimeError(f"prompt_act: x [n,d] and w [d] expected, got {tuple(x.shape)} and {tuple(w.shape)}")
+    out = torch.empty_like(x)
+    if x.numel():
+        with torch.cuda.device(x.device):
+            L.check(L.load().rag_prompt_act_f32(_p(x), x.shape[0], x.shape[1], _p(w), act, _p(out), _stream()),
+                    "prompt_act")
+    return out
+
+
+@prompt_act.register_fake
+def _(x, w, act=0):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op("ragraph::prototype_scores", mutates_args=())
+def prototype_scores(x: Tensor, proto: Tensor, mode: int = 0, w: Optional[Tensor] = None, act: int = 0,
+                     eps: float = 1e-8) -> Tensor:
+    """[n,C] cosine of every (optionally prompted) row of x against the class prototypes; mode 0 raw, 1 softmax,
+    2 log_softmax over the classes."""
+    _need_cuda(x, proto, w)
+    x, proto = _f32c(x, "prototype_scores"), _f32c(proto, "prototype_scores")
+    if x.dim() != 2 or proto.dim() != 2 or proto.shape[1] != x.shape[1]:
+        raise RuntimeError(f"prototype_scores: x [n,d] and proto [C,d] expected, got {tuple(x.shape)}, {tuple(proto.shape)}")
+    if w is not None:
+        w = _f32c(w, "w").reshape(-1)
+        if w.numel() != x.shape[1]:
+            raise RuntimeError("prototype_scores: w must have d entries")
+    n, d, C_ = x.shape[0], x.shape[1], proto.shape[0]
+    out = torch.empty((n, C_), dtype=torch.float32, device=x.device)
+    if n:
+        with torch.cuda.device(x.device):
+            L.check(L.load().rag_prototype_scores_f32(_p(x), n, d, _p(w), act, _p(proto), C_, eps, mode, _p(out),
+                                                      _stream()), "prototype_scores")
+    return out
+
+
+@prototype_scores.register_fake
+def _(x, proto, mode=0, w=None, act=0, eps=1e-8):
+    return x.new_empty((x.shape[0], proto.shape[0]))
+
+
 def gather_oob_count() -> int:
     return int(L.load().rag_gather_oob_count())

@@ -47,6 +47,8 @@ class ToyGraphBase:
         self._keys = self._values = self._labels = self._positions = None
         self._inv_norm = self._keys_bf16 = None
         self._derived_rows = 0                # rows [0, _derived_rows) of inv_norm / bf16 shadow are valid
+        self._class_ids = None                # argmax of the label rows (few-shot fusion), valid for _class_rows rows
+        self._class_rows = 0
         self.shard_lo = 0                     # global index of local row 0 (key-row sharded libraries)
         self._reserve(capacity)
 
@@ -111,6 +113,15 @@ class ToyGraphBase:
     def key_inv_norm(self) -> Tensor:
         self._refresh_derived(False)
         return self._inv_norm[:self._n]
+
+    def class_ids(self) -> Tensor:
+        """int64 [N]: argmax over the label columns of every library row -- what the few-shot fusion looks up per
+        retrieved row (``torch.argmax(rag_labels, dim=-1)``, RAGraph_node_fewshot/RAGraph.py:54); computed once per
+        library state instead of once per retrieved copy."""
+        if self._class_ids is None or self._class_rows != self._n:
+            self._class_ids = torch.argmax(self.resource_labels, dim=-1).contiguous()
+            self._class_rows = self._n
+        return self._class_ids
 
     def __len__(self) -> int:
         return self._n

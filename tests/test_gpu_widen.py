@@ -1,0 +1,206 @@
+"""GPU parity tests for the rows widened after the core path: downstream prompt (section 8 a9), few-shot fusion (a7,
+few-shot variants), edge time encoding (K10).  Same bar as tests/test_gpu_parity.py: everything goes through
+torch.ops.ragraph -> C ABI and is compared with the oracle / the reference-generated golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+import ragraph_b200 as R
+from ragraph_b200 import _lib as L
+from ragraph_b200 import downprompt as DP
+from ragraph_b200 import ops
+from oracle import ragraph_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+T = torch.from_numpy
+REL = 1e-5
+
+
+def cu(a):
+    return (T(a) if isinstance(a, np.ndarray) else a).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------ K10 time encoding
+def test_scatter_softmax_matches_oracle():
+    g = torch.Generator().manual_seed(5)
+    E, n = 20000, 700
+    index = torch.randint(0, n, (E,), generator=g)
+    index[index == 13] = 14                                   # an empty group
+    src = torch.randn(E, generator=g) * 3
+    out = ops.scatter_softmax(cu(src), cu(index), n).cpu()
+    ref = O.scatter_softmax(src, index, n)
+    assert O.rel_err(out, ref) < REL
+    sums = torch.zeros(n).index_add_(0, index, out)
+    present = torch.bincount(index, minlength=n) > 0
+    assert torch.allclose(sums[present], torch.ones(int(present.sum())), atol=1e-5)
+
+
+def test_scatter_softmax_edge_cases():
+    assert ops.scatter_softmax(torch.empty(0, device=DEV), torch.empty(0, dtype=torch.int64, device=DEV), 5).numel() == 0
+    one = ops.scatter_softmax(torch.tensor([3.0, -2.0, 100.0], device=DEV), torch.tensor([0, 1, 2], device=DEV), 3)
+    assert torch.equal(one.cpu(), torch.ones(3))              # singleton groups, large magnitudes: no overflow
+    big = ops.scatter_softmax(torch.tensor([1000.0, 999.0], device=DEV), torch.tensor([0, 0], device=DEV), 1).cpu()
+    assert O.rel_err(big, torch.softmax(torch.tensor([1000.0, 999.0]), 0)) < REL
+    with pytest.raises(RuntimeError):
+        ops.scatter_softmax(torch.zeros(3, device=DEV), torch.zeros(2, dtype=torch.int64, device=DEV), 1)
+
+
+def test_edge_time_encoding_golden(golden):
+    g = golden("edge_forward")
+    n = int(g["X"].shape[0])
+    tn = R.relative_edge_time_encoding(cu(g["edges"]), cu(g["times"]), n).cpu()
+    assert O.rel_err(tn, g["time_norm"]) < REL
+    mixed = R.relative_edge_time_encoding(cu(g["edges"]), cu(g["times"]), n, edge_norm=cu(g["w"])).cpu()
+    assert O.rel_err(mixed, O.edge_time_mix(T(g["w"]), T(g["time_norm"]))) < REL
+    # max_step given (RAGraph.forward(..., max_time_step)): oracle restatement
+    ms = float(g["times"].max()) * 1.5
+    tn2 = R.relative_edge_time_encoding(cu(g["edges"]), cu(g["times"]), n, max_step=ms).cpu()
+    assert O.rel_err(tn2, O.relative_edge_time_encoding(T(g["edges"]), T(g["times"]), n, torch.tensor(ms))) < REL
+
+
+def test_edge_forward_with_times_golden(golden):
+    """The whole modules/RAGraph.py:265-333 forward from raw edge times: time softmax + mix, 3 LightGCN layers,
+    per-batch retrieve + mean + blend, against the unmodified reference's output."""
+    g = golden("edge_forward")
+    out = R.edge_rag_forward(cu(g["X"]), cu(g["edges"]), cu(g["w"]), cu(g["keys"]), cu(g["values"]),
+                             int(g["num_layers"]), int(g["retrieve_num"]), int(g["batch_size"]),
+                             float(g["retrieve_weight"]), edge_times=cu(g["times"])).cpu()
+    assert O.rel_err(out, g["out"]) < REL
+
+
+# ------------------------------------------------------------------------------------------ a9 downstream prompt
+@pytest.mark.parametrize("d", [24, 64, 250, 256])
+@pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_ELU])
+def test_prompt_act(d, act):
+    g = torch.Generator().manual_seed(d + act)
+    x = torch.randn(333, d, generator=g) * 2
+    w = torch.randn(1, d, generator=g)
+    out = ops.prompt_act(cu(x), cu(w), act).cpu()
+    ref = O.downstream_prompt(x, w, elu=bool(act))
+    assert out.shape == ref.shape and O.rel_err(out, ref) < 1e-6
+    if act == L.ACT_NONE:
+        assert torch.equal(out, ref)                          # one fp32 multiply: bit exact
+
+
+@pytest.mark.parametrize("C,d,n", [(2, 24, 50), (3, 256, 777), (6, 64, 200), (7, 250, 129), (20, 32, 64), (32, 16, 40)])
+@pytest.mark.parametrize("mode", ["raw", "softmax", "log_softmax"])
+def test_prototype_scores(C, d, n, mode):
+    g = torch.Generator().manual_seed(C * 1000 + d)
+    x = torch.randn(n, d, generator=g)
+    x[3] = 0.0                                                # eps clamp row
+    proto = torch.randn(C, d, generator=g)
+    m = {"raw": L.SCORES_RAW, "softmax": L.SCORES_SOFTMAX, "log_softmax": L.SCORES_LOG_SOFTMAX}[mode]
+    out = ops.prototype_scores(cu(x), cu(proto), m).cpu()
+    xs = x[:64] if n > 64 else x                              # the oracle is a Python double loop
+    ref = O.prototype_scores(xs, proto, mode)
+    assert out.shape == (n, C)
+    assert float((out[:xs.shape[0]] - ref).abs().max()) < 2e-6
+    if mode == "softmax":
+        assert torch.allclose(out.sum(1), torch.ones(n), atol=1e-5)
+    # prompt applied on the fly == prompt materialised first
+    w = torch.randn(d, generator=g)
+    fused = ops.prototype_scores(cu(x), cu(proto), m, cu(w), L.ACT_ELU).cpu()
+    two = ops.prototype_scores(ops.prompt_act(cu(x), cu(w), L.ACT_ELU), cu(proto), m).cpu()
+    assert float((fused - two).abs().max()) < 2e-6
+
+
+def test_prototype_scores_limits():
+    x = torch.randn(4, 8, device=DEV)
+    with pytest.raises(RuntimeError, match="classes"):
+        ops.prototype_scores(x, torch.randn(33, 8, device=DEV))
+    with pytest.raises(RuntimeError):
+        ops.prototype_scores(x, torch.randn(3, 9, device=DEV))
+    assert ops.prototype_scores(torch.empty(0, 8, device=DEV), torch.randn(3, 8, device=DEV)).shape == (0, 3)
+
+
+def test_downprompt_node_golden(golden):
+    g = golden("downprompt_node")
+    d = g["seq"].shape[1]
+    p = torch.zeros(1, d, device=DEV)
+    m = DP.downprompt(p, p, p, d, 3, cu(g["feature"]), cu(g["labels"]))
+    m.downprompt.weight.data.copy_(cu(g["weight"]))
+    assert O.rel_err(m.ave.cpu(), g["ave_init"]) < REL
+    assert O.rel_err(m.downprompt(cu(g["seq"])).cpu(), g["prompted"]) < 1e-6
+    probs = m(cu(g["seq"]), 0).cpu()
+    assert float((probs - T(g["probs_eval"])).abs().max()) < 2e-6
+    probs_t = m(cu(g["seq"]), 1).cpu()
+    assert O.rel_err(m.ave.cpu(), g["ave_train"]) < REL
+    assert float((probs_t - T(g["probs_train"])).abs().max()) < 2e-6
+
+
+def test_downprompt_graph_golden(golden):
+    g = golden("downprompt_graph")
+    d = g["seq"].shape[1]
+    p = torch.zeros(1, d, device=DEV)
+    m = DP.downprompt(p, p, p, d, 6)
+    m.downprompt.weight.data.copy_(cu(g["weight"]))
+    gemb = m(cu(g["seq"]), cu(g["graph_sizes"]))
+    assert O.rel_err(gemb.cpu(), g["graph_emb"]) < REL
+    ave = DP.averageemb(cu(g["graph_labels"]), gemb, 6, slots=gemb.shape[0])
+    assert O.rel_err(ave.cpu(), g["ave"]) < REL
+    logp = DP.predict(gemb.shape[0], 6, gemb, ave).cpu()
+    assert float((logp - T(g["log_probs"])).abs().max()) < 5e-6
+
+
+def test_split_and_batchify_ragged():
+    g = torch.Generator().manual_seed(77)
+    sizes = torch.tensor([1, 0, 40, 3, 1500, 2])                # an empty graph, a long one (split-row path)
+    x = torch.randn(int(sizes.sum()), 48, generator=g)
+    out = DP.split_and_batchify_graph_feats(cu(x), cu(sizes)).cpu()
+    ref = O.split_and_batchify_graph_feats(x, sizes)
+    assert O.rel_err(out, ref) < REL and torch.all(out[1] == 0)
+
+
+# ------------------------------------------------------------------------------------------ a7 few-shot fusion
+class _FewShotBackbone:
+    """encode returns the fixed query embeddings; decode is the second GCN layer through the CUDA GCN mirror."""
+
+    def __init__(self, g):
+        self.emb = cu(g["emb_q"])
+        d, C = g["dec_weight"].shape[1], g["dec_weight"].shape[0]
+        self.layer = R.GCN(d, C, "prelu").to(DEV)
+        with torch.no_grad():
+            self.layer.fc.weight.copy_(cu(g["dec_weight"]))
+            self.layer.bias.copy_(cu(g["dec_bias"]))
+            self.layer.act.weight.copy_(cu(g["dec_alpha"]))
+
+    def encode(self, features, adj):
+        return self.emb
+
+    def decode(self, hidden, adj):
+        return self.layer((hidden, adj))
+
+
+def _fewshot_model(g, graph_level):
+    d, C = g["keys"].shape[1], g["labels"].shape[1]
+    base = R.ToyGraphBase(None, C, d, int(g["hop"]), device=DEV, variant="node" if graph_level else "node_fewshot")
+    base.retrieve_num = int(g["retrieve_num"])
+    base.add_entries(cu(g["keys"]), cu(g["values"]), cu(g["labels"]), None if graph_level else cu(g["positions"]))
+    return R.RAGraphFewShot(_FewShotBackbone(g), base, d, finetune=True, query_graph_hop=int(g["hop"]),
+                            retrieve_weight=float(g["retrieve_weight"]), label_weight=float(g["label_weight"]),
+                            graph_level=graph_level).eval()
+
+
+@pytest.mark.parametrize("graph_level", [False, True])
+def test_fewshot_forward_golden(golden, graph_level):
+    g = golden("fewshot_forward_graph" if graph_level else "fewshot_forward_node")
+    m = _fewshot_model(g, graph_level)
+    sp = None if graph_level else cu(g["search_positions"])
+    with torch.no_grad():
+        out = m(None, cu(g["adj"]), cu(g["mean_fewshot_logits"]), sp).cpu()
+        m.finetune = False
+        van = m(None, cu(g["adj"]), cu(g["mean_fewshot_logits"]), sp).cpu()
+    assert out.shape == g["out"].shape and van.shape == g["vanilla"].shape
+    assert float((out - T(g["out"])).abs().max()) < 5e-6
+    assert float((van - T(g["vanilla"])).abs().max()) < 1e-6
+
+
+def test_fewshot_noisy_branch_shapes(golden):
+    g = golden("fewshot_forward_node")
+    m = _fewshot_model(g, False)
+    m.noise_finetune = True
+    m.train()
+    with torch.no_grad():
+        out = m(None, cu(g["adj"]), cu(g["mean_fewshot_logits"]), cu(g["search_positions"]))
+    assert out.shape == g["out"].shape and bool(torch.isfinite(out).all())

@@ -106,3 +106,73 @@ def test_edge_eval_ranking(golden):
     g = golden("edge_eval")
     s, i = O.rating_topk(T(g["U"]), T(g["I"]), g["hist_rowptr"], g["hist_items"], int(g["k"]))
     assert np.array_equal(i.numpy(), g["top_items"]) and np.array_equal(s.numpy(), g["top_scores"])
+
+
+def test_edge_time_encoding(golden):
+    g = golden("edge_forward")
+    edges, times = T(g["edges"]), T(g["times"])
+    tn = O.relative_edge_time_encoding(edges, times, int(g["X"].shape[0]))
+    np.testing.assert_allclose(tn.numpy(), g["time_norm"], rtol=0, atol=1e-7)
+    # every destination's weights sum to one
+    sums = torch.zeros(int(g["X"].shape[0])).index_add_(0, edges[:, 1], tn)
+    present = torch.zeros(int(g["X"].shape[0])).index_add_(0, edges[:, 1], torch.ones_like(tn)) > 0
+    assert torch.allclose(sums[present], torch.ones(int(present.sum())), atol=1e-5)
+    w = O.edge_time_mix(T(g["w"]), tn)
+    out = O.edge_forward(T(g["X"]), edges, w, T(g["keys"]), T(g["values"]), int(g["num_layers"]),
+                         int(g["retrieve_num"]), int(g["batch_size"]), float(g["retrieve_weight"]))
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=0, atol=5e-6)
+
+
+def _fewshot_oracle(g, graph_level):
+    emb_q, adj = T(g["emb_q"]), T(g["adj"])
+    keys, values, labels = T(g["keys"]), T(g["values"]), T(g["labels"])
+    k = int(g["retrieve_num"])
+    if graph_level:
+        _, _, emb, lab = O.retrieve(emb_q, keys, values, labels, k)
+    else:
+        _, _, emb, lab = O.retrieve_two_metric(emb_q, T(g["search_positions"]), keys, T(g["positions"]), values, labels, k)
+    dec = (T(g["dec_weight"]), T(g["dec_bias"]), T(g["dec_alpha"]))
+    args = (emb_q, adj, emb, lab, T(g["mean_fewshot_logits"]), dec, float(g["retrieve_weight"]), float(g["label_weight"]),
+            int(g["hop"]))
+    return O.fuse_fewshot(*args, finetune=True, graph_level=graph_level), O.fuse_fewshot(*args, finetune=False,
+                                                                                        graph_level=graph_level)
+
+
+def test_fewshot_forward_node(golden):
+    g = golden("fewshot_forward_node")
+    out, van = _fewshot_oracle(g, False)
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=0, atol=1e-6)
+    assert np.array_equal(van.numpy(), g["vanilla"])
+
+
+def test_fewshot_forward_graph(golden):
+    g = golden("fewshot_forward_graph")
+    out, van = _fewshot_oracle(g, True)
+    assert out.shape == (1, 2)
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=0, atol=1e-6)
+    assert np.array_equal(van.numpy(), g["vanilla"])
+
+
+def test_downprompt_node(golden):
+    g = golden("downprompt_node")
+    labels, seq, w = T(g["labels"]), T(g["seq"]), T(g["weight"])
+    n = seq.shape[0]
+    ave0 = O.average_emb(labels, T(g["feature"]).squeeze(), 3, n // 2)
+    assert np.array_equal(ave0.numpy(), g["ave_init"])
+    prompted = O.downstream_prompt(seq, w, elu=True)
+    assert np.array_equal(prompted.numpy(), g["prompted"])
+    np.testing.assert_allclose(O.prototype_scores(prompted, ave0, "softmax").numpy(), g["probs_eval"], rtol=0, atol=1e-7)
+    ave1 = O.average_emb(labels, prompted, 3, n // 2)
+    assert np.array_equal(ave1.numpy(), g["ave_train"])
+    np.testing.assert_allclose(O.prototype_scores(prompted, ave1, "softmax").numpy(), g["probs_train"], rtol=0, atol=1e-7)
+    assert np.all(np.isfinite(g["probs_eval"][7]))            # zero row: eps clamp, uniform probabilities
+
+
+def test_downprompt_graph(golden):
+    g = golden("downprompt_graph")
+    seq, sizes = T(g["seq"]), T(g["graph_sizes"])
+    gemb = O.split_and_batchify_graph_feats(O.downstream_prompt(seq, T(g["weight"]), elu=False), sizes)
+    assert np.array_equal(gemb.numpy(), g["graph_emb"])
+    ave = O.average_emb(T(g["graph_labels"]), gemb, 6, gemb.shape[0])
+    assert np.array_equal(ave.numpy(), g["ave"])
+    np.testing.assert_allclose(O.prototype_scores(gemb, ave, "log_softmax").numpy(), g["log_probs"], rtol=0, atol=1e-6)
