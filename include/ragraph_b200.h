@@ -51,6 +51,8 @@ enum rag_status {
 /* similarity modes of rag_cosine_topk_f32 */
 enum rag_sim_mode {
   RAG_SIM_FP32 = 0,       /* fp32 FMA on CUDA cores, exact-order oracle-grade path */
+  RAG_SIM_TF32 = 1,       /* tcgen05 tf32 x tf32 -> fp32 in TMEM, raw approximate scores (|err| <= 2^-10 for unit
+                             vectors); d <= 64 with k <= 26, d <= 128 with k <= 10 */
   RAG_SIM_BF16 = 2,       /* tcgen05 bf16 x bf16 -> fp32 in TMEM, raw approximate scores */
   RAG_SIM_BF16_REFINE = 3 /* bf16 tensor-core filter + fp32 re-score + certificate; results
                              equal RAG_SIM_FP32 (uncertified rows are recomputed in fp32) */
@@ -88,6 +90,13 @@ RAG_API int rag_row_inv_norm_f32(const float* x, int64_t rows, int32_t d, float 
 RAG_API int rag_rows_to_bf16(const float* x, int64_t rows, int32_t d, int32_t normalize, float eps,
                      uint16_t* out, int32_t d_pad, rag_stream_t stream);
 
+/* tf32 shadow of the key matrix for RAG_SIM_TF32: out[r, 0:d] = tf32_rn(x[r,:] * (normalize ? 1/max(||x[r]||,eps) : 1))
+ * stored as fp32 words (low 13 mantissa bits zero), columns d..d_pad-1 zero filled; d_pad = rag_tf32_shadow_dpad(d)
+ * (32, 64 or 128; 0 if d > 128), out is [rows, d_pad] fp32, 16-byte aligned. */
+RAG_API int32_t rag_tf32_shadow_dpad(int32_t d);
+RAG_API int rag_rows_to_tf32(const float* x, int64_t rows, int32_t d, int32_t normalize, float eps, float* out,
+                     int32_t d_pad, rag_stream_t stream);
+
 /* ---- a1/K2: materialised similarity (API compatibility) ------------------------------- */
 /* out[Q,N] = cosine (or dot with RAG_SIM_DOT) similarity, fp32.
  * Replaces SimilarityFunctions.calculate_cosine_similarity (SimilarityFunctions.py:6-16). */
@@ -100,13 +109,14 @@ RAG_API int rag_cosine_similarity_f32(const float* q, int64_t Q, const float* ke
 /* Replaces calculate_cosine_similarity + torch.topk(largest, sorted)
  * (ToyGraphBase.py:53,67; RAGraph_edge/modules/RAGraph.py:303,311).
  *   q[Q,d], keys[N,d] fp32.  key_inv_norm[N] nullable (computed into workspace if null and
- *   cosine).  keys_bf16 [N,d_pad] nullable: the shadow made by rag_rows_to_bf16 (normalised
- *   unless RAG_SIM_DOT); REQUIRED for the BF16 modes.  d_pad = round_up(d, 64).
+ *   cosine).  keys_shadow nullable: REQUIRED for the tensor-core modes -- the bf16 shadow [N, round_up(d,64)] made
+ *   by rag_rows_to_bf16 for the BF16 modes, the tf32 shadow [N, rag_tf32_shadow_dpad(d)] fp32 made by
+ *   rag_rows_to_tf32 for RAG_SIM_TF32 (both L2-normalised).
  *   out_scores[Q,k] fp32 descending; out_idx[Q,k] int64 = idx_offset + local row; order is
  *   deterministic: score desc, index asc.  Requires 1 <= k <= min(N, RAG_MAX_K). */
 RAG_API size_t rag_cosine_topk_workspace(int64_t Q, int64_t N, int32_t d, int32_t k, int32_t mode);
 RAG_API int rag_cosine_topk_f32(const float* q, int64_t Q, const float* keys, const float* key_inv_norm,
-                        const uint16_t* keys_bf16, int64_t N, int32_t d, int32_t k, int32_t mode,
+                        const void* keys_shadow, int64_t N, int32_t d, int32_t k, int32_t mode,
                         uint32_t flags, int64_t idx_offset, float* out_scores, int64_t* out_idx,
                         void* workspace, size_t workspace_bytes, rag_stream_t stream);
 

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libragraph_b200.so")
 
 RAG_OK = 0
 RAG_MAX_K = 128
-SIM_FP32, SIM_BF16, SIM_BF16_REFINE = 0, 2, 3
+SIM_FP32, SIM_TF32, SIM_BF16, SIM_BF16_REFINE = 0, 1, 2, 3
 SIM_DOT = 1
 EPI_ROWNORM, EPI_BIAS, EPI_RELU, EPI_PRELU, EPI_BLEND, EPI_ACCUM = 1, 2, 4, 8, 16, 32
 REDUCE_SUM, REDUCE_MEAN = 0, 1
@@ -32,6 +32,8 @@ SIGNATURES = {
     "rag_sim_mode_supported": (C.c_int, [_i32, _i32, _i32]),
     "rag_row_inv_norm_f32": (C.c_int, [_p, _i64, _i32, _f32, _p, _p]),
     "rag_rows_to_bf16": (C.c_int, [_p, _i64, _i32, _i32, _f32, _p, _i32, _p]),
+    "rag_tf32_shadow_dpad": (_i32, [_i32]),
+    "rag_rows_to_tf32": (C.c_int, [_p, _i64, _i32, _i32, _f32, _p, _i32, _p]),
     "rag_cosine_similarity_workspace": (_sz, [_i64, _i64]),
     "rag_cosine_similarity_f32": (C.c_int, [_p, _i64, _p, _i64, _i32, _u32, _p, _p, _sz, _p]),
     "rag_cosine_topk_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),

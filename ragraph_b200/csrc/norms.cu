@@ -51,7 +51,44 @@ __global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restri
   }
 }
 
+// tf32 shadow: fp32 words whose low 13 mantissa bits are already zero (cvt.rna = round to nearest, ties away), so the
+// tensor core's truncation of kind::tf32 operands is exact and the per-element error is 2^-11 instead of 2^-10
+__global__ void __launch_bounds__(256) rows_to_tf32_kernel(const float* __restrict__ x, int64_t rows, int d,
+                                                           int normalize, float eps, float* __restrict__ out,
+                                                           int d_pad) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float* xr = x + r * d;
+    float inv = 1.0f;
+    if (normalize) inv = 1.0f / fmaxf(sqrtf(row_sumsq(xr, d, lane)), eps);
+    float* o = out + r * d_pad;
+    for (int c = lane; c < d_pad; c += 32) {
+      const float v = c < d ? __ldg(xr + c) * inv : 0.f;
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+      o[c] = __uint_as_float(u);
+    }
+  }
+}
+
 }  // namespace rag
+
+extern "C" int rag_rows_to_tf32(const float* x, int64_t rows, int32_t d, int32_t normalize, float eps, float* out,
+                                int32_t d_pad, rag_stream_t stream) {
+  RAG_REQUIRE(rows >= 0 && d >= 1 && d_pad >= d && d_pad % 32 == 0, RAG_EINVAL,
+              "rows_to_tf32: rows=%lld d=%d d_pad=%d (d_pad must be a multiple of 32, >= d)", (long long)rows, d, d_pad);
+  if (rows == 0) return RAG_OK;
+  RAG_REQUIRE(x && out, RAG_EINVAL, "rows_to_tf32: null pointer");
+  RAG_REQUIRE(rag::aligned16(out), RAG_EALIGN, "rows_to_tf32: out not 16-byte aligned");
+  int64_t blocks = (rows + 7) / 8;
+  int64_t cap = (int64_t)rag::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  rag::rows_to_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, d, normalize, eps, out, d_pad);
+  RAG_LAUNCH_OK("rows_to_tf32_kernel");
+  return RAG_OK;
+}
 
 extern "C" int rag_row_inv_norm_f32(const float* x, int64_t rows, int32_t d, float eps, float* out,
                                     rag_stream_t stream) {

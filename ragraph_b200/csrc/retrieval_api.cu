@@ -10,7 +10,9 @@ int topk_f32_run(const float* q, int64_t Q, const float* keys, const float* key_
 // topk_tc.cu (tcgen05 filter + fp32 refine)
 size_t topk_tc_workspace(int64_t Q, int64_t N, int d, int k, int mode);
 bool topk_tc_available(int d, int k);
-int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const uint16_t* keys_bf16,
+bool topk_tc_tf32_available(int d, int k);
+int topk_tc_tf32_dpad(int d);
+int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const void* keys_shadow,
                 int64_t N, int d, int k, int mode, uint32_t flags, int64_t idx_offset, float* out_scores,
                 int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s);
 
@@ -51,8 +53,11 @@ static int check_topk_args(const char* fn, const float* q, int64_t Q, const floa
 extern "C" int rag_sim_mode_supported(int32_t mode, int32_t d, int32_t k) {
   if (mode == RAG_SIM_FP32) return (d >= 1 && k >= 1 && k <= RAG_MAX_K) ? 1 : 0;
   if (mode == RAG_SIM_BF16 || mode == RAG_SIM_BF16_REFINE) return rag::topk_tc_available(d, k) ? 1 : 0;
+  if (mode == RAG_SIM_TF32) return rag::topk_tc_tf32_available(d, k) ? 1 : 0;
   return 0;
 }
+
+extern "C" int32_t rag_tf32_shadow_dpad(int32_t d) { return (d >= 1 && d <= 128) ? rag::topk_tc_tf32_dpad(d) : 0; }
 
 extern "C" size_t rag_cosine_topk_workspace(int64_t Q, int64_t N, int32_t d, int32_t k, int32_t mode) {
   if (Q <= 0 || N <= 0 || d < 1 || k < 1) return 256;
@@ -62,7 +67,7 @@ extern "C" size_t rag_cosine_topk_workspace(int64_t Q, int64_t N, int32_t d, int
 }
 
 extern "C" int rag_cosine_topk_f32(const float* q, int64_t Q, const float* keys, const float* key_inv_norm,
-                                   const uint16_t* keys_bf16, int64_t N, int32_t d, int32_t k, int32_t mode,
+                                   const void* keys_shadow, int64_t N, int32_t d, int32_t k, int32_t mode,
                                    uint32_t flags, int64_t idx_offset, float* out_scores, int64_t* out_idx,
                                    void* workspace, size_t workspace_bytes, rag_stream_t stream) {
   int st = check_topk_args("cosine_topk", q, Q, keys, N, d, k, out_scores, out_idx);
@@ -72,10 +77,11 @@ extern "C" int rag_cosine_topk_f32(const float* q, int64_t Q, const float* keys,
     case RAG_SIM_FP32:
       return rag::topk_f32_run(q, Q, keys, key_inv_norm, N, d, k, flags, idx_offset, out_scores, out_idx, workspace,
                                workspace_bytes, s);
+    case RAG_SIM_TF32:
     case RAG_SIM_BF16:
     case RAG_SIM_BF16_REFINE:
-      RAG_REQUIRE(keys_bf16, RAG_EINVAL, "cosine_topk: mode %d needs the bf16 key shadow (rag_rows_to_bf16)", mode);
-      return rag::topk_tc_run(q, Q, keys, key_inv_norm, keys_bf16, N, d, k, mode, flags, idx_offset, out_scores,
+      RAG_REQUIRE(keys_shadow, RAG_EINVAL, "cosine_topk: mode %d needs the key shadow (rag_rows_to_bf16 / rag_rows_to_tf32)", mode);
+      return rag::topk_tc_run(q, Q, keys, key_inv_norm, keys_shadow, N, d, k, mode, flags, idx_offset, out_scores,
                               out_idx, workspace, workspace_bytes, s);
     default:
       return rag::fail(RAG_EINVAL, "cosine_topk: unknown mode %d", mode);

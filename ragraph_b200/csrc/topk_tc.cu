@@ -110,6 +110,13 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, ui
                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum) : "memory");
 }
+// kind::tf32: fp32 words in shared memory, the tensor core reads the upper 19 bits; K = 8 per instruction (32 bytes, the
+// same K-step in bytes as kind::f16, so descriptors, swizzle and stage geometry are shared with the bf16 path)
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -183,6 +190,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
 }
 // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((128u >> 4) << 24);
+// same shape with A = B = tf32 (format code 2 in bits [7,10) and [10,13))
+constexpr uint32_t TC_IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_BN >> 3) << 17) | ((128u >> 4) << 24);
 
 // Candidate list of one (query row, key split): KP unsorted (score, index) slots in shared memory, entry p of
 // row r at ls[p*256 + r] (conflict free across a warp), plus meta[r] = slots in use | (position of the
@@ -250,8 +259,9 @@ struct __align__(8) TcBarriers {
   uint32_t tmem_base;
 };
 
-// KH = K halves of 64 (d_pad = 64*KH); NSTAGE = pipeline depth in 16 KB boxes; KP = list length
-template <int KH, int NSTAGE, int KP>
+// KH = K chunks of 128 bytes (bf16: d_pad = 64*KH; tf32: d_pad = 32*KH); NSTAGE = pipeline depth in 16 KB boxes;
+// KP = list length; TF32 = operands are fp32 words consumed as tf32 (RAG_SIM_TF32), else bf16
+template <int KH, int NSTAGE, int KP, bool TF32 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                       const TcArgs a) {
@@ -273,6 +283,11 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   const int tile0 = split * a.tiles_per_split;
   const int tile1 = min(tile0 + a.tiles_per_split, a.n_tiles);
   const int n_my_tiles = max(tile1 - tile0, 0);
+  constexpr int BOX_ELEMS = TF32 ? 32 : 64;                 // elements per 128-byte box row (TMA K coordinate step)
+  auto mma = [](uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accum) {
+    if constexpr (TF32) tc_mma_tf32(tmem_d, da, db, TC_IDESC_TF32, accum);
+    else tc_mma_bf16(tmem_d, da, db, TC_IDESC, accum);
+  };
 
   // ---- one-time setup ---------------------------------------------------------------------------
   if (warp == TC_EPI_WARPS && lane == 0) {
@@ -301,13 +316,13 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       mbar_expect_tx(&bars->a_full, 2 * KH * TC_BOX_BYTES);
       for (int rb = 0; rb < 2; ++rb)
         for (int kh = 0; kh < KH; ++kh)
-          tma_load_2d(sA + (rb * KH + kh) * TC_BOX_BYTES, &map_q, kh * 64, qtile * TC_ROWS + rb * 128, &bars->a_full);
+          tma_load_2d(sA + (rb * KH + kh) * TC_BOX_BYTES, &map_q, kh * BOX_ELEMS, qtile * TC_ROWS + rb * 128, &bars->a_full);
       int s = 0; uint32_t ph = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
         for (int kh = 0; kh < KH; ++kh) {
           mbar_wait(&bars->empty[s], ph ^ 1);
           mbar_expect_tx(&bars->full[s], TC_BOX_BYTES);
-          tma_load_2d(sB + s * TC_BOX_BYTES, &map_k, kh * 64, (tile0 + t) * TC_BN, &bars->full[s]);
+          tma_load_2d(sB + s * TC_BOX_BYTES, &map_k, kh * BOX_ELEMS, (tile0 + t) * TC_BN, &bars->full[s]);
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
       }
@@ -339,7 +354,7 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
               for (int k4 = 0; k4 < 4; ++k4) {
                 const uint64_t da = umma_desc(a_addr + (rb * KH + kh) * TC_BOX_BYTES + k4 * 32);
                 const uint64_t db = umma_desc(b_addr + sk * TC_BOX_BYTES + k4 * 32);
-                tc_mma_bf16(tmem_base + (uint32_t)((b * 2 + rb) * TC_BN), da, db, TC_IDESC, (kh | k4) != 0 ? 1u : 0u);
+                mma(tmem_base + (uint32_t)((b * 2 + rb) * TC_BN), da, db, (kh | k4) != 0 ? 1u : 0u);
               }
               if (++sk == NSTAGE) { sk = 0; phk ^= 1; }
             }
@@ -364,7 +379,7 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
               for (int k4 = 0; k4 < 4; ++k4) {
                 const uint64_t da = umma_desc(a_addr + (rb * KH + kh) * TC_BOX_BYTES + k4 * 32);
                 const uint64_t db = umma_desc(b_addr + s * TC_BOX_BYTES + k4 * 32);
-                tc_mma_bf16(tmem_base + (uint32_t)((b * 2 + rb) * TC_BN), da, db, TC_IDESC, (kh | k4) != 0 ? 1u : 0u);
+                mma(tmem_base + (uint32_t)((b * 2 + rb) * TC_BN), da, db, (kh | k4) != 0 ? 1u : 0u);
               }
             }
             tc_commit(&bars->empty[s]);
@@ -1151,14 +1166,15 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int d_pad, int box_rows) {
+// K-major [rows, d_pad] operand image, boxes of box_rows x 128 bytes (64 bf16 or 32 fp32/tf32 elements), SWIZZLE_128B
+static int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int d_pad, int box_rows, bool f32 = false) {
   PFN_encodeTiled enc = get_encode();
   RAG_REQUIRE(enc, RAG_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d_pad * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {f32 ? 32u : 64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RAG_REQUIRE(r == CUDA_SUCCESS, RAG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -1182,6 +1198,9 @@ static bool tc_shape_ok_ss(int d, int k) {
 // TS kernel shapes (query tile resident in tensor memory): d <= 256; k' = 16 slots per (row, split) for k <= 10,
 // 32 for k <= 26 (d <= 128 only: 128 KB of lists + append buffers leave 4 pipeline stages, d > 128 needs 8)
 bool tc_shape_ok(int d, int k) { return d >= 1 && d <= 256 && k >= 1 && (k <= 10 || (k <= 26 && d <= 128)); }
+// tf32 (SS kernel only): an fp32 operand row is twice as wide as a bf16 one, so d <= 64 has the bf16 d <= 128 budget
+// (k <= 26) and d <= 128 the bf16 d = 256 budget (128 KB of resident queries, 16-entry lists, k <= 10)
+bool tc_shape_ok_tf32(int d, int k) { return d >= 1 && k >= 1 && ((d <= 64 && k <= 26) || (d <= 128 && k <= 10)); }
 
 // Which filter kernel runs.  Measured on B200 (profiles/r1_midsize_ab.jsonl, r1_variant_ab_v4.jsonl): the query-stationary
 // TS kernel wins once a CTA streams many key tiles (12.5 M keys x 4096 queries: parity; 100 M: +6 %), because its hit
@@ -1197,11 +1216,16 @@ static bool tc_use_ts(int d, int k, int tiles_per_split) {
   return !ss_ok || tiles_per_split >= TS_MIN_TILES_PER_SPLIT;
 }
 
-static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts) {
+static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = false) {
   TcPlan p{};
-  p.d_pad = (d + 63) / 64 * 64;
-  p.kh = p.d_pad / 64;                       // 1..4
-  if (!ts && p.kh == 3) p.kh = 4;            // SS instantiations: 1, 2, 4
+  if (tf32) {
+    p.d_pad = d <= 32 ? 32 : (d <= 64 ? 64 : 128);   // fp32 elements; the shadow is padded to the SS instantiations 1, 2, 4
+    p.kh = p.d_pad / 32;
+  } else {
+    p.d_pad = (d + 63) / 64 * 64;
+    p.kh = p.d_pad / 64;                     // 1..4
+    if (!ts && p.kh == 3) p.kh = 4;          // SS instantiations: 1, 2, 4
+  }
   p.kp = (k <= 10) ? 16 : 32;
   // shared memory: (SS: A 2*KH boxes +) NSTAGE boxes + lists + barriers + 1 KB alignment slack  <= 227 KB
   // SS: lists + meta + pending queues; TS: sorted lists + append buffers (stride 257) + 16 B alignment slack
@@ -1223,7 +1247,7 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts) {
   p.tiles_per_split = (p.n_tiles + s - 1) / s;
   p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   size_t off = 0;
-  p.off_qbf = off; off += align_up((size_t)p.n_qtiles * TC_ROWS * p.d_pad * 2, 256);
+  p.off_qbf = off; off += align_up((size_t)p.n_qtiles * TC_ROWS * p.d_pad * (tf32 ? 4 : 2), 256);
   p.off_qinv = off; off += align_up((size_t)Q * 4, 256);
   p.off_ps = off; off += align_up((size_t)p.n_splits * Q * p.kp * 4, 256);
   p.off_pi = off; off += align_up((size_t)p.n_splits * Q * p.kp * 4, 256);
@@ -1250,15 +1274,18 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts) {
 }
 
 bool topk_tc_available(int d, int k) { return tc_shape_ok(d, k); }
+bool topk_tc_tf32_available(int d, int k) { return tc_shape_ok_tf32(d, k); }
+int topk_tc_tf32_dpad(int d) { return d <= 32 ? 32 : (d <= 64 ? 64 : 128); }
 
 size_t topk_tc_workspace(int64_t Q, int64_t N, int d, int k, int mode) {
+  if (mode == RAG_SIM_TF32) return tc_shape_ok_tf32(d, k) ? tc_plan(Q, N, d, k, false, true).total : 256;
   if (!tc_shape_ok(d, k)) return 256;
   return tc_plan(Q, N, d, k, true).total;   // offsets do not depend on the variant
 }
 
-template <int KH, int NSTAGE, int KP>
+template <int KH, int NSTAGE, int KP, bool TF32 = false>
 static int launch_filter(const CUtensorMap& mq, const CUtensorMap& mk, const TcArgs& a, const TcPlan& p, cudaStream_t s) {
-  auto kern = cosine_topk_tc_kernel<KH, NSTAGE, KP>;
+  auto kern = cosine_topk_tc_kernel<KH, NSTAGE, KP, TF32>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(cosine_topk_tc_kernel)");
   kern<<<(unsigned)(p.n_qtiles * p.n_splits), TC_THREADS, p.smem, s>>>(mq, mk, a);
@@ -1277,26 +1304,33 @@ static int launch_filter_ts(const CUtensorMap& mk, const uint16_t* q_bf, const T
   return RAG_OK;
 }
 
-int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const uint16_t* keys_bf16,
+int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const void* keys_shadow,
                 int64_t N, int d, int k, int mode, uint32_t flags, int64_t idx_offset, float* out_scores,
                 int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
+  const bool tf32 = (mode == RAG_SIM_TF32);
+  const uint16_t* keys_bf16 = static_cast<const uint16_t*>(keys_shadow);
   RAG_REQUIRE(!(flags & RAG_SIM_DOT), RAG_EUNSUPPORTED, "cosine_topk: the tensor-core modes implement cosine only");
-  RAG_REQUIRE(tc_shape_ok(d, k), RAG_EUNSUPPORTED,
-              "cosine_topk: tensor-core modes cover d <= 128 with k <= 26 and d <= 256 with k <= 10 (d=%d k=%d)", d, k);
+  if (tf32)
+    RAG_REQUIRE(tc_shape_ok_tf32(d, k), RAG_EUNSUPPORTED,
+                "cosine_topk: the tf32 mode covers d <= 64 with k <= 26 and d <= 128 with k <= 10 (d=%d k=%d)", d, k);
+  else
+    RAG_REQUIRE(tc_shape_ok(d, k), RAG_EUNSUPPORTED,
+                "cosine_topk: tensor-core modes cover d <= 128 with k <= 26 and d <= 256 with k <= 10 (d=%d k=%d)", d, k);
   RAG_REQUIRE(key_inv_norm, RAG_EINVAL, "cosine_topk: the tensor-core modes need key_inv_norm (rag_row_inv_norm_f32)");
-  RAG_REQUIRE(aligned16(keys_bf16), RAG_EALIGN, "cosine_topk: keys_bf16 must be 16-byte aligned");
-  const bool ts = tc_use_ts(d, k, tc_plan(Q, N, d, k, true).tiles_per_split);
-  TcPlan p = tc_plan(Q, N, d, k, ts);
+  RAG_REQUIRE(aligned16(keys_shadow), RAG_EALIGN, "cosine_topk: the key shadow must be 16-byte aligned");
+  const bool ts = !tf32 && tc_use_ts(d, k, tc_plan(Q, N, d, k, true).tiles_per_split);
+  TcPlan p = tc_plan(Q, N, d, k, ts, tf32);
   RAG_REQUIRE(ws_bytes >= p.total, RAG_EWORKSPACE, "cosine_topk: workspace %zu < %zu bytes", ws_bytes, p.total);
   RAG_REQUIRE(ws && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, RAG_EALIGN, "cosine_topk: workspace must be 256-byte aligned");
   RAG_REQUIRE(p.smem <= (size_t)max_smem_optin(), RAG_EUNSUPPORTED, "cosine_topk: needs %zu bytes of shared memory", p.smem);
   unsigned char* w = static_cast<unsigned char*>(ws);
   uint16_t* q_bf = reinterpret_cast<uint16_t*>(w + p.off_qbf);
   float* qinv = reinterpret_cast<float*>(w + p.off_qinv);
-  const int d_pad_keys = (d + 63) / 64 * 64;        // layout of the caller's shadow
+  const int d_pad_keys = tf32 ? topk_tc_tf32_dpad(d) : (d + 63) / 64 * 64;        // layout of the caller's shadow
   RAG_REQUIRE(p.d_pad == d_pad_keys, RAG_EUNSUPPORTED, "internal: d_pad mismatch");
 
-  int st = rag_rows_to_bf16(q, Q, d, 1, 1e-12f, q_bf, p.d_pad, s);
+  int st = tf32 ? rag_rows_to_tf32(q, Q, d, 1, 1e-12f, reinterpret_cast<float*>(q_bf), p.d_pad, s)
+                : rag_rows_to_bf16(q, Q, d, 1, 1e-12f, q_bf, p.d_pad, s);
   if (st) return st;
   st = rag_row_inv_norm_f32(q, Q, d, 1e-12f, qinv, s);
   if (st) return st;
@@ -1304,7 +1338,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(fb_count)");
 
   CUtensorMap mq, mk;
-  st = make_map_bf16(&mk, keys_bf16, N, p.d_pad, TC_BN);
+  st = make_map_bf16(&mk, keys_shadow, N, p.d_pad, TC_BN, tf32);
   if (st) return st;
 
   TcArgs a{};
@@ -1344,10 +1378,12 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
     }
     st = run_ts(a);
   } else {
-    st = make_map_bf16(&mq, q_bf, Q, p.d_pad, 128);
+    st = make_map_bf16(&mq, q_bf, Q, p.d_pad, 128, tf32);
     if (st) return st;
 #define RAG_TC_CASE(KH_, NS_, KP_) \
-  if (p.kh == KH_ && p.nstage == NS_ && p.kp == KP_) st = launch_filter<KH_, NS_, KP_>(mq, mk, a, p, s); else
+  if (p.kh == KH_ && p.nstage == NS_ && p.kp == KP_) \
+    st = tf32 ? launch_filter<KH_, NS_, KP_, true>(mq, mk, a, p, s) : launch_filter<KH_, NS_, KP_, false>(mq, mk, a, p, s); \
+  else
     RAG_TC_CASE(1, 8, 16) RAG_TC_CASE(1, 7, 32) RAG_TC_CASE(2, 7, 16) RAG_TC_CASE(2, 5, 32)
     RAG_TC_CASE(4, 3, 16)
     return fail(RAG_EUNSUPPORTED, "cosine_topk: no tensor-core instantiation for kh=%d nstage=%d kp=%d", p.kh, p.nstage, p.kp);

@@ -78,6 +78,32 @@ def _(x, normalize=True, eps=1e-12):
     return x.new_empty((x.shape[0], round_up(x.shape[1], 64)), dtype=torch.bfloat16)
 
 
+def tf32_shadow_dpad(d: int) -> int:
+    """columns of the tf32 key shadow for embedding dim d (32, 64 or 128; 0 = d not covered by RAG_SIM_TF32)"""
+    return int(L.load().rag_tf32_shadow_dpad(d))
+
+
+@torch.library.custom_op("ragraph::rows_to_tf32", mutates_args=())
+def rows_to_tf32(x: Tensor, normalize: bool = True, eps: float = 1e-12) -> Tensor:
+    """tf32-rounded (optionally L2-normalised) fp32 shadow [rows, tf32_shadow_dpad(d)] for RAG_SIM_TF32."""
+    _need_cuda(x)
+    x = _f32c(x, "rows_to_tf32")
+    d_pad = tf32_shadow_dpad(x.shape[1])
+    if d_pad == 0:
+        raise RuntimeError(f"rows_to_tf32: the tf32 mode covers d <= 128, got d={x.shape[1]}")
+    out = torch.empty((x.shape[0], d_pad), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.load().rag_rows_to_tf32(_p(x), x.shape[0], x.shape[1], int(normalize), eps, _p(out), d_pad,
+                                          _stream()), "rows_to_tf32")
+    return out
+
+
+@rows_to_tf32.register_fake
+def _(x, normalize=True, eps=1e-12):
+    d = x.shape[1]
+    return x.new_empty((x.shape[0], 32 if d <= 32 else (64 if d <= 64 else 128)))
+
+
 # ----------------------------------------------------------------------------- similarity
 @torch.library.custom_op("ragraph::cosine_similarity", mutates_args=())
 def cosine_similarity(q: Tensor, keys: Tensor, flags: int = 0) -> Tensor:
@@ -104,7 +130,8 @@ def _(q, keys, flags=0):
 def cosine_topk(q: Tensor, keys: Tensor, k: int, key_inv_norm: Optional[Tensor] = None,
                 keys_bf16: Optional[Tensor] = None, mode: int = 0, flags: int = 0,
                 idx_offset: int = 0) -> Tuple[Tensor, Tensor]:
-    """Fused similarity + top-k.  Returns (scores[Q,k] f32 desc, idx[Q,k] int64)."""
+    """Fused similarity + top-k.  Returns (scores[Q,k] f32 desc, idx[Q,k] int64).  ``keys_bf16`` is the key shadow of
+    the tensor-core modes: rows_to_bf16(keys) for SIM_BF16 / SIM_BF16_REFINE, rows_to_tf32(keys) for SIM_TF32."""
     _need_cuda(q, keys, key_inv_norm, keys_bf16)
     q, keys = _f32c(q, "cosine_topk"), _f32c(keys, "cosine_topk")
     if q.dim() != 2 or keys.dim() != 2 or q.shape[1] != keys.shape[1]:
@@ -114,7 +141,11 @@ def cosine_topk(q: Tensor, keys: Tensor, k: int, key_inv_norm: Optional[Tensor] 
         key_inv_norm = _f32c(key_inv_norm, "key_inv_norm")
         if key_inv_norm.numel() != N:
             raise RuntimeError("cosine_topk: key_inv_norm must have N entries")
-    if keys_bf16 is not None:
+    if keys_bf16 is not None and mode == L.SIM_TF32:
+        if keys_bf16.dtype != torch.float32 or tuple(keys_bf16.shape) != (N, tf32_shadow_dpad(d)) \
+                or not keys_bf16.is_contiguous():
+            raise RuntimeError("cosine_topk: SIM_TF32 needs the contiguous [N, tf32_shadow_dpad(d)] fp32 shadow (rows_to_tf32)")
+    elif keys_bf16 is not None:
         if keys_bf16.dtype != torch.bfloat16 or tuple(keys_bf16.shape) != (N, round_up(d, 64)) \
                 or not keys_bf16.is_contiguous():
             raise RuntimeError("cosine_topk: keys_bf16 must be the contiguous [N, round_up(d,64)] bf16 shadow")

@@ -45,7 +45,7 @@ class ToyGraphBase:
         self._cap = 0
         self._label_dtype = label_dtype
         self._keys = self._values = self._labels = self._positions = None
-        self._inv_norm = self._keys_bf16 = None
+        self._inv_norm = self._keys_bf16 = self._keys_tf32 = None
         self._derived_rows = 0                # rows [0, _derived_rows) of inv_norm / bf16 shadow are valid
         self._class_ids = None                # argmax of the label rows (few-shot fusion), valid for _class_rows rows
         self._class_rows = 0
@@ -71,7 +71,7 @@ class ToyGraphBase:
         if self.variant == "node_fewshot":           # position codes only feed the two-metric score
             self._positions = grow(self._positions, (cap, self.num_anchors), torch.float32)
         self._inv_norm = grow(self._inv_norm, (cap,), torch.float32)
-        self._keys_bf16 = None                # rebuilt lazily at the size in use
+        self._keys_bf16 = self._keys_tf32 = None   # rebuilt lazily at the size in use
         self._cap = cap
 
     def add_entries(self, keys: Tensor, values: Tensor, labels: Tensor, positions: Optional[Tensor] = None) -> None:
@@ -89,15 +89,22 @@ class ToyGraphBase:
                 self._positions[s].zero_()
         self._n += m
 
-    def _refresh_derived(self, want_bf16: bool) -> None:
+    def _refresh_derived(self, want_bf16: bool, want_tf32: bool = False) -> None:
         n = self._n
         if self._derived_rows < n:
             lo = self._derived_rows
             self._inv_norm[lo:n].copy_(ops.row_inv_norm(self._keys[lo:n]))
             self._derived_rows = n
-            self._keys_bf16 = None
+            self._keys_bf16 = self._keys_tf32 = None
         if want_bf16 and (self._keys_bf16 is None or self._keys_bf16.shape[0] != n):
             self._keys_bf16 = ops.rows_to_bf16(self._keys[:n], True)
+        if want_tf32 and (self._keys_tf32 is None or self._keys_tf32.shape[0] != n):
+            self._keys_tf32 = ops.rows_to_tf32(self._keys[:n], True)
+
+    def _shadow(self, mode: int) -> Optional[Tensor]:
+        """the key shadow the similarity mode reads (None for the fp32 path), refreshed for the rows in use"""
+        self._refresh_derived(mode in (L.SIM_BF16, L.SIM_BF16_REFINE), mode == L.SIM_TF32)
+        return self._keys_tf32 if mode == L.SIM_TF32 else (self._keys_bf16 if mode != L.SIM_FP32 else None)
 
     # reference attribute names (views of the rows in use)
     @property
@@ -218,9 +225,8 @@ class ToyGraphBase:
         if k > L.RAG_MAX_K:
             return self._topk_large(search_keys, k)
         mode = self._pick_mode(search_keys.shape[0], k)
-        self._refresh_derived(mode != L.SIM_FP32)
-        return ops.cosine_topk(search_keys, self.resource_keys, k, self._inv_norm[:self._n],
-                               self._keys_bf16 if mode != L.SIM_FP32 else None, mode)
+        shadow = self._shadow(mode)
+        return ops.cosine_topk(search_keys, self.resource_keys, k, self._inv_norm[:self._n], shadow, mode)
 
     def _topk_large(self, search_keys: Tensor, k: int, budget_bytes: int = 1 << 30) -> Tuple[Tensor, Tensor]:
         """k > RAG_MAX_K (the edge variant's vanilla configs ask for retrieve_num = 100000, i.e. most of the library,

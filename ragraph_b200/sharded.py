@@ -45,9 +45,8 @@ def owner_of(idx: Tensor, n_rows: int, world: int) -> Tensor:
 def _default_local_topk(store, q, k):
     from . import ops
     mode = store._pick_mode(q.shape[0], k)
-    store._refresh_derived(mode != 0)
-    return ops.cosine_topk(q, store.resource_keys, k, store._inv_norm[:len(store)],
-                           store._keys_bf16 if mode != 0 else None, mode, 0, store.shard_lo)
+    shadow = store._shadow(mode)
+    return ops.cosine_topk(q, store.resource_keys, k, store._inv_norm[:len(store)], shadow, mode, 0, store.shard_lo)
 
 
 def _default_merge(scores, idx, k):
