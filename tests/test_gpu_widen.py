@@ -118,7 +118,7 @@ def test_downprompt_node_golden(golden):
     g = golden("downprompt_node")
     d = g["seq"].shape[1]
     p = torch.zeros(1, d, device=DEV)
-    m = DP.downprompt(p, p, p, d, 3, cu(g["feature"]), cu(g["labels"]))
+    m = DP.downprompt(p, p, p, d, 3, cu(g["feature"]), cu(g["labels"])).to(DEV)
     m.downprompt.weight.data.copy_(cu(g["weight"]))
     assert O.rel_err(m.ave.cpu(), g["ave_init"]) < REL
     assert O.rel_err(m.downprompt(cu(g["seq"])).cpu(), g["prompted"]) < 1e-6
@@ -133,7 +133,7 @@ def test_downprompt_graph_golden(golden):
     g = golden("downprompt_graph")
     d = g["seq"].shape[1]
     p = torch.zeros(1, d, device=DEV)
-    m = DP.downprompt(p, p, p, d, 6)
+    m = DP.downprompt(p, p, p, d, 6).to(DEV)
     m.downprompt.weight.data.copy_(cu(g["weight"]))
     gemb = m(cu(g["seq"]), cu(g["graph_sizes"]))
     assert O.rel_err(gemb.cpu(), g["graph_emb"]) < REL
