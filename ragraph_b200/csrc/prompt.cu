@@ -22,20 +22,34 @@ __global__ void __launch_bounds__(PR_THREADS) prompt_act_kernel(const float* __r
                                                                  int64_t n, int d, int act, float* __restrict__ out,
                                                                  int vec4) {
   const int64_t total = n * (int64_t)d;
+  // the column of element i is i mod d; a 64-bit modulo per element costs more than the load it indexes, so every
+  // thread keeps a running column that advances by (grid stride mod d) per iteration
   if (vec4) {
     const int d4 = d >> 2;
     const int64_t total4 = total >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * PR_THREADS + threadIdx.x; i < total4; i += (int64_t)gridDim.x * PR_THREADS) {
-      const int c = (int)(i % d4);
+    const int64_t stride = (int64_t)gridDim.x * PR_THREADS;
+    const int step = (int)(stride % d4);
+    int64_t i = (int64_t)blockIdx.x * PR_THREADS + threadIdx.x;
+    int c = (int)(i % d4);
+    for (; i < total4; i += stride) {
       float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
       const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + c);
       v.x = prompt_act(v.x * ww.x, act); v.y = prompt_act(v.y * ww.y, act);
       v.z = prompt_act(v.z * ww.z, act); v.w = prompt_act(v.w * ww.w, act);
-      reinterpret_cast<float4*>(out)[i] = v;
+      __stcs(reinterpret_cast<float4*>(out) + i, v);
+      c += step;
+      if (c >= d4) c -= d4;
     }
   } else {
-    for (int64_t i = (int64_t)blockIdx.x * PR_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * PR_THREADS)
-      out[i] = prompt_act(__ldcs(x + i) * __ldg(w + (int)(i % d)), act);
+    const int64_t stride = (int64_t)gridDim.x * PR_THREADS;
+    const int step = (int)(stride % d);
+    int64_t i = (int64_t)blockIdx.x * PR_THREADS + threadIdx.x;
+    int c = (int)(i % d);
+    for (; i < total; i += stride) {
+      out[i] = prompt_act(__ldcs(x + i) * __ldg(w + c), act);
+      c += step;
+      if (c >= d) c -= d;
+    }
   }
 }
 
@@ -95,6 +109,115 @@ __global__ void __launch_bounds__(PR_THREADS) prototype_scores_kernel(const floa
   }
 }
 
+// Vector path (d % 4 == 0, C <= 8): 8 lanes per row, every 8-lane group works on TWO rows at a time so that each
+// prototype float4 read from shared memory feeds 8 FMAs (shared-memory traffic per row = C/2 KB against 1 KB of HBM at
+// d = 256, inside the 128 B/clk port at full HBM rate); the 8-lane reductions are 3 shuffle steps per value.  A warp
+// covers 8 rows per iteration with 128-bit loads: 4 rows x 128 contiguous bytes per instruction.
+template <int CMAX>
+__global__ void __launch_bounds__(PR_THREADS) prototype_scores_vec_kernel(const float4* __restrict__ x, const float* __restrict__ w,
+                                                                           const float* __restrict__ proto, int64_t n, int d4,
+                                                                           int C, int act, float eps, int mode,
+                                                                           float* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  float4* sp = reinterpret_cast<float4*>(sm);            // [C, d4]
+  float4* sw = sp + (size_t)C * d4;                      // [d4]
+  float* spn = reinterpret_cast<float*>(sw + d4);        // [C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = PR_THREADS / 32;
+  const int d = d4 * 4;
+  for (int i = threadIdx.x; i < C * d; i += PR_THREADS) sm[i] = __ldg(proto + i);
+  for (int i = threadIdx.x; i < d; i += PR_THREADS) reinterpret_cast<float*>(sw)[i] = w ? __ldg(w + i) : 1.f;
+  __syncthreads();
+  for (int c = warp; c < C; c += wpb) {
+    float s = 0.f;
+    for (int j = lane; j < d; j += 32) s = fmaf(sm[(size_t)c * d + j], sm[(size_t)c * d + j], s);
+    s = warp_sum(s);
+    if (lane == 0) spn[c] = fmaxf(sqrtf(s), eps);
+  }
+  __syncthreads();
+
+  const int sub = lane & 7, grp = lane >> 3;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t base = ((int64_t)blockIdx.x * wpb + warp) * 8; base < n; base += (int64_t)gridDim.x * wpb * 8) {
+    const int64_t r0 = base + 2 * grp, r1 = r0 + 1;
+    const bool v0 = r0 < n, v1 = r1 < n;
+    const float4* x0 = x + r0 * d4;
+    const float4* x1 = x + r1 * d4;
+    float dot0[CMAX], dot1[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) { dot0[c] = 0.f; dot1[c] = 0.f; }
+    float n0 = 0.f, n1 = 0.f;
+#pragma unroll 2
+    for (int j = sub; j < d4; j += 8) {
+      float4 a = v0 ? __ldcs(x0 + j) : zero;
+      float4 b = v1 ? __ldcs(x1 + j) : zero;
+      const float4 ww = sw[j];
+      a.x = prompt_act(a.x * ww.x, act); a.y = prompt_act(a.y * ww.y, act);
+      a.z = prompt_act(a.z * ww.z, act); a.w = prompt_act(a.w * ww.w, act);
+      b.x = prompt_act(b.x * ww.x, act); b.y = prompt_act(b.y * ww.y, act);
+      b.z = prompt_act(b.z * ww.z, act); b.w = prompt_act(b.w * ww.w, act);
+      n0 = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, n0))));
+      n1 = fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(b.z, b.z, fmaf(b.w, b.w, n1))));
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+          const float4 p = sp[(size_t)c * d4 + j];
+          dot0[c] = fmaf(a.x, p.x, fmaf(a.y, p.y, fmaf(a.z, p.z, fmaf(a.w, p.w, dot0[c]))));
+          dot1[c] = fmaf(b.x, p.x, fmaf(b.y, p.y, fmaf(b.z, p.z, fmaf(b.w, p.w, dot1[c]))));
+        }
+      }
+    }
+    // 8-lane group reductions: afterwards every lane of the group holds the totals of its two rows
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      n0 += __shfl_xor_sync(0xffffffffu, n0, o);
+      n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+          dot0[c] += __shfl_xor_sync(0xffffffffu, dot0[c], o);
+          dot1[c] += __shfl_xor_sync(0xffffffffu, dot1[c], o);
+        }
+      }
+    }
+    n0 = fmaxf(sqrtf(n0), eps);
+    n1 = fmaxf(sqrtf(n1), eps);
+    float m0 = -FLT_MAX, m1 = -FLT_MAX;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < C) {
+        dot0[c] = (dot0[c] / n0) / spn[c];
+        dot1[c] = (dot1[c] / n1) / spn[c];
+        m0 = fmaxf(m0, dot0[c]);
+        m1 = fmaxf(m1, dot1[c]);
+      }
+    }
+    float mine0 = 0.f, mine1 = 0.f;           // lane `sub` of the group writes class `sub`
+    if (mode != 0) {
+      float den0 = 0.f, den1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < C) { den0 += expf(dot0[c] - m0); den1 += expf(dot1[c] - m1); }
+      }
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < C && c == sub) {
+          mine0 = mode == 1 ? expf(dot0[c] - m0) / den0 : (dot0[c] - m0) - logf(den0);
+          mine1 = mode == 1 ? expf(dot1[c] - m1) / den1 : (dot1[c] - m1) - logf(den1);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < C && c == sub) { mine0 = dot0[c]; mine1 = dot1[c]; }
+      }
+    }
+    if (sub < C) {
+      if (v0) out[r0 * (int64_t)C + sub] = mine0;
+      if (v1) out[r1 * (int64_t)C + sub] = mine1;
+    }
+  }
+}
+
 }  // namespace rag
 
 extern "C" int rag_prompt_act_f32(const float* x, int64_t n, int32_t d, const float* w, int32_t act, float* out,
@@ -125,9 +248,27 @@ extern "C" int rag_prototype_scores_f32(const float* x, int64_t n, int32_t d, co
   RAG_REQUIRE(smem <= (size_t)max_smem_optin(), RAG_EUNSUPPORTED,
               "prototype_scores: C*d = %d*%d prototypes do not fit shared memory", C, d);
   const int wpb = PR_THREADS / 32;
+  cudaError_t e;
+  if (C <= 8 && d % 4 == 0 && aligned16(x)) {
+    const int64_t want = (n + wpb * 8 - 1) / (wpb * 8);
+    const int grid = (int)(want < (int64_t)sm_count() * 4 ? want : (int64_t)sm_count() * 4);
+#define RAG_PSV_LAUNCH(CM)                                                                                                 \
+  do {                                                                                                                     \
+    if (smem > 48 * 1024) {                                                                                                \
+      e = cudaFuncSetAttribute(prototype_scores_vec_kernel<CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+      if (e != cudaSuccess) return cuda_fail(e, "prototype_scores: cudaFuncSetAttribute");                                 \
+    }                                                                                                                      \
+    prototype_scores_vec_kernel<CM><<<grid, PR_THREADS, smem, (cudaStream_t)stream>>>(                                     \
+        reinterpret_cast<const float4*>(x), w, proto, n, d / 4, C, act, eps, mode, out);                                   \
+  } while (0)
+    if (C <= 4) RAG_PSV_LAUNCH(4);
+    else RAG_PSV_LAUNCH(8);
+#undef RAG_PSV_LAUNCH
+    RAG_LAUNCH_OK("prototype_scores_vec_kernel");
+    return RAG_OK;
+  }
   const int64_t want = (n + wpb - 1) / wpb;
   const int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
-  cudaError_t e;
 #define RAG_PS_LAUNCH(CM)                                                                                              \
   do {                                                                                                                 \
     if (smem > 48 * 1024) {                                                                                            \
