@@ -16,7 +16,21 @@ namespace rag {
 constexpr int PR_THREADS = 256;
 constexpr int PR_MAX_CLASSES = 32;
 
-__device__ __forceinline__ float prompt_act(float v, int act) { return act == 1 ? (v > 0.f ? v : expm1f(v)) : v; }
+// exp(v) - 1 for v <= 0 without a branch (libdevice expm1f branches per element and a warp sees both signs): a degree-7
+// Taylor polynomial above -1/4 (truncation < 4e-10), ex2.approx below it (|result| >= 0.22, so the absolute error of
+// ~2e-7 stays under 1e-6 relative); both are computed and one is selected.
+__device__ __forceinline__ float expm1_nonpos(float v) {
+  const float p = v * fmaf(v, fmaf(v, fmaf(v, fmaf(v, fmaf(v, fmaf(v, 1.f / 5040.f, 1.f / 720.f), 1.f / 120.f), 1.f / 24.f),
+                                          1.f / 6.f), 0.5f), 1.f);
+  const float e = __expf(v) - 1.0f;
+  return v > -0.25f ? p : e;
+}
+// act 1 = ELU (alpha 1): v > 0 ? v : exp(v) - 1.  `act` is uniform over the launch.
+__device__ __forceinline__ float prompt_act(float v, int act) {
+  if (act != 1) return v;
+  const float neg = expm1_nonpos(fminf(v, 0.f));
+  return v > 0.f ? v : neg;
+}
 
 __global__ void __launch_bounds__(PR_THREADS) prompt_act_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                  int64_t n, int d, int act, float* __restrict__ out,
@@ -131,7 +145,7 @@ __global__ void __launch_bounds__(PR_THREADS) prototype_scores_vec_kernel(const 
     float s = 0.f;
     for (int j = lane; j < d; j += 32) s = fmaf(sm[(size_t)c * d + j], sm[(size_t)c * d + j], s);
     s = warp_sum(s);
-    if (lane == 0) spn[c] = fmaxf(sqrtf(s), eps);
+    if (lane == 0) spn[c] = 1.0f / fmaxf(sqrtf(s), eps);       // reciprocal of the clamped prototype norm
   }
   __syncthreads();
 
@@ -172,44 +186,34 @@ __global__ void __launch_bounds__(PR_THREADS) prototype_scores_vec_kernel(const 
       n0 += __shfl_xor_sync(0xffffffffu, n0, o);
       n1 += __shfl_xor_sync(0xffffffffu, n1, o);
 #pragma unroll
-      for (int c = 0; c < CMAX; ++c) {
-        if (c < C) {
-          dot0[c] += __shfl_xor_sync(0xffffffffu, dot0[c], o);
-          dot1[c] += __shfl_xor_sync(0xffffffffu, dot1[c], o);
-        }
+      for (int c = 0; c < CMAX; ++c) {            // unconditional: classes >= C hold zeros (no predicated collectives)
+        dot0[c] += __shfl_xor_sync(0xffffffffu, dot0[c], o);
+        dot1[c] += __shfl_xor_sync(0xffffffffu, dot1[c], o);
       }
     }
-    n0 = fmaxf(sqrtf(n0), eps);
-    n1 = fmaxf(sqrtf(n1), eps);
-    float m0 = -FLT_MAX, m1 = -FLT_MAX;
+    // lane `sub` of the group owns class `sub`: one scale, then max / sum over the group's 8 lanes
+    const float inv0 = 1.0f / fmaxf(sqrtf(n0), eps), inv1 = 1.0f / fmaxf(sqrtf(n1), eps);
+    float mine0 = -FLT_MAX, mine1 = -FLT_MAX;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
-      if (c < C) {
-        dot0[c] = (dot0[c] / n0) / spn[c];
-        dot1[c] = (dot1[c] / n1) / spn[c];
-        m0 = fmaxf(m0, dot0[c]);
-        m1 = fmaxf(m1, dot1[c]);
-      }
+      if (c < C && c == sub) { mine0 = dot0[c] * inv0 * spn[c]; mine1 = dot1[c] * inv1 * spn[c]; }
     }
-    float mine0 = 0.f, mine1 = 0.f;           // lane `sub` of the group writes class `sub`
     if (mode != 0) {
-      float den0 = 0.f, den1 = 0.f;
+      float m0 = mine0, m1 = mine1;
 #pragma unroll
-      for (int c = 0; c < CMAX; ++c) {
-        if (c < C) { den0 += expf(dot0[c] - m0); den1 += expf(dot1[c] - m1); }
+      for (int o = 4; o > 0; o >>= 1) {
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
       }
+      const float e0 = sub < C ? expf(mine0 - m0) : 0.f, e1 = sub < C ? expf(mine1 - m1) : 0.f;
+      float den0 = e0, den1 = e1;
 #pragma unroll
-      for (int c = 0; c < CMAX; ++c) {
-        if (c < C && c == sub) {
-          mine0 = mode == 1 ? expf(dot0[c] - m0) / den0 : (dot0[c] - m0) - logf(den0);
-          mine1 = mode == 1 ? expf(dot1[c] - m1) / den1 : (dot1[c] - m1) - logf(den1);
-        }
+      for (int o = 4; o > 0; o >>= 1) {
+        den0 += __shfl_xor_sync(0xffffffffu, den0, o);
+        den1 += __shfl_xor_sync(0xffffffffu, den1, o);
       }
-    } else {
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c) {
-        if (c < C && c == sub) { mine0 = dot0[c]; mine1 = dot1[c]; }
-      }
+      mine0 = mode == 1 ? e0 / den0 : (mine0 - m0) - logf(den0);
+      mine1 = mode == 1 ? e1 / den1 : (mine1 - m1) - logf(den1);
     }
     if (sub < C) {
       if (v0) out[r0 * (int64_t)C + sub] = mine0;
@@ -251,13 +255,19 @@ extern "C" int rag_prototype_scores_f32(const float* x, int64_t n, int32_t d, co
   cudaError_t e;
   if (C <= 8 && d % 4 == 0 && aligned16(x)) {
     const int64_t want = (n + wpb * 8 - 1) / (wpb * 8);
-    const int grid = (int)(want < (int64_t)sm_count() * 4 ? want : (int64_t)sm_count() * 4);
+    // persistent grid = exactly the CTAs that are resident at once (a partial second wave would run at a fraction of
+    // the machine for as long as the first)
 #define RAG_PSV_LAUNCH(CM)                                                                                                 \
   do {                                                                                                                     \
     if (smem > 48 * 1024) {                                                                                                \
       e = cudaFuncSetAttribute(prototype_scores_vec_kernel<CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
       if (e != cudaSuccess) return cuda_fail(e, "prototype_scores: cudaFuncSetAttribute");                                 \
     }                                                                                                                      \
+    int per_sm = 0;                                                                                                        \
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prototype_scores_vec_kernel<CM>, PR_THREADS, smem);         \
+    if (e != cudaSuccess || per_sm < 1) per_sm = 1;                                                                        \
+    const int64_t cap = (int64_t)sm_count() * per_sm;                                                                      \
+    const int grid = (int)(want < cap ? want : cap);                                                                       \
     prototype_scores_vec_kernel<CM><<<grid, PR_THREADS, smem, (cudaStream_t)stream>>>(                                     \
         reinterpret_cast<const float4*>(x), w, proto, n, d / 4, C, act, eps, mode, out);                                   \
   } while (0)
