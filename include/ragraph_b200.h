@@ -84,6 +84,10 @@ RAG_API int rag_sim_mode_supported(int32_t mode, int32_t d, int32_t k);
 /* out_inv_norm[r] = 1 / max(||x[r,:]||_2, eps) */
 RAG_API int rag_row_inv_norm_f32(const float* x, int64_t rows, int32_t d, float eps, float* out_inv_norm,
                          rag_stream_t stream);
+/* out[r,:] = x[r,:] / max(||x[r,:]||_2, eps): F.normalize(x, p=2, dim=-1) as applied to library keys at insert
+ * (ToyGraphBase.py:109, RAGraph_graph/.../ToyGraphBase.py:112).  out may alias x. */
+RAG_API int rag_rows_normalize_f32(const float* x, int64_t rows, int32_t d, float eps, float* out,
+                           rag_stream_t stream);
 /* bf16 shadow of the key matrix for the tensor-core filter: out[r, 0:d] =
  * bf16_rn(x[r,:] * (normalize ? 1/max(||x[r]||,eps) : 1)), columns d..d_pad-1 zero filled.
  * d_pad % 64 == 0, out is [rows, d_pad] bf16 (uint16 storage), 16-byte aligned. */

@@ -387,8 +387,65 @@ def gen_downprompt():
         torch.FloatTensor = real_ft
 
 
+def gen_library_build():
+    """Library construction with the RNG-driven steps disabled (num_augment_scale = 0, num_inverse_sample = 0): the
+    unmodified _build_toy_graph_base of the node and graph variants and the edge _make_resource_graph."""
+    g = torch.Generator().manual_seed(60606)
+    d, C = 24, 3
+    graphs = []
+    for n in (17, 9, 30):
+        graphs.append((_sym_norm_adj(n, 0.2, g), torch.randn(n, d, generator=g),
+                       torch.nn.functional.one_hot(torch.randint(0, C, (n,), generator=g), C).float(),
+                       torch.randint(0, C, (1,), generator=g)))
+
+    class _PM:
+        def __init__(self):
+            self.emb = None
+
+        def inference(self, features, adj):
+            return self.emb
+
+    out = {}
+    for variant in ("RAGraph_node", "RAGraph_graph"):
+        _enter_variant(variant)
+        from ragraph_utils.ToyGraphBase import ToyGraphBase
+        pm = _PM()
+        base = ToyGraphBase(pm, C, d, 3 if variant == "RAGraph_node" else 1)      # real constructor (cuda() patched)
+        base.num_augment_scale, base.num_inverse_sample = 0, 0
+        torch.manual_seed(1)                                                       # PositionAwareEncoder anchors (unused)
+        for adj, emb, nl, gl in graphs:
+            pm.emb = emb
+            base._build_toy_graph_base(None, adj, nl if variant == "RAGraph_node" else gl)
+        tag = "node" if variant == "RAGraph_node" else "graph"
+        out[f"{tag}_keys"], out[f"{tag}_values"], out[f"{tag}_labels"] = base.resource_keys, base.resource_values, base.resource_labels
+        out[f"{tag}_hop"] = base.toy_graph_hop
+    for i, (adj, emb, nl, gl) in enumerate(graphs):
+        out[f"adj{i}"], out[f"emb{i}"], out[f"node_labels{i}"], out[f"graph_label{i}"] = adj, emb, nl, gl
+
+    # edge: _make_resource_graph on a shim
+    _enter_variant("RAGraph_edge", argv=["x", "--device", "cpu", "--data_path", "dataset/amazon"])
+    from modules.RAGraph import RAGraph
+    from utils.parse_args import args
+    nu, ni, de, E = 40, 30, 16, 400
+    n = nu + ni
+    u = torch.randint(0, nu, (E,), generator=g); i = torch.randint(0, ni, (E,), generator=g) + nu
+    adj_sp = torch.sparse_coo_tensor(torch.cat([torch.stack([u, i]), torch.stack([i, u])], 1),
+                                     torch.rand(2 * E, generator=g), (n, n)).coalesce()
+    X = torch.randn(n, de, generator=g)
+    shim = types.SimpleNamespace(num_users=nu, num_items=ni, adj=adj_sp, edges=adj_sp._indices().t(),
+                                 edge_norm=adj_sp._values(), resource_graph_radius=args.num_layers,
+                                 num_augment_scale=0, num_inverse_sample=0, resource_keys=None, resource_values=None)
+    shim._agg = types.MethodType(RAGraph._agg, shim)
+    pre = types.SimpleNamespace(generate=lambda: (X[:nu], X[nu:]))
+    with torch.no_grad():
+        RAGraph._make_resource_graph(shim, pre)
+    out.update(edge_X=X, edge_edges=shim.edges, edge_w=shim.edge_norm, edge_radius=args.num_layers,
+               edge_keys=shim.resource_keys, edge_values=shim.resource_values)
+    _save("library_build", n_graphs=len(graphs), **out)
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
     _install_stubs()
     gen_node(); gen_graph(); gen_node_fewshot(); gen_edge(); gen_edge_eval()
-    gen_fewshot_forward(); gen_downprompt()
+    gen_fewshot_forward(); gen_downprompt(); gen_library_build()

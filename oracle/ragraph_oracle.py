@@ -335,6 +335,36 @@ def fuse_fewshot(pretrain_emb, adj, rag_embeddings, rag_labels, mean_fewshot_log
 
 
 # ----------------------------------------------------------------------------------------
+# a8 / 8f-2  library construction (deterministic core: no augmentation, no inverse sampling)
+# ----------------------------------------------------------------------------------------
+def build_library_rows_node(embeddings, adj, node_labels, toy_graph_hop):
+    """RAGraph_node/ragraph_utils/ToyGraphBase.py:104-119 for one graph (the `else` branch of :95-107):
+    keys = F.normalize(emb), values = aggregate_k_hop_features(adj, keys, hop - 1), labels = node labels."""
+    keys = F.normalize(embeddings, p=2, dim=-1)
+    values = aggregate_k_hop_features(adj, keys, toy_graph_hop)
+    return keys, values, node_labels
+
+
+def build_library_rows_graph(embeddings, adj, graph_label, num_class, toy_graph_hop):
+    """RAGraph_graph/ragraph_utils/ToyGraphBase.py:112-126: one row per graph -- node keys / values averaged,
+    label = one_hot(graph_label) (int64)."""
+    keys = F.normalize(embeddings, p=2, dim=-1)
+    values = aggregate_k_hop_features(adj, keys, toy_graph_hop)
+    return (torch.mean(keys, dim=0).unsqueeze(0), torch.mean(values, dim=0).unsqueeze(0),
+            F.one_hot(graph_label, num_classes=num_class))
+
+
+def edge_resource_graph(all_emb, edges, edge_norm, radius):
+    """RAGraph_edge/modules/RAGraph.py:185-196,212-226 with num_augment_scale = num_inverse_sample = 0:
+    keys = last propagation layer, values = sum of the even layers (res_emb[0::2])."""
+    n = all_emb.shape[0]
+    res_emb = [all_emb]
+    for _ in range(radius):
+        res_emb.append(edge_agg(res_emb[-1], edges, edge_norm, n))
+    return res_emb[-1], sum(res_emb[0::2])
+
+
+# ----------------------------------------------------------------------------------------
 # multi-GPU restatement (new functionality, C1): merge of per-shard candidates
 # ----------------------------------------------------------------------------------------
 def rating_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, hist_rowptr, hist_items, k: int):

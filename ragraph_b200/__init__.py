@@ -6,7 +6,7 @@ calling any op needs the built library and CUDA tensors (no CPU fallback).
 """
 from . import _lib, ops
 from .csr import CSRGraph, as_csr
-from .edge import (EdgeAggregator, edge_rag_forward, rating_topk, relative_edge_time_encoding, scatter_add,
+from .edge import (EdgeAggregator, edge_rag_forward, make_resource_graph, rating_topk, relative_edge_time_encoding, scatter_add,
                    scatter_softmax, scatter_sum)
 from .layers import GCN
 from .ragraph_utils import Propagation, SimilarityFunctions, TaskDecoder, ToyGraphBase
@@ -17,6 +17,6 @@ from .utility import normalized_adjacency_csr, process_graph_batch
 
 __all__ = ["_lib", "ops", "CSRGraph", "as_csr", "EdgeAggregator", "edge_rag_forward", "rating_topk", "scatter_add", "scatter_sum",
            "GCN", "Propagation", "SimilarityFunctions", "TaskDecoder", "ToyGraphBase", "RAGraph", "RAGraphFewShot", "downprompt",
-           "relative_edge_time_encoding", "scatter_softmax",
+           "relative_edge_time_encoding", "scatter_softmax", "make_resource_graph",
            "ShardedRetriever", "owner_of", "shard_bounds", "normalized_adjacency_csr", "process_graph_batch"]
 __version__ = "0.1.0"

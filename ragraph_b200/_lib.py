@@ -31,6 +31,7 @@ SIGNATURES = {
     "rag_launch_count": (_i64, []),
     "rag_sim_mode_supported": (C.c_int, [_i32, _i32, _i32]),
     "rag_row_inv_norm_f32": (C.c_int, [_p, _i64, _i32, _f32, _p, _p]),
+    "rag_rows_normalize_f32": (C.c_int, [_p, _i64, _i32, _f32, _p, _p]),
     "rag_rows_to_bf16": (C.c_int, [_p, _i64, _i32, _i32, _f32, _p, _i32, _p]),
     "rag_tf32_shadow_dpad": (_i32, [_i32]),
     "rag_rows_to_tf32": (C.c_int, [_p, _i64, _i32, _i32, _f32, _p, _i32, _p]),

@@ -51,6 +51,28 @@ __global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restri
   }
 }
 
+// F.normalize(x, p=2, dim=-1): out[r,:] = x[r,:] / max(||x[r,:]||, eps)  (library insert, ToyGraphBase.py:109)
+__global__ void __launch_bounds__(256) rows_normalize_kernel(const float* __restrict__ x, int64_t rows, int d, float eps,
+                                                             float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float* xr = x + r * d;
+    const float nrm = fmaxf(sqrtf(row_sumsq(xr, d, lane)), eps);
+    float* o = out + r * d;
+    if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(o)) & 15u) == 0) {
+      for (int c = lane; c < (d >> 2); c += 32) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(xr) + c);
+        v.x /= nrm; v.y /= nrm; v.z /= nrm; v.w /= nrm;      // true division, like the reference
+        reinterpret_cast<float4*>(o)[c] = v;
+      }
+    } else {
+      for (int c = lane; c < d; c += 32) o[c] = __ldg(xr + c) / nrm;
+    }
+  }
+}
+
 // tf32 shadow: fp32 words whose low 13 mantissa bits are already zero (cvt.rna = round to nearest, ties away), so the
 // tensor core's truncation of kind::tf32 operands is exact and the per-element error is 2^-11 instead of 2^-10
 __global__ void __launch_bounds__(256) rows_to_tf32_kernel(const float* __restrict__ x, int64_t rows, int d,
@@ -74,6 +96,18 @@ __global__ void __launch_bounds__(256) rows_to_tf32_kernel(const float* __restri
 }
 
 }  // namespace rag
+
+extern "C" int rag_rows_normalize_f32(const float* x, int64_t rows, int32_t d, float eps, float* out, rag_stream_t stream) {
+  RAG_REQUIRE(rows >= 0 && d >= 1, RAG_EINVAL, "rows_normalize: rows=%lld d=%d", (long long)rows, d);
+  if (rows == 0) return RAG_OK;
+  RAG_REQUIRE(x && out, RAG_EINVAL, "rows_normalize: null pointer");
+  int64_t blocks = (rows + 7) / 8;
+  int64_t cap = (int64_t)rag::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  rag::rows_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, d, eps, out);
+  RAG_LAUNCH_OK("rows_normalize_kernel");
+  return RAG_OK;
+}
 
 extern "C" int rag_rows_to_tf32(const float* x, int64_t rows, int32_t d, int32_t normalize, float eps, float* out,
                                 int32_t d_pad, rag_stream_t stream) {

@@ -84,6 +84,23 @@ class EdgeAggregator:
         return self.csr(edges, edge_norm).spmm(all_emb, **epi)
 
 
+def make_resource_graph(all_emb: Tensor, edges: Tensor, edge_norm: Tensor, radius: int = 3,
+                        aggregator: Optional[EdgeAggregator] = None):
+    """Deterministic core of ``_make_resource_graph`` (modules/RAGraph.py:185-226 with num_augment_scale = 0 and
+    num_inverse_sample = 0, the finetune-phase settings :45-50): the library is every node, keys = A^radius X0 (the last
+    propagation layer), values = sum of the even layers X0 + A^2 X0 + ... (``res_emb[0::2]``).  Each layer is one SpMM over
+    the CSR built once from (edges, edge_norm); no [E, d] temporaries.  Returns (resource_keys, resource_values)."""
+    agg = aggregator or EdgeAggregator(all_emb.shape[0])
+    g = agg.csr(edges, edge_norm)
+    layer, values = all_emb, all_emb
+    with torch.no_grad():
+        for l in range(1, radius + 1):
+            layer = g.spmm(layer)
+            if l % 2 == 0:
+                values = values + layer
+    return layer, values
+
+
 def _agg(all_emb: Tensor, edges: Tensor, edge_norm: Tensor, num_nodes: int) -> Tensor:
     """Stateless form with the reference argument order (+ num_users+num_items made explicit)."""
     return CSRGraph.from_coo(edges, edge_norm, num_nodes, num_nodes).spmm(all_emb)

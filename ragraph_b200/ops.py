@@ -60,6 +60,25 @@ def _(x, eps=1e-12):
     return x.new_empty(x.shape[0])
 
 
+@torch.library.custom_op("ragraph::rows_normalize", mutates_args=())
+def rows_normalize(x: Tensor, eps: float = 1e-12) -> Tensor:
+    """F.normalize(x, p=2, dim=-1) for a 2-D fp32 tensor."""
+    _need_cuda(x)
+    x = _f32c(x, "rows_normalize")
+    if x.dim() != 2:
+        raise RuntimeError("rows_normalize: 2-D tensor expected")
+    out = torch.empty_like(x)
+    if x.numel():
+        with torch.cuda.device(x.device):
+            L.check(L.load().rag_rows_normalize_f32(_p(x), x.shape[0], x.shape[1], eps, _p(out), _stream()), "rows_normalize")
+    return out
+
+
+@rows_normalize.register_fake
+def _(x, eps=1e-12):
+    return torch.empty_like(x)
+
+
 @torch.library.custom_op("ragraph::rows_to_bf16", mutates_args=())
 def rows_to_bf16(x: Tensor, normalize: bool = True, eps: float = 1e-12) -> Tensor:
     """bf16 (optionally L2-normalised) shadow [rows, round_up(d, 64)] for the tensor-core filter."""

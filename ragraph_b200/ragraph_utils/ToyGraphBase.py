@@ -89,6 +89,29 @@ class ToyGraphBase:
                 self._positions[s].zero_()
         self._n += m
 
+    def add_graph(self, embeddings: Tensor, adj, node_labels: Optional[Tensor] = None, graph_label: Optional[Tensor] = None,
+                  positions: Optional[Tensor] = None) -> None:
+        """Insert one resource graph: the deterministic core of ``_build_toy_graph_base`` (ToyGraphBase.py:91-119; graph
+        variant RAGraph_graph/.../ToyGraphBase.py:97-129) for a graph whose backbone embeddings are given -- keys =
+        F.normalize(embeddings), values = k-hop propagation of the keys over ``adj`` (toy_graph_hop = query hop - 1),
+        labels = the node labels (node variants) or one_hot(graph_label) with keys / values averaged over the nodes
+        (graph variant: one library row per graph).  The RNG-driven augmentation / inverse sampling in front of it are
+        library-build policy and stay with the caller: call this once per augmented or sampled copy."""
+        from .Propagation import Propagation
+        keys = ops.rows_normalize(embeddings)
+        values = Propagation.aggregate_k_hop_features(adj, keys, self.toy_graph_hop)
+        if self.variant == "graph":
+            if graph_label is None:
+                raise RuntimeError("add_graph: the graph variant stores one_hot(graph_label) per graph")
+            keys = torch.mean(keys, dim=0).unsqueeze(0)
+            values = torch.mean(values, dim=0).unsqueeze(0)
+            labels = torch.nn.functional.one_hot(graph_label.reshape(-1)[:1].to(torch.int64), num_classes=self.num_class)
+        else:
+            if node_labels is None:
+                raise RuntimeError("add_graph: node_labels [n, C] needed")
+            labels = node_labels
+        self.add_entries(keys, values, labels, positions)
+
     def _refresh_derived(self, want_bf16: bool, want_tf32: bool = False) -> None:
         n = self._n
         if self._derived_rows < n:

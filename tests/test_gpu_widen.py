@@ -204,3 +204,35 @@ def test_fewshot_noisy_branch_shapes(golden):
     with torch.no_grad():
         out = m(None, cu(g["adj"]), cu(g["mean_fewshot_logits"]), cu(g["search_positions"]))
     assert out.shape == g["out"].shape and bool(torch.isfinite(out).all())
+
+
+# ------------------------------------------------------------------------------------------ a8 / 8f-2 library construction
+@pytest.mark.parametrize("d", [24, 64, 250])
+def test_rows_normalize(d):
+    g = torch.Generator().manual_seed(d)
+    x = torch.randn(500, d, generator=g) * 3
+    x[7] = 0.0                                                # zero row: eps clamp, stays zero
+    out = ops.rows_normalize(cu(x)).cpu()
+    ref = torch.nn.functional.normalize(x, p=2, dim=-1)
+    assert O.rel_err(out, ref) < 1e-6 and bool((out[7] == 0).all())
+
+
+def test_library_build_golden(golden):
+    g = golden("library_build")
+    d, C = g["emb0"].shape[1], 3
+    node = R.ToyGraphBase(None, C, d, 3, device=DEV, variant="node", capacity=4)
+    graph = R.ToyGraphBase(None, C, d, 1, device=DEV, variant="graph", capacity=1, label_dtype=torch.int64)
+    for i in range(int(g["n_graphs"])):
+        node.add_graph(cu(g[f"emb{i}"]), cu(g[f"adj{i}"]), node_labels=cu(g[f"node_labels{i}"]))
+        graph.add_graph(cu(g[f"emb{i}"]), cu(g[f"adj{i}"]), graph_label=cu(g[f"graph_label{i}"]))
+    assert O.rel_err(node.resource_keys.cpu(), g["node_keys"]) < REL
+    assert O.rel_err(node.resource_values.cpu(), g["node_values"]) < REL
+    assert np.array_equal(node.resource_labels.cpu().numpy(), g["node_labels"])
+    assert O.rel_err(graph.resource_keys.cpu(), g["graph_keys"]) < REL
+    assert O.rel_err(graph.resource_values.cpu(), g["graph_values"]) < REL
+    assert np.array_equal(graph.resource_labels.cpu().numpy(), g["graph_labels"])
+    keys, values = R.make_resource_graph(cu(g["edge_X"]), cu(g["edge_edges"]), cu(g["edge_w"]), int(g["edge_radius"]))
+    assert O.rel_err(keys.cpu(), g["edge_keys"]) < REL and O.rel_err(values.cpu(), g["edge_values"]) < REL
+    # a library built this way answers queries like the reference's: its own rows are their own nearest neighbours
+    _, idx = node.topk(node.resource_keys[:20].clone(), 1)
+    assert torch.equal(idx.cpu().reshape(-1), torch.arange(20))

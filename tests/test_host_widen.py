@@ -82,6 +82,7 @@ def cpu_ops(monkeypatch):
         "row_inv_norm": lambda x, eps=1e-12: 1.0 / x.norm(dim=1).clamp_min(eps),
         "prompt_act": lambda x, w, act=0: O.downstream_prompt(x, w.reshape(1, -1), bool(act)),
         "prototype_scores": _prototype_scores, "scatter_softmax": _scatter_softmax,
+        "rows_normalize": lambda x, eps=1e-12: torch.nn.functional.normalize(x, p=2, dim=-1, eps=eps),
     }
     for name, fn in table.items():
         monkeypatch.setattr(ops, name, fn)
@@ -177,3 +178,24 @@ def test_edge_time_encoding_host_logic(golden, cpu_ops):
     out = R.edge_rag_forward(T(g["X"]), edges, w, T(g["keys"]), T(g["values"]), int(g["num_layers"]),
                              int(g["retrieve_num"]), int(g["batch_size"]), float(g["retrieve_weight"]), edge_times=times)
     np.testing.assert_allclose(out.numpy(), g["out"], rtol=0, atol=5e-6)
+
+
+def test_library_build_host_logic(golden, cpu_ops):
+    g = golden("library_build")
+    d, C = g["emb0"].shape[1], 3
+    node = R.ToyGraphBase(None, C, d, 3, device="cpu", variant="node", capacity=4)
+    graph = R.ToyGraphBase(None, C, d, 1, device="cpu", variant="graph", capacity=1, label_dtype=torch.int64)
+    assert node.toy_graph_hop == int(g["node_hop"]) and graph.toy_graph_hop == int(g["graph_hop"])
+    for i in range(int(g["n_graphs"])):
+        node.add_graph(T(g[f"emb{i}"]), T(g[f"adj{i}"]), node_labels=T(g[f"node_labels{i}"]))
+        graph.add_graph(T(g[f"emb{i}"]), T(g[f"adj{i}"]), graph_label=T(g[f"graph_label{i}"]))
+    assert len(node) == g["node_keys"].shape[0] and len(graph) == 3
+    assert O.rel_err(node.resource_keys, g["node_keys"]) < 1e-6 and O.rel_err(node.resource_values, g["node_values"]) < 1e-6
+    assert np.array_equal(node.resource_labels.numpy(), g["node_labels"])
+    assert O.rel_err(graph.resource_keys, g["graph_keys"]) < 1e-6 and O.rel_err(graph.resource_values, g["graph_values"]) < 1e-6
+    assert np.array_equal(graph.resource_labels.numpy(), g["graph_labels"])
+    with pytest.raises(RuntimeError, match="graph_label"):
+        graph.add_graph(T(g["emb0"]), T(g["adj0"]))
+    keys, values = R.make_resource_graph(T(g["edge_X"]), T(g["edge_edges"]), T(g["edge_w"]), int(g["edge_radius"]))
+    np.testing.assert_allclose(keys.numpy(), g["edge_keys"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(values.numpy(), g["edge_values"], rtol=0, atol=2e-6)

@@ -176,3 +176,21 @@ def test_downprompt_graph(golden):
     ave = O.average_emb(T(g["graph_labels"]), gemb, 6, gemb.shape[0])
     assert np.array_equal(ave.numpy(), g["ave"])
     np.testing.assert_allclose(O.prototype_scores(gemb, ave, "log_softmax").numpy(), g["log_probs"], rtol=0, atol=1e-6)
+
+
+def test_library_build(golden):
+    g = golden("library_build")
+    nk, nv, nl, gk, gv, gl = [], [], [], [], [], []
+    for i in range(int(g["n_graphs"])):
+        adj, emb = T(g[f"adj{i}"]), T(g[f"emb{i}"])
+        k, v, l = O.build_library_rows_node(emb, adj, T(g[f"node_labels{i}"]), int(g["node_hop"]))
+        nk.append(k); nv.append(v); nl.append(l)
+        k, v, l = O.build_library_rows_graph(emb, adj, T(g[f"graph_label{i}"]), 3, int(g["graph_hop"]))
+        gk.append(k); gv.append(v); gl.append(l)
+    assert np.array_equal(torch.cat(nk).numpy(), g["node_keys"]) and np.array_equal(torch.cat(nv).numpy(), g["node_values"])
+    assert np.array_equal(torch.cat(nl).numpy(), g["node_labels"])
+    assert np.array_equal(torch.cat(gk).numpy(), g["graph_keys"]) and np.array_equal(torch.cat(gv).numpy(), g["graph_values"])
+    assert np.array_equal(torch.cat(gl).numpy(), g["graph_labels"])
+    keys, values = O.edge_resource_graph(T(g["edge_X"]), T(g["edge_edges"]), T(g["edge_w"]), int(g["edge_radius"]))
+    np.testing.assert_allclose(keys.numpy(), g["edge_keys"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(values.numpy(), g["edge_values"], rtol=0, atol=2e-6)
