@@ -184,6 +184,24 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+class StdoutToStderr:
+    """File-descriptor level: until restore(), everything written to stdout -- C libraries included -- lands on stderr.
+    NCCL prints its version banner straight to stdout when NCCL_DEBUG=VERSION (NCCL_DEBUG_FILE is only honoured from
+    WARN upwards), which would put a second line in front of the ONE JSON line the driver reads."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def restore(self):
+        if self.saved is not None:
+            sys.stdout.flush()
+            os.dup2(self.saved, 1)
+            os.close(self.saved)
+            self.saved = None
+
+
 # ----------------------------------------------------------------------------------------- our arm
 def main():
     global N_KEYS
@@ -208,6 +226,7 @@ def main():
 
     # rank 0 prints ONE JSON line on stdout: NCCL's own log (version banner at VERSION/WARN level) goes to stderr
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    guard = StdoutToStderr()
     import torch.distributed as dist
     import ragraph_b200 as R
     from ragraph_b200 import _lib as L, ops
@@ -345,9 +364,11 @@ def main():
                                 f"keys d={DIM}, mean of 2 runs; q/s extrapolated linearly in N to {N_KEYS}"}
     if world > 1:
         dist.barrier()
+    guard.restore()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        guard = StdoutToStderr()            # teardown chatter stays off stdout too
         dist.destroy_process_group()
 
 

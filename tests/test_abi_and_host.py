@@ -155,3 +155,15 @@ def test_process_graph_batch_matches_reference_dense_adjacency():
     dense[rows, csr.col.long()] = csr.val
     assert torch.equal(dense != 0, radj != 0)
     assert float((dense - radj).abs().max()) <= 1e-7
+
+
+def test_bench_stdout_guard_keeps_one_line():
+    """bench.py's fd-level guard: C-level and Python-level writes to stdout before restore() land on stderr."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; g = bench.StdoutToStderr(); os.write(1, b'NCCL version x\\n'); "
+            "print('python noise'); g.restore(); print('{\"ok\": 1}')" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout == '{"ok": 1}\n'
+    assert "NCCL version x" in r.stderr and "python noise" in r.stderr
