@@ -39,7 +39,7 @@ def spmm(graph: CSRGraph, x: Tensor) -> Tensor:
     """Differentiable `graph @ x` (x: [n_cols, F] float32 CUDA)."""
     if x.requires_grad and torch.is_grad_enabled():
         return _SpMMFn.apply(x, graph)
-    return ops.csr_spmm(graph.rowptr, graph.col, graph.val, x)
+    return ops.direct(ops.csr_spmm)(graph.rowptr, graph.col, graph.val, x)
 
 
 def spmm_epilogue(graph: CSRGraph, x: Tensor, epilogue: int = 0, bias: Optional[Tensor] = None,
@@ -51,8 +51,8 @@ def spmm_epilogue(graph: CSRGraph, x: Tensor, epilogue: int = 0, bias: Optional[
     needs_grad = torch.is_grad_enabled() and any(
         t is not None and t.requires_grad for t in (x, bias, alpha, blend_in, accum_in))
     if not needs_grad:
-        return ops.csr_spmm(graph.rowptr, graph.col, graph.val, x, epilogue, bias=bias, alpha=alpha,
-                            blend_in=blend_in, blend_w=blend_w, accum_in=accum_in)
+        return ops.direct(ops.csr_spmm)(graph.rowptr, graph.col, graph.val, x, epilogue, bias=bias, alpha=alpha,
+                                        blend_in=blend_in, blend_w=blend_w, accum_in=accum_in)
     g = graph.row_normalized() if epilogue & L.EPI_ROWNORM else graph
     y = _SpMMFn.apply(x, g) if x.requires_grad else ops.csr_spmm(g.rowptr, g.col, g.val, x)
     if epilogue & L.EPI_BIAS:

@@ -131,13 +131,14 @@ def edge_rag_forward(all_emb: Tensor, edges: Tensor, edge_norm: Tensor, resource
         key_inv_norm = ops.row_inv_norm(resource_keys)
     queries = all_emb.detach()              # indices are not differentiable; the library carries no grad (:186-226)
     out = torch.empty_like(queries)
+    cosine_topk, gather_reduce = ops.direct(ops.cosine_topk), ops.direct(ops.gather_reduce)   # ~60 batches per forward
     for start in range(0, n, batch_size):
         end = min(start + batch_size, n)
-        _, idx = ops.cosine_topk(queries[start:end], resource_keys, retrieve_num, key_inv_norm, keys_bf16, mode)
+        _, idx = cosine_topk(queries[start:end], resource_keys, retrieve_num, key_inv_norm, keys_bf16, mode)
         if train:
-            out[start:end] = ops.gather_reduce(resource_values, idx, L.REDUCE_MEAN)
+            out[start:end] = gather_reduce(resource_values, idx, L.REDUCE_MEAN)
         else:
-            out[start:end] = ops.gather_reduce(resource_values, idx, L.REDUCE_MEAN, total[start:end], retrieve_weight)
+            out[start:end] = gather_reduce(resource_values, idx, L.REDUCE_MEAN, total[start:end], retrieve_weight)
     if train:                               # gradient reaches all_emb through the layer sum only (:327-328)
         return (1 - retrieve_weight) * total + retrieve_weight * out
     return out

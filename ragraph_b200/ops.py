@@ -44,6 +44,16 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def direct(op):
+    """The Python body of a ``torch.ops.ragraph`` op without the torch.library dispatcher in front of it.
+
+    ``torch.library.custom_op`` costs ~15 us of host time per call (measured); a retrieve is 3-4 ops and the edge
+    variant's forward runs ~120 of them, so the eager, forward-only host loops (ToyGraphBase.retrieve, the no-grad SpMM
+    path, the sharded retriever) call the body directly -- same checks, same C-ABI call, same results.  The registered
+    ops stay the public surface (``torch.ops.ragraph.*``, fake kernels for tracing)."""
+    return getattr(op, "_init_fn", op)
+
+
 # ----------------------------------------------------------------------------- norms / shadow
 @torch.library.custom_op("ragraph::row_inv_norm", mutates_args=())
 def row_inv_norm(x: Tensor, eps: float = 1e-12) -> Tensor:

@@ -243,13 +243,13 @@ class ToyGraphBase:
         if self.variant == "node_fewshot" and self.structure_weight != 0.0:
             if search_positions is None:
                 raise RuntimeError("node_fewshot retrieval needs search_positions (position-aware codes)")
-            return ops.cosine2_topk(search_positions, self.resource_positions, self.structure_weight,
-                                    search_keys, self.resource_keys, self.semantic_weight, k)
+            return ops.direct(ops.cosine2_topk)(search_positions, self.resource_positions, self.structure_weight,
+                                                search_keys, self.resource_keys, self.semantic_weight, k)
         if k > L.RAG_MAX_K:
             return self._topk_large(search_keys, k)
         mode = self._pick_mode(search_keys.shape[0], k)
         shadow = self._shadow(mode)
-        return ops.cosine_topk(search_keys, self.resource_keys, k, self._inv_norm[:self._n], shadow, mode)
+        return ops.direct(ops.cosine_topk)(search_keys, self.resource_keys, k, self._inv_norm[:self._n], shadow, mode)
 
     def _topk_large(self, search_keys: Tensor, k: int, budget_bytes: int = 1 << 30) -> Tuple[Tensor, Tensor]:
         """k > RAG_MAX_K (the edge variant's vanilla configs ask for retrieve_num = 100000, i.e. most of the library,
@@ -277,8 +277,9 @@ class ToyGraphBase:
             search_keys = search_keys.unsqueeze(0)
         retrieve_num = 2 * self.retrieve_num if add_noise else self.retrieve_num
         _, topk_indices = self.topk(search_keys, retrieve_num, search_positions)
-        rag_embeddings = ops.gather_rows(self.resource_values, topk_indices)
-        rag_labels = ops.gather_rows(self.resource_labels, topk_indices)
+        gather_rows = ops.direct(ops.gather_rows)
+        rag_embeddings = gather_rows(self.resource_values, topk_indices)
+        rag_labels = gather_rows(self.resource_labels, topk_indices)
         if add_noise:
             if self.variant == "graph":
                 noise = torch.normal(mean=0, std=self.noise_std, size=rag_embeddings.shape).to(rag_embeddings.device)
@@ -286,8 +287,8 @@ class ToyGraphBase:
             else:
                 noise_indices = torch.randint(0, self._n, (search_keys.shape[0], self.noise_retrieve_num))
                 noise_indices = noise_indices.to(self.device)
-                rag_embeddings = torch.cat([rag_embeddings, ops.gather_rows(self.resource_values, noise_indices)], dim=1)
-                rag_labels = torch.cat([rag_labels, ops.gather_rows(self.resource_labels, noise_indices)], dim=1)
+                rag_embeddings = torch.cat([rag_embeddings, gather_rows(self.resource_values, noise_indices)], dim=1)
+                rag_labels = torch.cat([rag_labels, gather_rows(self.resource_labels, noise_indices)], dim=1)
         return rag_embeddings, rag_labels
 
     def retrieve_fused(self, search_keys: Tensor, k: Optional[int] = None, reduce: int = L.REDUCE_SUM,
@@ -298,7 +299,8 @@ class ToyGraphBase:
             search_keys = search_keys.unsqueeze(0)
         k = self.retrieve_num if k is None else k
         _, idx = self.topk(search_keys, k)
-        emb = ops.gather_reduce(self.resource_values, idx, reduce, blend_in, blend_w)
+        gather_reduce = ops.direct(ops.gather_reduce)
+        emb = gather_reduce(self.resource_values, idx, reduce, blend_in, blend_w)
         labels = self.resource_labels if self.resource_labels.dtype == torch.float32 else self.resource_labels.float()
-        lab = ops.gather_reduce(labels, idx, L.REDUCE_MEAN)
+        lab = gather_reduce(labels, idx, L.REDUCE_MEAN)
         return emb, lab, idx

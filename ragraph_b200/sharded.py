@@ -46,7 +46,8 @@ def _default_local_topk(store, q, k):
     from . import ops
     mode = store._pick_mode(q.shape[0], k)
     shadow = store._shadow(mode)
-    return ops.cosine_topk(q, store.resource_keys, k, store._inv_norm[:len(store)], shadow, mode, 0, store.shard_lo)
+    return ops.direct(ops.cosine_topk)(q, store.resource_keys, k, store._inv_norm[:len(store)], shadow, mode, 0,
+                                       store.shard_lo)
 
 
 def _default_merge(scores, idx, k):
