@@ -444,8 +444,47 @@ def gen_library_build():
     _save("library_build", n_graphs=len(graphs), **out)
 
 
+def gen_graph_forward():
+    """Unmodified RAGraph_graph/RAGraph.py:48-75 forward on a shim (one query graph -> [1, C] class probabilities)."""
+    _enter_variant("RAGraph_graph")
+    import importlib
+    from ragraph_utils.ToyGraphBase import ToyGraphBase
+    from ragraph_utils.TaskDecoder import TaskDecoder
+    RAG = importlib.import_module("RAGraph").RAGraph
+    g = torch.Generator().manual_seed(777)
+    nq, N, d, C = 23, 260, 32, 6
+    adj = _sym_norm_adj(nq, 0.15, g)
+    emb_q = torch.randn(nq, d, generator=g)
+    keys = torch.randn(N, d, generator=g) * 0.3
+    values = torch.randn(N, d, generator=g)
+    labels = torch.nn.functional.one_hot(torch.randint(0, C, (N,), generator=g), C)
+    base = ToyGraphBase(None, C, d, 1)
+    base.resource_keys, base.resource_values = keys, values
+    base.resource_labels = torch.cat((torch.empty(0, C), labels), dim=0)
+    torch.manual_seed(12)
+    dec = TaskDecoder(d, d, C)
+
+    class _PM:
+        def inference(self, features, a):
+            return emb_q
+
+    shim = object.__new__(RAG)
+    torch.nn.Module.__init__(shim)
+    shim.pretrain_model, shim.toy_graph_base, shim.decoder = _PM(), base, dec
+    shim.retrieve_weight, shim.label_weight, shim.finetune = 0.3, 0.3, True
+    shim.noise_finetune, shim.query_graph_hop = False, 1
+    shim.eval()
+    with torch.no_grad():
+        logits = shim.forward(None, adj)
+        shim.finetune = False
+        vanilla = shim.forward(None, adj)
+    _save("graph_forward", emb_q=emb_q, adj=adj, keys=keys, values=values, labels=base.resource_labels,
+          w1=dec.fc1.weight.detach(), b1=dec.fc1.bias.detach(), w2=dec.fc2.weight.detach(), b2=dec.fc2.bias.detach(),
+          logits=logits, vanilla=vanilla, retrieve_num=base.retrieve_num)
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
     _install_stubs()
     gen_node(); gen_graph(); gen_node_fewshot(); gen_edge(); gen_edge_eval()
-    gen_fewshot_forward(); gen_downprompt(); gen_library_build()
+    gen_fewshot_forward(); gen_downprompt(); gen_library_build(); gen_graph_forward()

@@ -236,3 +236,26 @@ def test_library_build_golden(golden):
     # a library built this way answers queries like the reference's: its own rows are their own nearest neighbours
     _, idx = node.topk(node.resource_keys[:20].clone(), 1)
     assert torch.equal(idx.cpu().reshape(-1), torch.arange(20))
+
+
+# ------------------------------------------------------------------------------------------ a7 graph-variant forward
+def test_graph_forward_golden(golden):
+    g = golden("graph_forward")
+    d, C = g["keys"].shape[1], g["labels"].shape[1]
+
+    class PM:
+        def inference(self, features, adj):
+            return cu(g["emb_q"])
+
+    base = R.ToyGraphBase(None, C, d, 1, device=DEV, variant="graph")
+    base.add_entries(cu(g["keys"]), cu(g["values"]), cu(g["labels"]))
+    model = R.RAGraph(PM(), base, 0, C, d, variant="graph").to(DEV).eval()
+    with torch.no_grad():
+        model.decoder.fc1.weight.copy_(cu(g["w1"])); model.decoder.fc1.bias.copy_(cu(g["b1"]))
+        model.decoder.fc2.weight.copy_(cu(g["w2"])); model.decoder.fc2.bias.copy_(cu(g["b2"]))
+        out = model(None, cu(g["adj"])).cpu()
+        model.finetune = False
+        van = model(None, cu(g["adj"])).cpu()
+    assert out.shape == (1, C)
+    assert float((out - T(g["logits"])).abs().max()) < 1e-5
+    assert float((van - T(g["vanilla"])).abs().max()) < 1e-6

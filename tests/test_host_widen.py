@@ -199,3 +199,28 @@ def test_library_build_host_logic(golden, cpu_ops):
     keys, values = R.make_resource_graph(T(g["edge_X"]), T(g["edge_edges"]), T(g["edge_w"]), int(g["edge_radius"]))
     np.testing.assert_allclose(keys.numpy(), g["edge_keys"], rtol=0, atol=2e-6)
     np.testing.assert_allclose(values.numpy(), g["edge_values"], rtol=0, atol=2e-6)
+
+
+def test_graph_forward_host_logic(golden, cpu_ops):
+    """RAGraph(variant="graph"): one query = mean of the node embeddings, 1-hop propagation averaged over the nodes,
+    weights 0.3 / 0.3 (RAGraph_graph/RAGraph.py:48-75)."""
+    g = golden("graph_forward")
+    d, C = g["keys"].shape[1], g["labels"].shape[1]
+
+    class PM:
+        def inference(self, features, adj):
+            return T(g["emb_q"])
+
+    base = R.ToyGraphBase(None, C, d, 1, device="cpu", variant="graph")
+    assert base.retrieve_num == int(g["retrieve_num"])
+    base.add_entries(T(g["keys"]), T(g["values"]), T(g["labels"]))
+    model = R.RAGraph(PM(), base, 0, C, d, variant="graph").eval()
+    with torch.no_grad():
+        model.decoder.fc1.weight.copy_(T(g["w1"])); model.decoder.fc1.bias.copy_(T(g["b1"]))
+        model.decoder.fc2.weight.copy_(T(g["w2"])); model.decoder.fc2.bias.copy_(T(g["b2"]))
+        out = model(None, T(g["adj"]))
+        model.finetune = False
+        van = model(None, T(g["adj"]))
+    assert out.shape == (1, C)
+    assert float((out - T(g["logits"])).abs().max()) < 1e-6
+    assert float((van - T(g["vanilla"])).abs().max()) < 1e-6

@@ -194,3 +194,16 @@ def test_library_build(golden):
     keys, values = O.edge_resource_graph(T(g["edge_X"]), T(g["edge_edges"]), T(g["edge_w"]), int(g["edge_radius"]))
     np.testing.assert_allclose(keys.numpy(), g["edge_keys"], rtol=0, atol=2e-6)
     np.testing.assert_allclose(values.numpy(), g["edge_values"], rtol=0, atol=2e-6)
+
+
+def test_graph_forward_fusion(golden):
+    g = golden("graph_forward")
+    keys, values, labels = T(g["keys"]), T(g["values"]), T(g["labels"])
+    emb_q, adj = T(g["emb_q"]), T(g["adj"])
+    _, _, emb, lab = O.retrieve_graph(torch.mean(emb_q, dim=0), keys, values, labels, int(g["retrieve_num"]))
+    params = (T(g["w1"]), T(g["b1"]), T(g["w2"]), T(g["b2"]))
+    out = O.fuse_graph(emb_q, adj, emb, lab, params)
+    assert out.shape == (1, 6)
+    np.testing.assert_allclose(out.numpy(), g["logits"], rtol=0, atol=1e-6)
+    van = O.fuse_graph(emb_q, adj, emb, lab, params, finetune=False)
+    assert np.array_equal(van.numpy(), g["vanilla"])
