@@ -235,9 +235,16 @@ def gen_edge():
     with torch.no_grad():
         time_norm = fw._relative_edge_time_encoding(edges, times)
         ur, ir = RAGraph.forward(fw, edges, w, times)
+    # noisy training branch (:296,310,316-319): top-(k+1) + one torch.randint row per query and batch
+    fw.use_noise, fw.training = True, True
+    with torch.no_grad():
+        torch.manual_seed(2024)
+        urn, irn = RAGraph.forward(fw, edges, w, times)
+    torch.manual_seed(2024)
+    noise_idx = torch.cat([torch.randint(0, n, (min(s0 + 32, n) - s0, 1)) for s0 in range(0, n, 32)], 0)
     _save("edge_forward", X=X, edges=edges, w=w, times=times, time_norm=time_norm, keys=keys, values=values,
           num_layers=args.num_layers, batch_size=32, retrieve_num=10, retrieve_weight=0.3,
-          out=torch.cat([ur, ir], 0))
+          out=torch.cat([ur, ir], 0), noise_seed=2024, noise_indices=noise_idx, out_noise=torch.cat([urn, irn], 0))
 
 
 def gen_edge_eval():

@@ -216,10 +216,12 @@ def fuse_graph(pretrain_emb, adj, rag_embeddings, rag_labels, decoder_params,
 
 
 def edge_forward(all_emb, edges, edge_norm, resource_keys, resource_values, num_layers=3,
-                 retrieve_num=10, batch_size=4096, retrieve_weight=0.3):
-    """RAGraph_edge/modules/RAGraph.py:279-328 (no LoRA/gating/noise): LightGCN layers via
+                 retrieve_num=10, batch_size=4096, retrieve_weight=0.3, noise_indices=None, noise_retrieve_num=1):
+    """RAGraph_edge/modules/RAGraph.py:279-328 (no LoRA/gating): LightGCN layers via
     _agg, then per 4096-query batch cosine -> top-k -> values[idx].mean(1), then the blend
-    res = (1-w) * sum(layers) + w * rag_emb."""
+    res = (1-w) * sum(layers) + w * rag_emb.  ``noise_indices`` ([n, noise_retrieve_num], the
+    per-batch torch.randint draws of :317 stacked) switches the noisy branch on: top-(k + noise)
+    plus the random rows, all averaged (:310,316-322)."""
     n = all_emb.shape[0]
     res_emb = [all_emb]
     for _ in range(num_layers):
@@ -229,8 +231,11 @@ def edge_forward(all_emb, edges, edge_norm, resource_keys, resource_values, num_
     for start in range(0, n, batch_size):
         end = min(start + batch_size, n)
         scores = cosine_similarity(query_emb[start:end], resource_keys)
-        _, idx = topk(scores, retrieve_num)
-        rag_emb[start:end] = resource_values[idx].mean(dim=1)
+        _, idx = topk(scores, retrieve_num + noise_retrieve_num if noise_indices is not None else retrieve_num)
+        batch_rag_emb = resource_values[idx]
+        if noise_indices is not None:
+            batch_rag_emb = torch.cat([batch_rag_emb, resource_values[noise_indices[start:end]]], dim=1)
+        rag_emb[start:end] = batch_rag_emb.mean(dim=1)
     res = sum(res_emb)
     return (1 - retrieve_weight) * res + retrieve_weight * rag_emb
 

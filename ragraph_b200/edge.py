@@ -111,12 +111,14 @@ def edge_rag_forward(all_emb: Tensor, edges: Tensor, edge_norm: Tensor, resource
                      retrieve_weight: float = 0.3, key_inv_norm: Optional[Tensor] = None,
                      keys_bf16: Optional[Tensor] = None, mode: int = L.SIM_FP32,
                      aggregator: Optional[EdgeAggregator] = None, edge_times: Optional[Tensor] = None,
-                     max_time_step=None) -> Tensor:
-    """modules/RAGraph.py:265-328 without LoRA/gating/noise: (time-aware edge weights when ``edge_times`` is given,
-    :266-267) + LightGCN layer sum + retrieval blend.
+                     max_time_step=None, add_noise: bool = False, noise_retrieve_num: int = 1) -> Tensor:
+    """modules/RAGraph.py:265-328 behind the LoRA / gating of the embedding tables (dense torch modules that produce
+    ``all_emb``): time-aware edge weights when ``edge_times`` is given (:266-267), LightGCN layer sum, retrieval blend.
     res = (1-w) * (X0 + A X0 + A^2 X0 + A^3 X0) + w * mean_k values[topk(cos(X0, keys))].
-    The layer sum rides in the SpMM epilogue (RAG_EPI_ACCUM); per 4096-query batch the retrieve is one fused
-    similarity+top-k launch and the mean + convex blend one gather_reduce launch."""
+    Per 4096-query batch the retrieve is one fused similarity+top-k launch and the mean + convex blend one
+    gather_reduce launch.  ``add_noise`` (use_noise and training, :296): top-(k + noise_retrieve_num) plus
+    noise_retrieve_num uniformly random library rows per query (CPU ``torch.randint`` like :317, same RNG stream),
+    all averaged together."""
     n = all_emb.shape[0]
     if edge_times is not None:
         edge_norm = relative_edge_time_encoding(edges, edge_times, n, max_time_step, edge_norm)
@@ -132,9 +134,13 @@ def edge_rag_forward(all_emb: Tensor, edges: Tensor, edge_norm: Tensor, resource
     queries = all_emb.detach()              # indices are not differentiable; the library carries no grad (:186-226)
     out = torch.empty_like(queries)
     cosine_topk, gather_reduce = ops.direct(ops.cosine_topk), ops.direct(ops.gather_reduce)   # ~60 batches per forward
+    k_eff = retrieve_num + noise_retrieve_num if add_noise else retrieve_num
     for start in range(0, n, batch_size):
         end = min(start + batch_size, n)
-        _, idx = cosine_topk(queries[start:end], resource_keys, retrieve_num, key_inv_norm, keys_bf16, mode)
+        _, idx = cosine_topk(queries[start:end], resource_keys, k_eff, key_inv_norm, keys_bf16, mode)
+        if add_noise:
+            noise_indices = torch.randint(0, resource_values.shape[0], (end - start, noise_retrieve_num))
+            idx = torch.cat([idx, noise_indices.to(idx.device)], dim=1)
         if train:
             out[start:end] = gather_reduce(resource_values, idx, L.REDUCE_MEAN)
         else:

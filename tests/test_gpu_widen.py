@@ -259,3 +259,12 @@ def test_graph_forward_golden(golden):
     assert out.shape == (1, C)
     assert float((out - T(g["logits"])).abs().max()) < 1e-5
     assert float((van - T(g["vanilla"])).abs().max()) < 1e-6
+
+
+def test_edge_forward_noisy_golden(golden):
+    g = golden("edge_forward")
+    torch.manual_seed(int(g["noise_seed"]))                     # the noise rows come from the CPU generator, like the reference
+    out = R.edge_rag_forward(cu(g["X"]), cu(g["edges"]), cu(g["w"]), cu(g["keys"]), cu(g["values"]),
+                             int(g["num_layers"]), int(g["retrieve_num"]), int(g["batch_size"]),
+                             float(g["retrieve_weight"]), edge_times=cu(g["times"]), add_noise=True).cpu()
+    assert O.rel_err(out, g["out_noise"]) < REL

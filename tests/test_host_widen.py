@@ -224,3 +224,13 @@ def test_graph_forward_host_logic(golden, cpu_ops):
     assert out.shape == (1, C)
     assert float((out - T(g["logits"])).abs().max()) < 1e-6
     assert float((van - T(g["vanilla"])).abs().max()) < 1e-6
+
+
+def test_edge_forward_noisy_host_logic(golden, cpu_ops):
+    """use_noise and training (modules/RAGraph.py:296,310,316-322): same CPU RNG stream as the reference."""
+    g = golden("edge_forward")
+    torch.manual_seed(int(g["noise_seed"]))
+    out = R.edge_rag_forward(T(g["X"]), T(g["edges"]), T(g["w"]), T(g["keys"]), T(g["values"]), int(g["num_layers"]),
+                             int(g["retrieve_num"]), int(g["batch_size"]), float(g["retrieve_weight"]),
+                             edge_times=T(g["times"]), add_noise=True, noise_retrieve_num=1)
+    np.testing.assert_allclose(out.numpy(), g["out_noise"], rtol=0, atol=5e-6)

@@ -207,3 +207,13 @@ def test_graph_forward_fusion(golden):
     np.testing.assert_allclose(out.numpy(), g["logits"], rtol=0, atol=1e-6)
     van = O.fuse_graph(emb_q, adj, emb, lab, params, finetune=False)
     assert np.array_equal(van.numpy(), g["vanilla"])
+
+
+def test_edge_forward_noisy_branch(golden):
+    g = golden("edge_forward")
+    w = O.edge_time_mix(T(g["w"]), T(g["time_norm"]))
+    out = O.edge_forward(T(g["X"]), T(g["edges"]), w, T(g["keys"]), T(g["values"]), int(g["num_layers"]),
+                         int(g["retrieve_num"]), int(g["batch_size"]), float(g["retrieve_weight"]),
+                         noise_indices=T(g["noise_indices"]))
+    np.testing.assert_allclose(out.numpy(), g["out_noise"], rtol=0, atol=5e-6)
+    assert not np.allclose(g["out_noise"], g["out"], atol=1e-4)       # the branch changes the result
