@@ -1344,11 +1344,16 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   TcArgs a{};
   a.Q = Q; a.N = N; a.n_qtiles = p.n_qtiles; a.n_splits = p.n_splits; a.tiles_per_split = p.tiles_per_split;
   a.n_tiles = p.n_tiles; a.kp = p.kp;
-  { const char* dbg = getenv("RAG_TC_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
-  { const char* tr = getenv("RAG_TC_TRACE"); a.trace = (tr && atoi(tr)) ? 1 : 0; if (a.debug == 3) { a.debug = 0; a.trace = 1; } }
-  { const char* t0 = getenv("RAG_TC_TRACE_T0"); a.trace_t0 = t0 ? atoi(t0) : 0; }
-  { const char* nt = getenv("RAG_TC_NOTMA"); a.no_tma = nt ? atoi(nt) : 0; }
-  { const char* sw = getenv("RAG_TS_SWAP"); a.swap_halves = sw ? atoi(sw) : 0; }
+  // Diagnostic switches (tools/ only: MMA-only ceilings, pipeline trace, operand experiments).  They change or void the
+  // results, so they are honoured only in a process started with RAG_DIAG=1 (read once); production calls never look.
+  static const bool diag = [] { const char* e = getenv("RAG_DIAG"); return e && atoi(e) != 0; }();
+  if (diag) {
+    { const char* dbg = getenv("RAG_TC_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
+    { const char* tr = getenv("RAG_TC_TRACE"); a.trace = (tr && atoi(tr)) ? 1 : 0; if (a.debug == 3) { a.debug = 0; a.trace = 1; } }
+    { const char* t0 = getenv("RAG_TC_TRACE_T0"); a.trace_t0 = t0 ? atoi(t0) : 0; }
+    { const char* nt = getenv("RAG_TC_NOTMA"); a.no_tma = nt ? atoi(nt) : 0; }
+    { const char* sw = getenv("RAG_TS_SWAP"); a.swap_halves = sw ? atoi(sw) : 0; }
+  }
   a.part_s = reinterpret_cast<float*>(w + p.off_ps);
   a.part_i = reinterpret_cast<int32_t*>(w + p.off_pi);
   a.overflow = reinterpret_cast<float*>(w + p.off_ovf);

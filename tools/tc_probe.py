@@ -1,5 +1,7 @@
 """Time the fused retrieval op alone (GPU): python tools/tc_probe.py [N] [d] [Q] [mode] [iters]"""
 import os, sys, time
+
+os.environ["RAG_DIAG"] = "1"      # this tool uses the library's diagnostic switches (RAG_TC_DEBUG / trace / ...)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ragraph_b200 import ops, _lib as L

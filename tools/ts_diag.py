@@ -3,6 +3,8 @@
     python tools/ts_diag.py            prints max |score - exact| and recall@10 for ss / ts / ts with swapped halves
 """
 import os, sys
+
+os.environ["RAG_DIAG"] = "1"      # this tool uses the library's diagnostic switches (RAG_TC_DEBUG / trace / ...)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ragraph_b200 import ops, _lib as L

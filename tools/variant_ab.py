@@ -6,6 +6,8 @@ variant ts = query tile stationary in tensor memory, ss = query tile in shared m
 mode 2, MMA only (RAG_TC_DEBUG=1: epilogue skips TMEM reads) and MMA + TMEM loads without the filter (=2).
 """
 import json, os, sys
+
+os.environ["RAG_DIAG"] = "1"      # this tool uses the library's diagnostic switches (RAG_TC_DEBUG / trace / ...)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ragraph_b200 import ops
