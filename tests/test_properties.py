@@ -1,0 +1,121 @@
+"""Property-based CPU tests (hypothesis) of the host logic and of the oracle's own helpers: shard partition /
+ownership, shard-merge == single scan (with exact ties across shards), CSR-direct preprocessing == the reference's dense
+block-diagonal adjacency, deterministic COO -> CSR, the parity criterion itself.  No compute call touches the CUDA library."""
+import numpy as np
+import torch
+from hypothesis import given, settings, strategies as st
+
+from oracle import ragraph_oracle as O
+from ragraph_b200 import process_graph_batch
+from ragraph_b200.csr import CSRGraph
+from ragraph_b200.sharded import owner_of, shard_bounds
+
+FAST = settings(max_examples=30, deadline=None)
+
+
+@FAST
+@given(n=st.integers(0, 5000), world=st.integers(1, 16))
+def test_shard_bounds_and_owner_agree(n, world):
+    spans = [shard_bounds(n, world, r) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    assert all(b == c for (_, b), (c, _) in zip(spans, spans[1:]))
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) - min(sizes) <= 1 and sorted(sizes, reverse=True) == sizes     # the extra rows go to the first ranks
+    if n:
+        own = owner_of(torch.arange(n), n, world)
+        for r, (a, b) in enumerate(spans):
+            assert bool((own[a:b] == r).all())
+
+
+@FAST
+@given(seed=st.integers(0, 2 ** 31 - 1), world=st.integers(1, 6), k=st.integers(1, 12), dup=st.booleans())
+def test_shard_merge_equals_single_scan(seed, world, k, dup):
+    """Per-shard top-k with global indices, merged in the product's order (score desc, index asc), equals the top-k of
+    the whole library -- including exact duplicate keys that land in different shards."""
+    g = torch.Generator().manual_seed(seed)
+    Q, N, d = 7, 60, 8
+    q = torch.randn(Q, d, generator=g)
+    keys = torch.randn(N, d, generator=g)
+    if dup:
+        keys[N - 1] = keys[0]
+        keys[N // 2] = keys[1]
+    S = O.cosine_similarity(q, keys)
+    parts_s, parts_i = [], []
+    for r in range(world):
+        lo, hi = shard_bounds(N, world, r)
+        kk = min(k, hi - lo)
+        # the shard's top-k in the product's deterministic order (score desc, index asc); torch.topk leaves the order of
+        # ties -- and WHICH of two tied keys survives at the cut -- unspecified
+        loc = np.lexsort((np.arange(hi - lo)[None, :].repeat(Q, 0), -S[:, lo:hi].numpy().astype(np.float64)), axis=1)[:, :kk]
+        i = torch.from_numpy(loc) + lo                         # global row ids
+        s = torch.gather(S, 1, i)
+        if kk < k:                                             # tiny shard: padded like ShardedRetriever._local
+            s = torch.cat([s, s.new_full((Q, k - kk), -torch.finfo(torch.float32).max)], 1)
+            i = torch.cat([i, i.new_full((Q, k - kk), -1)], 1)
+        parts_s.append(s); parts_i.append(i)
+    ms, mi = O.merge_topk(torch.stack(parts_s), torch.stack(parts_i), k)
+    # reference order: score desc, index asc over the whole row
+    order = np.lexsort((np.arange(N)[None, :].repeat(Q, 0), -S.numpy().astype(np.float64)), axis=1)[:, :k]
+    assert np.array_equal(mi.numpy(), order)
+    assert np.array_equal(ms.numpy(), np.take_along_axis(S.numpy(), order, axis=1))
+    ok, bad = O.topk_sets_match(mi.numpy(), O.cosine_similarity_f64(q, keys), k)
+    assert ok, bad
+
+
+@FAST
+@given(seed=st.integers(0, 2 ** 31 - 1), k=st.integers(1, 6))
+def test_parity_criterion_accepts_tie_swaps_and_rejects_wrong_rows(seed, k):
+    rng = np.random.default_rng(seed)
+    Q, N = 4, 30
+    S = rng.standard_normal((Q, N))
+    S[:, 7] = S[:, 3]                                          # an exact tie in every row
+    top = np.argsort(-S, axis=1, kind="stable")[:, :k]
+    assert O.topk_sets_match(top, S, k)[0]
+    swapped = top.copy()
+    for r in range(Q):                                         # exchanging the tied pair keeps the answer admissible
+        swapped[r] = [7 if x == 3 else (3 if x == 7 else x) for x in swapped[r]]
+    assert O.topk_sets_match(swapped, S, k)[0]
+    worst = np.argsort(S, axis=1)[:, :1]                       # the lowest-scoring key can never be in the top k < N
+    wrong = top.copy(); wrong[:, -1] = worst[:, 0]
+    if k < N and not np.any(np.abs(S[np.arange(Q), worst[:, 0]] - np.sort(S, axis=1)[:, -k]) <= 1e-6):
+        assert not O.topk_sets_match(wrong, S, k)[0]
+    dupl = top.copy()
+    if k >= 2:
+        dupl[:, 1] = dupl[:, 0]
+        assert not O.topk_sets_match(dupl, S, k)[0]
+
+
+@FAST
+@given(seed=st.integers(0, 2 ** 31 - 1), n_graphs=st.integers(1, 4))
+def test_csr_preprocessing_equals_reference_dense_adjacency(seed, n_graphs):
+    g = torch.Generator().manual_seed(seed)
+    xs, eis = [], []
+    for _ in range(n_graphs):
+        n = int(torch.randint(1, 12, (1,), generator=g))
+        E = int(torch.randint(0, 3 * n, (1,), generator=g))
+        xs.append(torch.rand(n, 5, generator=g))
+        eis.append(torch.randint(0, n, (2, E), generator=g))
+    feats, csr, labs = process_graph_batch(xs, eis, 3)
+    rf, radj, rl = O.process_tu_arrays([x.numpy() for x in xs], [e.numpy() for e in eis], 3)
+    assert torch.equal(feats, rf) and torch.equal(labs, rl)
+    dense = torch.zeros(csr.n_rows, csr.n_cols)
+    dense[csr.row_ids(), csr.col.long()] = csr.val
+    assert float((dense - radj).abs().max()) <= 1e-7 and torch.equal(dense != 0, radj != 0)
+    assert int(csr.rowptr[-1]) == csr.nnz and bool((csr.rowptr[1:] >= csr.rowptr[:-1]).all())
+
+
+@FAST
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 40), E=st.integers(0, 200), weighted=st.booleans())
+def test_deterministic_coo_to_csr_is_the_same_matrix(seed, n, E, weighted):
+    g = torch.Generator().manual_seed(seed)
+    edges = torch.stack([torch.randint(0, n, (E,), generator=g), torch.randint(0, n, (E,), generator=g)], 1)
+    w = torch.rand(E, generator=g) if weighted else None
+    csr = CSRGraph.from_coo(edges, w, n, n, deterministic=True)
+    X = torch.randn(n, 3, generator=g).double()
+    ref = torch.from_numpy(O.edge_agg_f64(X.numpy(), edges.numpy(), (w if w is not None else torch.ones(E)).numpy(), n))
+    val = csr.val.double() if csr.val is not None else torch.ones(E, dtype=torch.float64)
+    got = torch.zeros(n, 3, dtype=torch.float64).index_add_(0, csr.row_ids(), X[csr.col.long()] * val[:, None])
+    assert torch.allclose(got, ref, atol=1e-9)
+    # inside a row, entries keep the original edge order (fixed fp32 summation order)
+    t = csr.transpose().transpose()
+    assert t is csr
