@@ -490,8 +490,40 @@ def gen_graph_forward():
           logits=logits, vanilla=vanilla, retrieve_num=base.retrieve_num)
 
 
+def gen_inverse_sampling():
+    """InverseSampling.compute_sample_prob: dense variant (RAGraph_node/ragraph_utils/InverseSampling.py:6-56) on an
+    adjacency with a dangling node, sparse variant (RAGraph_edge/modules/ragraph_utils/InverseSampling.py:6-69)."""
+    g = torch.Generator().manual_seed(4242)
+    _enter_variant("RAGraph_node")
+    from ragraph_utils.InverseSampling import InverseSampling as ISdense
+    n = 40
+    a = (torch.rand(n, n, generator=g) < 0.1).float()
+    a = torch.triu(a, 1); a = a + a.t()
+    a[7, :] = 0.0                                           # node 7 has no out-links (but keeps in-links): dangling row
+    with torch.no_grad():
+        pr = ISdense.pagerank_algorithm(a.clone())
+        dc = ISdense.degree_centrality_algorithm(a.clone())
+        sp = ISdense.compute_sample_prob(a.clone())
+    adj_norm = _sym_norm_adj(25, 0.2, g)
+    with torch.no_grad():
+        sp_norm = ISdense.compute_sample_prob(adj_norm.clone())
+    _enter_variant("RAGraph_edge", argv=["x", "--device", "cpu", "--data_path", "dataset/amazon"])
+    from modules.ragraph_utils.InverseSampling import InverseSampling as ISsparse
+    nu, ni, E = 30, 20, 200
+    m = nu + ni
+    u = torch.randint(0, nu, (E,), generator=g); i = torch.randint(0, ni - 1, (E,), generator=g) + nu   # last item isolated
+    adj_sp = torch.sparse_coo_tensor(torch.cat([torch.stack([u, i]), torch.stack([i, u])], 1),
+                                     torch.rand(2 * E, generator=g), (m, m)).coalesce()
+    with torch.no_grad():
+        sp_sparse = ISsparse.compute_sample_prob(adj_sp)
+        pr_sparse = ISsparse.pagerank_algorithm(adj_sp)
+    _save("inverse_sampling", adj=a, pagerank=pr, degree_centrality=dc, sample_prob=sp, adj_norm=adj_norm,
+          sample_prob_norm=sp_norm, sparse_indices=adj_sp._indices(), sparse_values=adj_sp._values(), sparse_n=m,
+          pagerank_sparse=pr_sparse, sample_prob_sparse=sp_sparse)
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
     _install_stubs()
     gen_node(); gen_graph(); gen_node_fewshot(); gen_edge(); gen_edge_eval()
-    gen_fewshot_forward(); gen_downprompt(); gen_library_build(); gen_graph_forward()
+    gen_fewshot_forward(); gen_downprompt(); gen_library_build(); gen_graph_forward(); gen_inverse_sampling()

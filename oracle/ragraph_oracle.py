@@ -370,6 +370,40 @@ def edge_resource_graph(all_emb, edges, edge_norm, radius):
 
 
 # ----------------------------------------------------------------------------------------
+# 8f-2  inverse-importance sampling probabilities (library build; PageRank as an SpMV)
+# ----------------------------------------------------------------------------------------
+def pagerank(adj: torch.Tensor, d=0.85, eps=1e-6) -> torch.Tensor:
+    """RAGraph_node/ragraph_utils/InverseSampling.py:22-47 (dense): row-normalised transition matrix, rows without
+    out-links replaced by the uniform row, power iteration until the L1 change is < eps; returns the PREVIOUS iterate."""
+    N = adj.shape[0]
+    out_degree = torch.sum(adj, dim=1)
+    zero_out_degree = out_degree == 0
+    out_degree[zero_out_degree] = 1
+    adj_normalized = adj / out_degree[:, None]
+    adj_normalized[zero_out_degree] = 1.0 / N
+    p = torch.ones(N, dtype=torch.float32) / N
+    adj_normalized_t = adj_normalized.t()
+    while True:
+        new_p = (1 - d) / N + d * torch.mv(adj_normalized_t, p)
+        if torch.norm(new_p - p, p=1) < eps:
+            break
+        p = new_p
+    return p
+
+
+def degree_centrality(adj: torch.Tensor) -> torch.Tensor:
+    """InverseSampling.py:49-56: column sums / (N - 1)."""
+    return torch.sum(adj, dim=0) / (adj.shape[0] - 1)
+
+
+def sample_prob(adj: torch.Tensor) -> torch.Tensor:
+    """InverseSampling.py:6-19: probabilities proportional to 1 / (0.5 PageRank + 0.5 degree centrality + 1e-6)."""
+    node_importance = 0.5 * pagerank(adj.clone()) + 0.5 * degree_centrality(adj)
+    inverse_node_importance = 1 / (node_importance + 1e-6)
+    return inverse_node_importance / torch.sum(inverse_node_importance)
+
+
+# ----------------------------------------------------------------------------------------
 # multi-GPU restatement (new functionality, C1): merge of per-shard candidates
 # ----------------------------------------------------------------------------------------
 def rating_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, hist_rowptr, hist_items, k: int):

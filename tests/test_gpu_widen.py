@@ -268,3 +268,19 @@ def test_edge_forward_noisy_golden(golden):
                              int(g["num_layers"]), int(g["retrieve_num"]), int(g["batch_size"]),
                              float(g["retrieve_weight"]), edge_times=cu(g["times"]), add_noise=True).cpu()
     assert O.rel_err(out, g["out_noise"]) < REL
+
+
+# ------------------------------------------------------------------------------------------ 8f-2 PageRank as SpMV
+def test_inverse_sampling_golden(golden):
+    # The power iteration stops when the L1 change drops below 1e-6: a different fp32 summation order can move the stop
+    # by one step, which moves an entry by up to ~1e-6 / n of absolute value -- hence 5e-5 relative to the largest entry.
+    tol = 5e-5
+    g = golden("inverse_sampling")
+    IS = R.InverseSampling
+    assert O.rel_err(IS.pagerank_algorithm(cu(g["adj"])).cpu(), g["pagerank"]) < tol
+    sp = IS.compute_sample_prob(cu(g["adj"])).cpu()
+    assert O.rel_err(sp, g["sample_prob"]) < tol and abs(float(sp.sum()) - 1.0) < 1e-5
+    assert O.rel_err(IS.compute_sample_prob(cu(g["adj_norm"])).cpu(), g["sample_prob_norm"]) < tol
+    n = int(g["sparse_n"])
+    adj_sp = torch.sparse_coo_tensor(cu(g["sparse_indices"]), cu(g["sparse_values"]), (n, n)).coalesce()
+    assert O.rel_err(IS.compute_sample_prob(adj_sp).cpu(), g["sample_prob_sparse"]) < tol

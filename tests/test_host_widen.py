@@ -234,3 +234,19 @@ def test_edge_forward_noisy_host_logic(golden, cpu_ops):
                              int(g["retrieve_num"]), int(g["batch_size"]), float(g["retrieve_weight"]),
                              edge_times=T(g["times"]), add_noise=True, noise_retrieve_num=1)
     np.testing.assert_allclose(out.numpy(), g["out_noise"], rtol=0, atol=5e-6)
+
+
+def test_inverse_sampling_host_logic(golden, cpu_ops):
+    """PageRank as F = 1 SpMM steps on the transposed transition CSR; dense, sym-normalised and torch-sparse inputs."""
+    g = golden("inverse_sampling")
+    IS = R.InverseSampling
+    adj = T(g["adj"])
+    assert O.rel_err(IS.pagerank_algorithm(adj), g["pagerank"]) < 1e-5
+    assert O.rel_err(IS.degree_centrality_algorithm(adj), g["degree_centrality"]) < 1e-6
+    sp = IS.compute_sample_prob(adj)
+    assert O.rel_err(sp, g["sample_prob"]) < 1e-5 and abs(float(sp.sum()) - 1.0) < 1e-5
+    assert O.rel_err(IS.compute_sample_prob(T(g["adj_norm"])), g["sample_prob_norm"]) < 1e-5
+    n = int(g["sparse_n"])
+    adj_sp = torch.sparse_coo_tensor(T(g["sparse_indices"]), T(g["sparse_values"]), (n, n)).coalesce()
+    assert O.rel_err(IS.pagerank_algorithm(adj_sp), g["pagerank_sparse"]) < 1e-5
+    assert O.rel_err(IS.compute_sample_prob(adj_sp), g["sample_prob_sparse"]) < 1e-5

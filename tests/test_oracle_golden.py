@@ -217,3 +217,18 @@ def test_edge_forward_noisy_branch(golden):
                          noise_indices=T(g["noise_indices"]))
     np.testing.assert_allclose(out.numpy(), g["out_noise"], rtol=0, atol=5e-6)
     assert not np.allclose(g["out_noise"], g["out"], atol=1e-4)       # the branch changes the result
+
+
+def test_inverse_sampling(golden):
+    g = golden("inverse_sampling")
+    adj = T(g["adj"])
+    assert np.array_equal(O.pagerank(adj.clone()).numpy(), g["pagerank"])
+    assert np.array_equal(O.degree_centrality(adj).numpy(), g["degree_centrality"])
+    assert np.array_equal(O.sample_prob(adj).numpy(), g["sample_prob"])
+    assert np.array_equal(O.sample_prob(T(g["adj_norm"])).numpy(), g["sample_prob_norm"])
+    assert abs(float(g["sample_prob"].sum()) - 1.0) < 1e-5 and abs(float(g["pagerank"].sum()) - 1.0) < 1e-4
+    # the sparse variant of the edge package computes the same quantity: dense restatement on the densified matrix
+    n = int(g["sparse_n"])
+    dense = torch.zeros(n, n).index_put_((T(g["sparse_indices"])[0], T(g["sparse_indices"])[1]), T(g["sparse_values"]))
+    np.testing.assert_allclose(O.pagerank(dense.clone()).numpy(), g["pagerank_sparse"], rtol=0, atol=2e-7)
+    np.testing.assert_allclose(O.sample_prob(dense).numpy(), g["sample_prob_sparse"], rtol=0, atol=2e-7)
