@@ -107,6 +107,7 @@ class RAGraphFewShot(nn.Module):
             rag_logits = torch.mean(mean_fewshot_logits[torch.argmax(rag_labels, dim=-1)], dim=1)
             idx = None
         else:
+            search_positions = base.query_positions(adj, search_positions)
             _, idx = base.topk(pretrain_embedddings, base.retrieve_num, search_positions)
             # labels[idx].argmax(-1) == class_id[idx]: one bit-exact gather of the per-row class ids, then the
             # mean over k of the few-shot logits as one gather-reduce over the [C, C'] logits table

@@ -242,7 +242,8 @@ class ToyGraphBase:
         """(scores[Q,k], indices[Q,k] int64): torch.topk(cosine(search_keys, resource_keys), k) fused."""
         if self.variant == "node_fewshot" and self.structure_weight != 0.0:
             if search_positions is None:
-                raise RuntimeError("node_fewshot retrieval needs search_positions (position-aware codes)")
+                raise RuntimeError("node_fewshot retrieval needs search_positions (position-aware codes); retrieve() "
+                                   "derives them from search_adj like the reference")
             return ops.direct(ops.cosine2_topk)(search_positions, self.resource_positions, self.structure_weight,
                                                 search_keys, self.resource_keys, self.semantic_weight, k)
         if k > L.RAG_MAX_K:
@@ -268,6 +269,17 @@ class ToyGraphBase:
             scores[a:b], idx[a:b] = torch.topk(s, k, dim=1, largest=True, sorted=True)
         return scores, idx
 
+    def query_positions(self, search_adj, search_positions: Optional[Tensor] = None) -> Optional[Tensor]:
+        """Structure codes of the query graph for the two-metric score (RAGraph_node_fewshot/.../ToyGraphBase.py:49):
+        the caller's ``search_positions`` if given, else derived from the dense ``search_adj`` like the reference does
+        (PositionAwareEncoder, random anchors from the CPU generator); None for the single-metric variants."""
+        if search_positions is not None or self.variant != "node_fewshot" or self.structure_weight == 0.0:
+            return search_positions
+        if not (isinstance(search_adj, Tensor) and search_adj.layout == torch.strided):
+            return None
+        from .PositionAwareEncoder import PositionAwareEncoder
+        return PositionAwareEncoder.encode_position_aware_code(search_adj, self.num_anchors, self.dis_q)
+
     def retrieve(self, search_keys: Tensor, search_adj, add_noise: bool, search_positions: Optional[Tensor] = None):
         """Same contract as the reference: returns (rag_embeddings[Q,k',d], rag_labels[Q,k',C]).
         node (:47-81): add_noise doubles k and appends noise_retrieve_num random rows (CPU torch.randint,
@@ -275,6 +287,7 @@ class ToyGraphBase:
         to the gathered values (:84-85)."""
         if search_keys.dim() == 1:
             search_keys = search_keys.unsqueeze(0)
+        search_positions = self.query_positions(search_adj, search_positions)
         retrieve_num = 2 * self.retrieve_num if add_noise else self.retrieve_num
         _, topk_indices = self.topk(search_keys, retrieve_num, search_positions)
         gather_rows = ops.direct(ops.gather_rows)

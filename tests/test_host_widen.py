@@ -250,3 +250,23 @@ def test_inverse_sampling_host_logic(golden, cpu_ops):
     adj_sp = torch.sparse_coo_tensor(T(g["sparse_indices"]), T(g["sparse_values"]), (n, n)).coalesce()
     assert O.rel_err(IS.pagerank_algorithm(adj_sp), g["pagerank_sparse"]) < 1e-5
     assert O.rel_err(IS.compute_sample_prob(adj_sp), g["sample_prob_sparse"]) < 1e-5
+
+
+def test_fewshot_positions_derived_from_adjacency(golden, cpu_ops):
+    """retrieve(search_keys, search_adj, add_noise) with the reference's three arguments: the few-shot variant derives
+    the query graph's position-aware codes from search_adj with the same seeded CPU randint as the reference."""
+    g = golden("fewshot_forward_node")
+    from ragraph_b200.ragraph_utils import PositionAwareEncoder
+    torch.manual_seed(516)                                   # the seed the golden generator used for this forward
+    sp = PositionAwareEncoder.encode_position_aware_code(T(g["adj"]), 10, 10)
+    assert np.array_equal(sp.numpy(), g["search_positions"])
+    d, C = g["keys"].shape[1], g["labels"].shape[1]
+    base = R.ToyGraphBase(None, C, d, int(g["hop"]), device="cpu", variant="node_fewshot")
+    base.retrieve_num = int(g["retrieve_num"])
+    base.add_entries(T(g["keys"]), T(g["values"]), T(g["labels"]), T(g["positions"]))
+    torch.manual_seed(516)
+    emb_a, lab_a = base.retrieve(T(g["emb_q"]), T(g["adj"]), False)                       # positions derived
+    emb_b, lab_b = base.retrieve(T(g["emb_q"]), T(g["adj"]), False, T(g["search_positions"]))
+    assert torch.equal(emb_a, emb_b) and torch.equal(lab_a, lab_b)
+    node = R.ToyGraphBase(None, C, d, 3, device="cpu", variant="node")
+    assert node.query_positions(T(g["adj"])) is None         # single-metric variants never compute them
