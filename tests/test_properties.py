@@ -119,3 +119,39 @@ def test_deterministic_coo_to_csr_is_the_same_matrix(seed, n, E, weighted):
     # inside a row, entries keep the original edge order (fixed fp32 summation order)
     t = csr.transpose().transpose()
     assert t is csr
+
+
+def _round_tf32_rna(x: torch.Tensor) -> torch.Tensor:
+    """cvt.rna.tf32.f32 on the CPU: keep 10 mantissa bits, round to nearest, ties away from zero."""
+    bits = x.contiguous().view(torch.int32)
+    mag = (bits & 0x7fffffff) + 0x1000                      # half of the dropped 13 bits: ties go away from zero
+    return ((bits & -0x80000000) | (mag & ~0x1fff)).view(torch.float32)
+
+
+@FAST
+@given(seed=st.integers(0, 2 ** 31 - 1), d=st.sampled_from([8, 30, 64, 128, 256]),
+       kind=st.sampled_from(["gauss", "sparse", "constant", "heavy"]))
+def test_low_precision_score_error_bounds(seed, d, kind):
+    """The premise of the exactness certificate (csrc/topk_tc.cu, TC_EPS) and of the tf32 error band the tests use: for
+    L2-normalised vectors whose components are rounded once to bf16 (8 significant bits) or tf32 (11), the dot product of
+    the rounded vectors differs from the exact cosine by at most 2^-8 resp. 2^-10 (plus fp32 accumulation slack)."""
+    g = torch.Generator().manual_seed(seed)
+    n = 64
+    if kind == "gauss":
+        q, k = torch.randn(n, d, generator=g), torch.randn(n, d, generator=g)
+    elif kind == "sparse":                                  # almost one-hot: a single large component
+        q = torch.randn(n, d, generator=g) * 1e-3; k = torch.randn(n, d, generator=g) * 1e-3
+        q[torch.arange(n), torch.randint(0, d, (n,), generator=g)] = 1.0
+        k[torch.arange(n), torch.randint(0, d, (n,), generator=g)] = -1.0
+    elif kind == "constant":                                # all components equal: every rounding error has the same sign
+        q = torch.full((n, d), 1.0) * torch.rand(n, 1, generator=g); k = q.clone()
+    else:                                                   # heavy tailed
+        q = torch.randn(n, d, generator=g) ** 3; k = torch.randn(n, d, generator=g) ** 3
+    qn, kn = torch.nn.functional.normalize(q, dim=-1), torch.nn.functional.normalize(k, dim=-1)
+    exact = (qn.double() * kn.double()).sum(-1)
+    bf = (qn.bfloat16().double() * kn.bfloat16().double()).sum(-1)
+    assert float((bf - exact).abs().max()) <= 2.0 ** -8 + 2.0 ** -10
+    tf = (_round_tf32_rna(qn).double() * _round_tf32_rna(kn).double()).sum(-1)
+    assert float((tf - exact).abs().max()) <= 2.0 ** -10 + 1e-5
+    r = _round_tf32_rna(qn)
+    assert int((r.view(torch.int32) & 0x1fff).abs().max()) == 0 and float((r - qn).abs().max()) <= 2.0 ** -11
