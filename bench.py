@@ -333,6 +333,7 @@ def main():
                        3: "cosine_topk_ts_kernel (tcgen05 bf16, query tile stationary in TMEM) + threshold pre-pass + fp32 refine"
                        }.get(mode, str(mode)),
             "kernel_ms": kern_ms, "peak_source": peaks["src"] + " bf16 burst (cuBLAS 8192^3)",
+            "peak_sustained": peaks["bf16_sustained"], "frac_of_sustained": tf_ach / peaks["bf16_sustained"],
             "algorithmic": "2*Q*N_local*d flop per launch"}
 
     line = {"metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
