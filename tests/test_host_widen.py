@@ -83,6 +83,7 @@ def cpu_ops(monkeypatch):
         "prompt_act": lambda x, w, act=0: O.downstream_prompt(x, w.reshape(1, -1), bool(act)),
         "prototype_scores": _prototype_scores, "scatter_softmax": _scatter_softmax,
         "rows_normalize": lambda x, eps=1e-12: torch.nn.functional.normalize(x, p=2, dim=-1, eps=eps),
+        "cosine_similarity": lambda q, keys, flags=0: O.cosine_similarity(q, keys),
     }
     for name, fn in table.items():
         monkeypatch.setattr(ops, name, fn)
