@@ -141,3 +141,133 @@ def test_edge_agg_and_scatter_with_integration_patches(reference, cpu_ops):  # n
     times = torch.randint(0, 1000, (edges.shape[0],), generator=g)
     want_t = RefEdge._relative_edge_time_encoding(shim, edges, times)
     assert float((R.relative_edge_time_encoding(edges, times, n) - want_t).abs().max()) < 1e-6
+
+
+def test_graph_forward_with_our_store(reference, cpu_ops):  # noqa: F811
+    """RAGraph_graph/RAGraph.py:48-75 unchanged, our ToyGraphBase (graph variant: 1-D query, int64 one-hot labels) behind it."""
+    reference("RAGraph_graph")
+    from ragraph_utils import TaskDecoder as RefDecoder
+    ref_tgb = sys.modules["ragraph_utils.ToyGraphBase"]
+    RefRAG = importlib.import_module("RAGraph").RAGraph
+    g = torch.Generator().manual_seed(8)
+    n, N, d, C = 19, 200, 32, 6
+    adj = _sym_norm_adj(n, 0.2, g)
+    emb = torch.randn(n, d, generator=g)
+    keys = torch.randn(N, d, generator=g) * 0.3
+    values = torch.randn(N, d, generator=g)
+    labels = torch.nn.functional.one_hot(torch.randint(0, C, (N,), generator=g), C)
+
+    class PM:
+        def inference(self, features, a):
+            return emb
+
+    base = ref_tgb.ToyGraphBase(None, C, d, 1)
+    base.resource_keys, base.resource_values = keys, values
+    base.resource_labels = torch.cat((torch.empty(0, C), labels), dim=0)
+    torch.manual_seed(9)
+    shim = object.__new__(RefRAG)
+    torch.nn.Module.__init__(shim)
+    shim.pretrain_model, shim.toy_graph_base, shim.decoder = PM(), base, RefDecoder(d, d, C)
+    shim.retrieve_weight, shim.label_weight, shim.finetune = 0.3, 0.3, True
+    shim.noise_finetune, shim.query_graph_hop = False, 1
+    shim.eval()
+    with torch.no_grad():
+        want = shim.forward(None, adj)
+    mine = R.ToyGraphBase(None, C, d, 1, device="cpu", variant="graph")
+    assert mine.retrieve_num == base.retrieve_num
+    mine.add_entries(keys, values, labels)
+    shim.toy_graph_base = mine
+    with torch.no_grad():
+        got = shim.forward(None, adj)
+    assert got.shape == want.shape == (1, C) and float((got - want).abs().max()) < 1e-5
+
+
+def test_node_fewshot_forward_with_our_store(reference, cpu_ops):  # noqa: F811
+    """RAGraph_node_fewshot/RAGraph.py:47-83 unchanged (encode -> retrieve(emb, adj, noise) -> ... -> decode); our store
+    derives the position-aware codes from the adjacency with the same seeded CPU randint as the reference's retrieve."""
+    reference("RAGraph_node_fewshot")
+    ref_tgb = sys.modules.get("ragraph_utils.ToyGraphBase") or importlib.import_module("ragraph_utils.ToyGraphBase")
+    import layers.gcn as ref_gcn
+    RefRAG = importlib.import_module("RAGraph").RAGraph
+    g = torch.Generator().manual_seed(10)
+    n, N, d, C = 22, 300, 32, 3
+    adj = _sym_norm_adj(n, 0.15, g)
+    emb = torch.randn(n, d, generator=g)
+    keys = torch.nn.functional.normalize(torch.randn(N, d, generator=g), dim=-1)
+    values = torch.randn(N, d, generator=g)
+    labels = torch.nn.functional.one_hot(torch.randint(0, C, (N,), generator=g), C).float()
+    positions = torch.rand(N, 10, generator=g)
+    logits_table = torch.randn(C, C, generator=g)
+    torch.manual_seed(11)
+    dec = ref_gcn.GCN(d, C, "prelu")
+
+    class PM:
+        def encode(self, features, a):
+            return emb
+
+        def decode(self, hidden, a):
+            with torch.no_grad():
+                return dec((hidden, a))
+
+    base = object.__new__(ref_tgb.ToyGraphBase)
+    base.retrieve_num, base.noise_retrieve_num, base.num_anchors, base.dis_q = 5, 1, 10, 10
+    base.structure_weight, base.semantic_weight = 0.001, 0.999
+    base.resource_keys, base.resource_values, base.resource_labels, base.resource_positions = keys, values, labels, positions
+    shim = object.__new__(RefRAG)
+    torch.nn.Module.__init__(shim)
+    shim.pretrain_model, shim.toy_graph_base = PM(), base
+    shim.retrieve_weight, shim.label_weight, shim.finetune = 0.5, 0.5, True
+    shim.noise_finetune, shim.query_graph_hop = False, 3
+    shim.eval()
+    with torch.no_grad():
+        torch.manual_seed(12)
+        want = shim.forward(None, adj, logits_table)
+    mine = R.ToyGraphBase(None, C, d, 3, device="cpu", variant="node_fewshot")
+    mine.retrieve_num = 5
+    mine.add_entries(keys, values, labels, positions)
+    shim.toy_graph_base = mine
+    with torch.no_grad():
+        torch.manual_seed(12)
+        got = shim.forward(None, adj, logits_table)
+    assert float((got - want).abs().max()) < 1e-5
+    # and our own few-shot module with the reference's backbone object
+    ours = R.RAGraphFewShot(PM(), mine, d, True, False, 3, 0.5, 0.5, graph_level=False).eval()
+    with torch.no_grad():
+        torch.manual_seed(12)
+        got2 = ours(None, adj, logits_table)
+    assert float((got2 - want).abs().max()) < 1e-5
+
+
+def test_edge_forward_with_integration_patches(reference, cpu_ops):  # noqa: F811
+    """modules/RAGraph.py:265-333 unchanged; scatter_sum, scatter_softmax and SimilarityFunctions swapped inside the module."""
+    reference("RAGraph_edge", argv=["x", "--device", "cpu", "--data_path", "dataset/amazon"])
+    from modules.RAGraph import RAGraph as RefEdge
+    import modules.RAGraph as ref_mod
+    from utils.parse_args import args
+    g = torch.Generator().manual_seed(13)
+    nu, ni, d, E = 40, 30, 16, 400
+    n = nu + ni
+    u = torch.randint(0, nu, (E,), generator=g); i = torch.randint(0, ni, (E,), generator=g) + nu
+    edges = torch.cat([torch.stack([u, i], 1), torch.stack([i, u], 1)], 0)
+    w = torch.rand(edges.shape[0], generator=g)
+    times = torch.randint(0, 500, (edges.shape[0],), generator=g)
+    X = torch.randn(n, d, generator=g)
+    keys, values = torch.randn(n, d, generator=g), torch.randn(n, d, generator=g)
+    fw = types.SimpleNamespace(num_users=nu, num_items=ni, phase="vanilla", use_RAG=True, use_noise=False, use_LoRA=False,
+                               training=False, user_embedding=X[:nu], item_embedding=X[nu:], emb_gate=lambda x: x,
+                               batch_size=32, retrieve_num=10, noise_retrieve_num=1, retrieve_weight=0.3,
+                               resource_keys=keys, resource_values=values)
+    fw._agg = types.MethodType(RefEdge._agg, fw)
+    fw._relative_edge_time_encoding = types.MethodType(RefEdge._relative_edge_time_encoding, fw)
+    with torch.no_grad():
+        wu, wi = RefEdge.forward(fw, edges, w, times)
+    want = torch.cat([wu, wi], 0)
+    ref_mod.scatter_sum = R.scatter_sum
+    ref_mod.scatter_softmax = lambda src, index, dim_size=None: R.scatter_softmax(src, index, dim_size=dim_size)
+    ref_mod.SimilarityFunctions = R.SimilarityFunctions
+    with torch.no_grad():
+        gu, gi = RefEdge.forward(fw, edges, w, times)
+    assert float((torch.cat([gu, gi], 0) - want).abs().max()) < 5e-6
+    # the one-call form of the same forward
+    got = R.edge_rag_forward(X, edges, w, keys, values, args.num_layers, 10, 32, 0.3, edge_times=times)
+    assert float((got - want).abs().max()) < 5e-6
