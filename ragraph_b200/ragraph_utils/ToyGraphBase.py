@@ -28,6 +28,9 @@ class ToyGraphBase:
         assert variant in ("node", "graph", "node_fewshot")
         self.variant = variant
         # inference-phase knobs, same names and defaults as the reference (:22-29)
+        # construct-phase knobs (:17-18; graph variant RAGraph_graph/.../ToyGraphBase.py:20-21): 0 disables
+        self.num_inverse_sample = 0 if variant == "graph" else 10
+        self.num_augment_scale = 0 if variant == "graph" else 3
         self.retrieve_num = num_class + 1 if variant != "graph" else min(3, num_class + 1)
         self.noise_retrieve_num = 1
         self.num_anchors = 10
@@ -111,6 +114,49 @@ class ToyGraphBase:
                 raise RuntimeError("add_graph: node_labels [n, C] needed")
             labels = node_labels
         self.add_entries(keys, values, labels, positions)
+
+    def _build_toy_graph_base(self, features: Tensor, adj: Tensor, labels: Tensor) -> None:
+        """One resource graph -> library rows, the reference's build step end to end (ToyGraphBase.py:91-119; graph variant
+        RAGraph_graph/.../ToyGraphBase.py:97-129): the original graph plus ``num_augment_scale`` random augmentations, each
+        embedded by ``pretrain_model.inference``, optionally reduced to ``num_inverse_sample`` nodes drawn by inverse
+        importance (sub-adjacency taken from the ORIGINAL adjacency, as the reference does), then inserted with
+        ``add_graph``.  ``labels`` = node labels [n, C] (node variants) or the graph label (graph variant).  Random draws
+        are issued in the reference's order, so a seeded build gives the reference's library."""
+        from ..sampling import InverseSampling
+        from .Augmentation import Augmentation
+        from .PositionAwareEncoder import PositionAwareEncoder
+        for aug_features, aug_adj in Augmentation.augment_graph(self.num_augment_scale, features, adj):
+            # few-shot backbones expose the first GCN layer as ``encode`` (RAGraph_node_fewshot/.../ToyGraphBase.py:92)
+            embed = getattr(self.pretrain_model, "encode", None) if self.variant == "node_fewshot" else None
+            embeddings = (embed or self.pretrain_model.inference)(aug_features, aug_adj)
+            if embeddings.dim() == 3 and embeddings.shape[0] == 1:
+                embeddings = embeddings[0]
+            node_labels = None if self.variant == "graph" else labels
+            if self.num_inverse_sample > 0:
+                sample_prob = InverseSampling.compute_sample_prob(aug_adj)
+                sample_mask = torch.multinomial(sample_prob, num_samples=self.num_inverse_sample, replacement=True)
+                sample_adj = adj[sample_mask, :][:, sample_mask]
+                embeddings = embeddings[sample_mask]
+                if node_labels is not None:
+                    node_labels = node_labels[sample_mask]
+            else:
+                sample_adj = aug_adj
+            positions = None
+            if self.variant != "graph":
+                # the reference encodes positions for every node variant (:114) -- one CPU randint per inserted graph; the
+                # codes are stored only where the two-metric score reads them
+                if self._positions is not None:
+                    positions = PositionAwareEncoder.encode_position_aware_code(sample_adj, self.num_anchors, self.dis_q)
+                else:
+                    torch.randint(low=0, high=sample_adj.shape[0], size=(int(self.num_anchors),))   # keeps the RNG stream aligned
+            self.add_graph(embeddings, sample_adj, node_labels=node_labels,
+                           graph_label=labels if self.variant == "graph" else None, positions=positions)
+
+    def build_toy_graph(self, resource_graphs) -> None:
+        """``resource_graphs``: iterable of (features, adj, labels) per resource graph, i.e. what the reference's loop over
+        ``DataLoader(resource_dataset, batch_size=1)`` + ``process_tu_dataset`` produces (:40-45)."""
+        for features, adj, labels in resource_graphs:
+            self._build_toy_graph_base(features, adj, labels)
 
     def _refresh_derived(self, want_bf16: bool, want_tf32: bool = False) -> None:
         n = self._n

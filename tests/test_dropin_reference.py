@@ -271,3 +271,59 @@ def test_edge_forward_with_integration_patches(reference, cpu_ops):  # noqa: F81
     # the one-call form of the same forward
     got = R.edge_rag_forward(X, edges, w, keys, values, args.num_layers, 10, 32, 0.3, edge_times=times)
     assert float((got - want).abs().max()) < 5e-6
+
+
+@pytest.mark.parametrize("variant", ["RAGraph_node", "RAGraph_node_fewshot", "RAGraph_graph"])
+def test_library_build_matches_reference_build(reference, cpu_ops, variant):  # noqa: F811
+    """The reference's own _build_toy_graph_base (augmentation x3 + inverse sampling of 10 nodes in the node variants;
+    plain in the graph variant) and ours, from the same seed, produce the same library."""
+    reference(variant)
+    ref_tgb = sys.modules.get("ragraph_utils.ToyGraphBase") or importlib.import_module("ragraph_utils.ToyGraphBase")
+    import layers.gcn as ref_gcn
+    g = torch.Generator().manual_seed(2025)
+    F_in, d, C = 12, 16, 3
+    torch.manual_seed(3)
+    layer = ref_gcn.GCN(F_in, d, "prelu")
+
+    class PM:
+        def inference(self, features, a):
+            with torch.no_grad():
+                return layer((features, a))
+
+        encode = inference                                    # the few-shot variant calls the first layer `encode`
+
+    graphs = []
+    for n in (14, 9, 21):
+        adj = _sym_norm_adj(n, 0.25, g)
+        feats = torch.rand(n, F_in, generator=g)
+        if variant == "RAGraph_graph":
+            labels = torch.randint(0, C, (1,), generator=g)
+        else:
+            labels = torch.nn.functional.one_hot(torch.randint(0, C, (n,), generator=g), C).float()
+        graphs.append((feats, adj, labels))
+
+    kind = {"RAGraph_node": "node", "RAGraph_node_fewshot": "node_fewshot", "RAGraph_graph": "graph"}[variant]
+    if kind == "node_fewshot":
+        ref = ref_tgb.ToyGraphBase(PM(), C, d, 3, 5)
+    else:
+        ref = ref_tgb.ToyGraphBase(PM(), C, d, 3 if kind == "node" else 1)
+    torch.manual_seed(99)
+    for feats, adj, labels in graphs:
+        ref._build_toy_graph_base(feats, adj, labels)
+
+    mine = R.ToyGraphBase(PM(), C, d, 3 if kind != "graph" else 1, device="cpu", variant=kind, capacity=8,
+                          label_dtype=torch.int64 if kind == "graph" else torch.float32)
+    assert (mine.num_inverse_sample, mine.num_augment_scale) == (ref.num_inverse_sample, ref.num_augment_scale)
+    torch.manual_seed(99)
+    mine.build_toy_graph(graphs)
+
+    assert len(mine) == ref.resource_keys.shape[0]
+    if kind != "graph":
+        assert len(mine) == 3 * (1 + 3) * 10                  # 3 graphs x (1 + 3 augmentations) x 10 sampled nodes
+    finite = torch.isfinite(ref.resource_values).all(dim=1)    # augmented 0/1 adjacencies can have empty rows: 0/0 = NaN
+    assert torch.equal(torch.isfinite(mine.resource_values).all(dim=1), finite)
+    assert float((mine.resource_keys - ref.resource_keys).abs().max()) < 1e-6
+    assert float((mine.resource_values[finite] - ref.resource_values[finite]).abs().max()) < 1e-5
+    assert torch.equal(mine.resource_labels.to(ref.resource_labels.dtype), ref.resource_labels)
+    if kind == "node_fewshot":
+        assert float((mine.resource_positions - ref.resource_positions).abs().max()) < 1e-6
