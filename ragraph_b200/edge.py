@@ -85,11 +85,15 @@ class EdgeAggregator:
 
 
 def make_resource_graph(all_emb: Tensor, edges: Tensor, edge_norm: Tensor, radius: int = 3,
-                        aggregator: Optional[EdgeAggregator] = None):
-    """Deterministic core of ``_make_resource_graph`` (modules/RAGraph.py:185-226 with num_augment_scale = 0 and
-    num_inverse_sample = 0, the finetune-phase settings :45-50): the library is every node, keys = A^radius X0 (the last
-    propagation layer), values = sum of the even layers X0 + A^2 X0 + ... (``res_emb[0::2]``).  Each layer is one SpMM over
-    the CSR built once from (edges, edge_norm); no [E, d] temporaries.  Returns (resource_keys, resource_values)."""
+                        aggregator: Optional[EdgeAggregator] = None, num_augment_scale: int = 0,
+                        num_inverse_sample: int = 0, adj=None):
+    """``_make_resource_graph`` (modules/RAGraph.py:185-226): keys = A^radius X0 (the last propagation layer), values =
+    sum of the even layers X0 + A^2 X0 + ... (``res_emb[0::2]``); each layer is one SpMM over the CSR built once from
+    (edges, edge_norm), no [E, d] temporaries.  With both knobs at 0 (the finetune-phase settings, :45-50) the library is
+    every node.  ``num_augment_scale`` adds that many noisy copies (Augmentation.augment_features on keys and values) and
+    ``num_inverse_sample`` keeps that many rows per copy, drawn by inverse importance of ``adj`` (the vanilla-phase
+    settings, :38-43); both use the reference's draw order, so a seeded call gives the reference's library.
+    Returns (resource_keys, resource_values)."""
     agg = aggregator or EdgeAggregator(all_emb.shape[0])
     g = agg.csr(edges, edge_norm)
     layer, values = all_emb, all_emb
@@ -98,7 +102,22 @@ def make_resource_graph(all_emb: Tensor, edges: Tensor, edge_norm: Tensor, radiu
             layer = g.spmm(layer)
             if l % 2 == 0:
                 values = values + layer
-    return layer, values
+    if num_augment_scale == 0 and num_inverse_sample == 0:
+        return layer, values
+    from .ragraph_utils.Augmentation import Augmentation
+    from .sampling import InverseSampling
+    # adj[i, j] of the reference is the weight of edge (i, j) = edges row (i, j): the CSR above is grouped by edges[:, 1],
+    # i.e. it is adj^T -- the importance scores need adj itself
+    sample_prob = InverseSampling.compute_sample_prob(adj if adj is not None else g.transpose())
+    keys_out, values_out = [], []
+    for i in range(1 + int(num_augment_scale)):
+        k_i, v_i = (layer, values) if i == 0 else (Augmentation.augment_features(layer, sample_prob),
+                                                   Augmentation.augment_features(values, sample_prob))
+        if num_inverse_sample > 0:
+            sample_mask = torch.multinomial(sample_prob, num_samples=int(num_inverse_sample), replacement=True)
+            k_i, v_i = k_i[sample_mask], v_i[sample_mask]
+        keys_out.append(k_i); values_out.append(v_i)
+    return torch.cat(keys_out, dim=0), torch.cat(values_out, dim=0)
 
 
 def _agg(all_emb: Tensor, edges: Tensor, edge_norm: Tensor, num_nodes: int) -> Tensor:

@@ -327,3 +327,37 @@ def test_library_build_matches_reference_build(reference, cpu_ops, variant):  # 
     assert torch.equal(mine.resource_labels.to(ref.resource_labels.dtype), ref.resource_labels)
     if kind == "node_fewshot":
         assert float((mine.resource_positions - ref.resource_positions).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("scale,n_sample", [(0, 0), (0, 7), (1, 7)])
+def test_edge_resource_graph_matches_reference_build(reference, cpu_ops, scale, n_sample):  # noqa: F811
+    """modules/RAGraph.py:185-226 unchanged (finetune-phase and vanilla-phase knob settings) vs make_resource_graph."""
+    reference("RAGraph_edge", argv=["x", "--device", "cpu", "--data_path", "dataset/amazon"])
+    from modules.RAGraph import RAGraph as RefEdge
+    from utils.parse_args import args
+    g = torch.Generator().manual_seed(404)
+    nu, ni, d, E = 35, 25, 16, 300
+    n = nu + ni
+    u = torch.randint(0, nu, (E,), generator=g); i = torch.randint(0, ni, (E,), generator=g) + nu
+    adj_sp = torch.sparse_coo_tensor(torch.cat([torch.stack([u, i]), torch.stack([i, u])], 1),
+                                     torch.rand(2 * E, generator=g), (n, n)).coalesce()
+    X = torch.randn(n, d, generator=g)
+    shim = types.SimpleNamespace(num_users=nu, num_items=ni, adj=adj_sp, edges=adj_sp._indices().t(),
+                                 edge_norm=adj_sp._values(), resource_graph_radius=args.num_layers,
+                                 num_augment_scale=scale, num_inverse_sample=n_sample, resource_keys=None, resource_values=None)
+    shim._agg = types.MethodType(RefEdge._agg, shim)
+    pre = types.SimpleNamespace(generate=lambda: (X[:nu], X[nu:]))
+    with torch.no_grad():
+        torch.manual_seed(55)
+        RefEdge._make_resource_graph(shim, pre)
+        torch.manual_seed(55)
+        keys, values = R.make_resource_graph(X, shim.edges, shim.edge_norm, args.num_layers, num_augment_scale=scale,
+                                             num_inverse_sample=n_sample, adj=adj_sp)
+    assert keys.shape == shim.resource_keys.shape and values.shape == shim.resource_values.shape
+    assert float((keys - shim.resource_keys).abs().max()) < 5e-6
+    assert float((values - shim.resource_values).abs().max()) < 5e-6
+    if scale or n_sample:                                     # adj omitted: the importance scores come from the transposed CSR
+        torch.manual_seed(55)
+        k2, v2 = R.make_resource_graph(X, shim.edges, shim.edge_norm, args.num_layers, num_augment_scale=scale,
+                                       num_inverse_sample=n_sample)
+        assert float((k2 - shim.resource_keys).abs().max()) < 5e-6 and float((v2 - shim.resource_values).abs().max()) < 5e-6
