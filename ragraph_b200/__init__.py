@@ -14,10 +14,10 @@ from .RAGraph import RAGraph, RAGraphFewShot
 from .sampling import InverseSampling
 from . import downprompt
 from .sharded import ShardedRetriever, owner_of, shard_bounds
-from .utility import normalized_adjacency_csr, process_graph_batch
+from .utility import normalized_adjacency_csr, process_graph_batch, process_tu_dataset
 
 __all__ = ["_lib", "ops", "CSRGraph", "as_csr", "EdgeAggregator", "edge_rag_forward", "rating_topk", "scatter_add", "scatter_sum",
            "GCN", "Propagation", "SimilarityFunctions", "TaskDecoder", "ToyGraphBase", "RAGraph", "RAGraphFewShot", "downprompt",
            "relative_edge_time_encoding", "scatter_softmax", "make_resource_graph", "InverseSampling",
-           "ShardedRetriever", "owner_of", "shard_bounds", "normalized_adjacency_csr", "process_graph_batch"]
+           "ShardedRetriever", "owner_of", "shard_bounds", "normalized_adjacency_csr", "process_graph_batch", "process_tu_dataset"]
 __version__ = "0.1.0"

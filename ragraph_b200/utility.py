@@ -55,3 +55,20 @@ def process_graph_batch(xs: Sequence[Tensor], edge_indices: Sequence[Tensor], nu
     features = x_all[:, :num_node_attributes].float().contiguous()
     node_labels = x_all[:, num_node_attributes:].float().contiguous()
     return features, normalized_adjacency_csr(ei.to(x_all.device), total), node_labels
+
+
+def process_tu_dataset(data, num_node_attributes: int, device: Optional[torch.device] = None
+                       ) -> Tuple[Tensor, CSRGraph, Tensor]:
+    """Signature of the reference's ``process_tu_dataset(data, num_node_attributes)`` (RAGraph_node/ragraph_utils/
+    utility.py:30-72) over ``process_graph_batch``: ``data`` is a torch_geometric ``Batch`` (or anything exposing
+    ``num_graphs`` and ``data[g].x`` / ``data[g].edge_index`` per graph).  Returns (features, adjacency, node_labels) like
+    the reference, except that the adjacency is the CSR handle every consumer here accepts in place of the dense [n,n]
+    tensor, and nothing goes through numpy / scipy.  ``device`` defaults to the current CUDA device when there is one
+    (the reference hard-codes ``.cuda()``), else to where ``data`` lives."""
+    xs = [data[g].x for g in range(data.num_graphs)]
+    eis = [data[g].edge_index for g in range(data.num_graphs)]
+    if device is None and torch.cuda.is_available():
+        device = torch.device("cuda", torch.cuda.current_device())
+    if device is not None:
+        xs, eis = [x.to(device) for x in xs], [e.to(device) for e in eis]
+    return process_graph_batch(xs, eis, num_node_attributes)

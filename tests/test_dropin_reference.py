@@ -361,3 +361,41 @@ def test_edge_resource_graph_matches_reference_build(reference, cpu_ops, scale, 
         k2, v2 = R.make_resource_graph(X, shim.edges, shim.edge_norm, args.num_layers, num_augment_scale=scale,
                                        num_inverse_sample=n_sample)
         assert float((k2 - shim.resource_keys).abs().max()) < 5e-6 and float((v2 - shim.resource_values).abs().max()) < 5e-6
+
+
+def test_process_tu_dataset_signature_and_result(reference, cpu_ops):  # noqa: F811
+    """The reference's process_tu_dataset on a duck-typed Batch vs ours with the same call: features / labels identical,
+    the CSR adjacency densifies to the reference's dense block-diagonal matrix."""
+    reference("RAGraph_node")
+    util = importlib.import_module("ragraph_utils.utility")
+    g = torch.Generator().manual_seed(66)
+
+    class Graph:
+        def __init__(self, n, E):
+            self.x = torch.rand(n, 9, generator=g)
+            self.edge_index = torch.randint(0, n, (2, E), generator=g)
+
+    class Batch(list):
+        @property
+        def num_graphs(self):
+            return len(self)
+
+        @property
+        def num_features(self):
+            return self[0].x.shape[1]
+
+    data = Batch([Graph(6, 10), Graph(1, 0), Graph(11, 30)])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                       # np.row_stack deprecation inside the reference
+        rf, radj, rl = util.process_tu_dataset(data, 6)
+    feats, csr, labs = R.process_tu_dataset(data, 6, device=torch.device("cpu"))
+    assert torch.equal(feats, rf) and torch.equal(labs, rl)
+    dense = torch.zeros(csr.n_rows, csr.n_cols)
+    dense[csr.row_ids(), csr.col.long()] = csr.val
+    assert float((dense - radj).abs().max()) <= 1e-7 and torch.equal(dense != 0, radj != 0)
+    # and the CSR is accepted where the reference passes the dense matrix
+    x = torch.randn(csr.n_rows, 8, generator=g)
+    a = R.Propagation.aggregate_k_hop_features(csr, x, 2)
+    b = O.aggregate_k_hop_features(radj, x, 2)
+    assert float((a - b).abs().max()) < 1e-5
