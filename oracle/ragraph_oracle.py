@@ -404,6 +404,20 @@ def sample_prob(adj: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------
+# few-shot helpers around the few-shot forward (RAGraph_node_fewshot/ragraph_utils/utility.py:75-162)
+# ----------------------------------------------------------------------------------------
+def fewshot_mean(fewshot_logits: torch.Tensor, fewshot_labels: torch.Tensor):
+    """utility.py:75-92: mean logits per unique label (sorted), one boolean mask per label."""
+    unique_labels = fewshot_labels.unique()
+    return torch.stack([fewshot_logits[fewshot_labels == label].mean(dim=0) for label in unique_labels]), unique_labels
+
+
+def fewshot_predict_logits(mean_fewshot_logits: torch.Tensor, logits: torch.Tensor) -> torch.Tensor:
+    """utility.py:129-134: broadcast cosine similarity [n, C]."""
+    return F.cosine_similarity(logits.unsqueeze(1), mean_fewshot_logits.unsqueeze(0), dim=-1)
+
+
+# ----------------------------------------------------------------------------------------
 # multi-GPU restatement (new functionality, C1): merge of per-shard candidates
 # ----------------------------------------------------------------------------------------
 def rating_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, hist_rowptr, hist_items, k: int):

@@ -399,3 +399,40 @@ def test_process_tu_dataset_signature_and_result(reference, cpu_ops):  # noqa: F
     a = R.Propagation.aggregate_k_hop_features(csr, x, 2)
     b = O.aggregate_k_hop_features(radj, x, 2)
     assert float((a - b).abs().max()) < 1e-5
+
+
+def test_fewshot_helpers_match_reference(reference, cpu_ops):  # noqa: F811
+    """RAGraph_node_fewshot/ragraph_utils/utility.py:75-162 vs ragraph_b200.fewshot, same calls."""
+    reference("RAGraph_node_fewshot")
+    util = importlib.import_module("ragraph_utils.utility")
+    F = R.fewshot
+    g = torch.Generator().manual_seed(123)
+    C, L_, n_support, n = 3, 12, 15, 40
+    support_logits = torch.randn(n_support, L_, generator=g)
+    support_labels = torch.arange(n_support) % C
+    support_labels = support_labels[torch.randperm(n_support, generator=g)]
+    logits = torch.randn(n, L_, generator=g)
+    logits[3] = 0.0
+    gold = torch.randint(0, C, (n,), generator=g)
+    rm, ru = util.fewshot_mean(support_logits, support_labels)
+    om, ou = F.fewshot_mean(support_logits, support_labels)
+    assert torch.equal(ou, ru) and float((om - rm).abs().max()) < 1e-6
+    assert float((F.fewshot_mean_logits(support_logits, support_labels) - util.fewshot_mean_logits(support_logits, support_labels)).abs().max()) < 1e-6
+    rmap = util.fewshot_logits_map(support_logits, support_labels); omap = F.fewshot_logits_map(support_logits, support_labels)
+    assert sorted(rmap) == sorted(omap) and all(float((omap[k] - rmap[k]).abs().max()) < 1e-6 for k in rmap)
+    sim_r = util.fewshot_predict_logits(rm, logits); sim_o = F.fewshot_predict_logits(om, logits)
+    assert sim_o.shape == sim_r.shape and float((sim_o - sim_r).abs().max()) < 2e-6
+    assert torch.equal(F.fewshot_predict_labels_by_mean(om, logits)[4:], util.fewshot_predict_labels_by_mean(rm, logits)[4:])
+    assert torch.equal(F.fewshot_predict_labels(support_logits, support_labels, logits)[4:],
+                       util.fewshot_predict_labels(support_logits, support_labels, logits)[4:])
+    lo = F.fewshot_predict_loss(support_logits, support_labels, logits, gold)
+    lr = util.fewshot_predict_loss(support_logits, support_labels, logits, gold)
+    assert abs(float(lo) - float(lr)) < 1e-6
+    # non-contiguous label ids (e.g. {1, 4}): means follow the sorted unique labels; the 0..C-1 table refuses them
+    odd = torch.tensor([4, 1, 4, 1, 1])
+    om2, ou2 = F.fewshot_mean(support_logits[:5], odd); rm2, ru2 = util.fewshot_mean(support_logits[:5], odd)
+    assert torch.equal(ou2, ru2) and float((om2 - rm2).abs().max()) < 1e-6
+    with pytest.raises(KeyError):
+        F.fewshot_mean_logits(support_logits[:5], odd)
+    with pytest.raises(KeyError):
+        util.fewshot_mean_logits(support_logits[:5], odd)

@@ -27,3 +27,8 @@ def test_fewshot_forward_body_runs_on_cpu(graph_level, golden, cpu_ops, monkeypa
 def test_ragged_readout_body_runs_on_cpu(cpu_ops, monkeypatch):  # noqa: F811
     monkeypatch.setattr(G, "DEV", "cpu")
     G.test_split_and_batchify_ragged()
+
+
+def test_fewshot_helpers_body_runs_on_cpu(cpu_ops, monkeypatch):  # noqa: F811
+    monkeypatch.setattr(G, "DEV", "cpu")
+    G.test_fewshot_helpers_vs_oracle()

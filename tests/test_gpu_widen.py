@@ -284,3 +284,26 @@ def test_inverse_sampling_golden(golden):
     n = int(g["sparse_n"])
     adj_sp = torch.sparse_coo_tensor(cu(g["sparse_indices"]), cu(g["sparse_values"]), (n, n)).coalesce()
     assert O.rel_err(IS.compute_sample_prob(adj_sp).cpu(), g["sample_prob_sparse"]) < tol
+
+
+# ------------------------------------------------------------------------------------------ few-shot helpers
+def test_fewshot_helpers_vs_oracle():
+    g = torch.Generator().manual_seed(123)
+    C, Ld, n_support, n = 3, 12, 15, 300
+    support_logits = torch.randn(n_support, Ld, generator=g)
+    support_labels = (torch.arange(n_support) % C)[torch.randperm(n_support, generator=g)]
+    logits = torch.randn(n, Ld, generator=g)
+    F_ = R.fewshot
+    means, uniq = F_.fewshot_mean(cu(support_logits), cu(support_labels))
+    ref_means, ref_uniq = O.fewshot_mean(support_logits, support_labels)
+    assert torch.equal(uniq.cpu(), ref_uniq) and O.rel_err(means.cpu(), ref_means) < REL
+    table = F_.fewshot_mean_logits(cu(support_logits), cu(support_labels))
+    sim = F_.fewshot_predict_logits(table, cu(logits)).cpu()
+    ref_sim = O.fewshot_predict_logits(ref_means, logits)
+    assert float((sim - ref_sim).abs().max()) < 2e-6
+    pred = F_.fewshot_predict_labels_by_mean(table, cu(logits)).cpu()
+    margin = ref_sim.topk(2, dim=1).values
+    clear = (margin[:, 0] - margin[:, 1]) > 1e-5                # rows whose best class is not a near tie
+    assert torch.equal(pred[clear], ref_sim.argmax(1)[clear])
+    loss = F_.fewshot_predict_loss(cu(support_logits), cu(support_labels), cu(logits), cu(torch.randint(0, C, (n,), generator=g)))
+    assert bool(torch.isfinite(loss))
