@@ -320,17 +320,19 @@ def main():
     loc = (idx[:chk] - lo).clamp(0, hi - lo - 1)
     kk = store.resource_keys[loc.reshape(-1)].double().reshape(chk, TOPK, DIM)
     ex = (torch.nn.functional.normalize(q_dev[:chk].double(), dim=-1)[:, None] * torch.nn.functional.normalize(kk, dim=-1)).sum(-1)
-    tol = 1e-5 if mode != L.SIM_BF16 else 1e-2
+    tol = 1e-5 if mode not in (L.SIM_BF16, L.SIM_F16) else 1e-2
     assert float(((scores[:chk].double() - ex).abs() * mine).max()) < tol, "returned scores disagree with exact re-score"
     assert bool(torch.equal(emb[:chk][mine], store.resource_values[loc[mine]])), "gather not bit exact"
 
     flops = 2.0 * Q_BATCH * (hi - lo) * DIM
     tf_ach = flops / (kern_ms * 1e-3) / 1e12
     roof = {"bound": "tensor", "achieved": tf_ach, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": tf_ach / peaks["bf16"],
-            "traffic": _ncu_traffic(f"cosine_topk_ts_kernel:N={hi - lo}:d={DIM}:Q={Q_BATCH}") if mode in (2, 3) else None,
+            "traffic": _ncu_traffic(f"cosine_topk_ts_kernel:N={hi - lo}:d={DIM}:Q={Q_BATCH}") if mode in (2, 3, 4, 5) else None,
             "kernel": {0: "cosine_topk_f32_kernel (CUDA-core fp32)",
                        2: "cosine_topk_ts_kernel (tcgen05 bf16, query tile stationary in TMEM) + threshold pre-pass",
-                       3: "cosine_topk_ts_kernel (tcgen05 bf16, query tile stationary in TMEM) + threshold pre-pass + fp32 refine"
+                       3: "cosine_topk_ts_kernel (tcgen05 bf16, query tile stationary in TMEM) + threshold pre-pass + fp32 refine",
+                       4: "cosine_topk_ts_kernel (tcgen05 fp16, query tile stationary in TMEM) + threshold pre-pass",
+                       5: "cosine_topk_ts_kernel (tcgen05 fp16, query tile stationary in TMEM) + threshold pre-pass + fp32 refine"
                        }.get(mode, str(mode)),
             "kernel_ms": kern_ms, "peak_source": peaks["src"] + " bf16 burst (cuBLAS 8192^3)",
             "peak_sustained": peaks["bf16_sustained"], "frac_of_sustained": tf_ach / peaks["bf16_sustained"],
@@ -338,7 +340,8 @@ def main():
 
     line = {"metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": {0: "f32", 2: "bf16", 3: "bf16 filter + f32 refine (exact)"}.get(mode, "f32"),
+            "vs_baseline": None, "dtype": {0: "f32", 2: "bf16", 3: "bf16 filter + f32 refine (exact)", 4: "f16",
+                                         5: "f16 filter + f32 refine (exact)"}.get(mode, "f32"),
             "data": "synthetic",
             "config": {"workload": f"top-{TOPK} cosine retrieve + value/label gather, {N_KEYS} keys d={DIM} sharded by key rows over "
                                    f"{world} GPU(s), {Q_BATCH}-query batches", "mode": mode,

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RAG_ABI_VERSION 1
+#define RAG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RAG_API __attribute__((visibility("default")))
@@ -54,9 +54,18 @@ enum rag_sim_mode {
   RAG_SIM_TF32 = 1,       /* tcgen05 tf32 x tf32 -> fp32 in TMEM, raw approximate scores (|err| <= 2^-10 for unit
                              vectors); d <= 64 with k <= 26, d <= 128 with k <= 10 */
   RAG_SIM_BF16 = 2,       /* tcgen05 bf16 x bf16 -> fp32 in TMEM, raw approximate scores */
-  RAG_SIM_BF16_REFINE = 3 /* bf16 tensor-core filter + fp32 re-score + certificate; results
-                             equal RAG_SIM_FP32 (uncertified rows are recomputed in fp32) */
+  RAG_SIM_BF16_REFINE = 3, /* bf16 tensor-core filter + fp32 re-score + certificate; results
+                              equal RAG_SIM_FP32 (see RAG_SIM_F16_REFINE) */
+  RAG_SIM_F16 = 4,         /* tcgen05 fp16 x fp16 -> fp32 in TMEM, raw approximate scores (8x tighter than bf16:
+                              unit vectors need no exponent range) */
+  RAG_SIM_F16_REFINE = 5   /* fp16 tensor-core filter + fp32 re-score + certificate; results equal RAG_SIM_FP32.
+                              Rows the first pass cannot certify (more near-ties than its candidate lists hold:
+                              clustered / duplicated libraries) take a SECOND tensor-core pass that collects every key
+                              above (exact k-th score - error bound); only rows that overflow that too fall back to
+                              the fp32 kernel.  The library's default exact mode. */
 };
+/* element formats of the 16-bit key shadow (rag_rows_to_shadow16) */
+enum rag_shadow_fmt { RAG_FMT_BF16 = 0, RAG_FMT_F16 = 1 };
 /* flags */
 #define RAG_SIM_DOT 1u /* skip L2 normalisation: plain dot product (edge eval top-k,
                           RAGraph_edge/utils/metrics.py:102-117) */
@@ -94,6 +103,14 @@ RAG_API int rag_rows_normalize_f32(const float* x, int64_t rows, int32_t d, floa
 RAG_API int rag_rows_to_bf16(const float* x, int64_t rows, int32_t d, int32_t normalize, float eps,
                      uint16_t* out, int32_t d_pad, rag_stream_t stream);
 
+/* 16-bit shadow (fmt = RAG_FMT_BF16 | RAG_FMT_F16) with the rounding-error norms the exactness certificate of the
+ * *_REFINE modes uses: err_rows[r] (nullable) = || rn16(xhat_r) - xhat_r ||_2 and *err_max (nullable, DEVICE float the
+ * caller zero-initialises; updated with atomicMax so a library can be converted in pieces) = the largest of them.
+ * By Cauchy-Schwarz |s_16 - s| <= err_query + err_key for unit vectors -- a proven bound about half the element-wise
+ * worst case.  fp16 subnormals are flushed to zero before the error is measured. */
+RAG_API int rag_rows_to_shadow16(const float* x, int64_t rows, int32_t d, int32_t fmt, int32_t normalize, float eps,
+                         uint16_t* out, int32_t d_pad, float* err_rows, float* err_max, rag_stream_t stream);
+
 /* tf32 shadow of the key matrix for RAG_SIM_TF32: out[r, 0:d] = tf32_rn(x[r,:] * (normalize ? 1/max(||x[r]||,eps) : 1))
  * stored as fp32 words (low 13 mantissa bits zero), columns d..d_pad-1 zero filled; d_pad = rag_tf32_shadow_dpad(d)
  * (32, 64 or 128; 0 if d > 128), out is [rows, d_pad] fp32, 16-byte aligned. */
@@ -113,16 +130,27 @@ RAG_API int rag_cosine_similarity_f32(const float* q, int64_t Q, const float* ke
 /* Replaces calculate_cosine_similarity + torch.topk(largest, sorted)
  * (ToyGraphBase.py:53,67; RAGraph_edge/modules/RAGraph.py:303,311).
  *   q[Q,d], keys[N,d] fp32.  key_inv_norm[N] nullable (computed into workspace if null and
- *   cosine).  keys_shadow nullable: REQUIRED for the tensor-core modes -- the bf16 shadow [N, round_up(d,64)] made
- *   by rag_rows_to_bf16 for the BF16 modes, the tf32 shadow [N, rag_tf32_shadow_dpad(d)] fp32 made by
- *   rag_rows_to_tf32 for RAG_SIM_TF32 (both L2-normalised).
+ *   cosine).  keys_shadow nullable: REQUIRED for the tensor-core modes -- the 16-bit shadow [N, round_up(d,64)] made
+ *   by rag_rows_to_shadow16 (bf16 for the BF16 modes, fp16 for the F16 modes), the tf32 shadow
+ *   [N, rag_tf32_shadow_dpad(d)] fp32 made by rag_rows_to_tf32 for RAG_SIM_TF32 (all L2-normalised).
+ *   shadow_err nullable: DEVICE float = err_max of rag_rows_to_shadow16 for this shadow; the *_REFINE certificate
+ *   then uses the measured bound, else the element-wise worst case (2^-8 bf16, 2^-11 fp16 per operand).
  *   out_scores[Q,k] fp32 descending; out_idx[Q,k] int64 = idx_offset + local row; order is
  *   deterministic: score desc, index asc.  Requires 1 <= k <= min(N, RAG_MAX_K). */
 RAG_API size_t rag_cosine_topk_workspace(int64_t Q, int64_t N, int32_t d, int32_t k, int32_t mode);
 RAG_API int rag_cosine_topk_f32(const float* q, int64_t Q, const float* keys, const float* key_inv_norm,
-                        const void* keys_shadow, int64_t N, int32_t d, int32_t k, int32_t mode,
-                        uint32_t flags, int64_t idx_offset, float* out_scores, int64_t* out_idx,
+                        const void* keys_shadow, const float* shadow_err, int64_t N, int32_t d, int32_t k,
+                        int32_t mode, uint32_t flags, int64_t idx_offset, float* out_scores, int64_t* out_idx,
                         void* workspace, size_t workspace_bytes, rag_stream_t stream);
+/* Byte offsets, inside the caller's workspace of the same (Q, N, d, k, mode), of two int32 counters the *_REFINE
+ * modes leave behind: offsets_out[0] = rows that needed the second tensor-core pass, offsets_out[1] = rows that fell
+ * back to the fp32 kernel.  Valid after the call's work has finished on the stream; 0/0 for other modes. */
+RAG_API int rag_cosine_topk_stat_offsets(int64_t Q, int64_t N, int32_t d, int32_t k, int32_t mode, size_t* offsets_out);
+/* Process-wide tuning / test hooks of the tensor-core path, read from the environment ONCE at load (RAG_TC_VARIANT,
+ * RAG_TC_PREPASS, RAG_TC_PREPASS_MIN_TILES, RAG_TC_PREPASS_DIV, RAG_TC_KP) and settable here: name without the RAG_TC_
+ * prefix in lower case ("variant": 0 auto / 1 ss / 2 ts; "prepass": 0/1; "prepass_min_tiles"; "prepass_div"; "kp": 0 auto /
+ * 16 / 32; "pass2": 0/1).  value < 0 restores the default.  Returns RAG_EINVAL for an unknown name. */
+RAG_API int rag_tc_set_option(const char* name, int32_t value);
 
 /* Top-k with per-query exclusion lists, fp32 path: query row r never returns the key indices
  * mask_col[mask_rowptr[r] .. mask_rowptr[r+1]) (global indices, i.e. including idx_offset; any order).  With

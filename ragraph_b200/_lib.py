@@ -13,8 +13,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libragraph_b200.so")
 
 RAG_OK = 0
+ABI_VERSION = 2
 RAG_MAX_K = 128
-SIM_FP32, SIM_TF32, SIM_BF16, SIM_BF16_REFINE = 0, 1, 2, 3
+SIM_FP32, SIM_TF32, SIM_BF16, SIM_BF16_REFINE, SIM_F16, SIM_F16_REFINE = 0, 1, 2, 3, 4, 5
+FMT_BF16, FMT_F16 = 0, 1
 SIM_DOT = 1
 EPI_ROWNORM, EPI_BIAS, EPI_RELU, EPI_PRELU, EPI_BLEND, EPI_ACCUM = 1, 2, 4, 8, 16, 32
 REDUCE_SUM, REDUCE_MEAN = 0, 1
@@ -33,12 +35,15 @@ SIGNATURES = {
     "rag_row_inv_norm_f32": (C.c_int, [_p, _i64, _i32, _f32, _p, _p]),
     "rag_rows_normalize_f32": (C.c_int, [_p, _i64, _i32, _f32, _p, _p]),
     "rag_rows_to_bf16": (C.c_int, [_p, _i64, _i32, _i32, _f32, _p, _i32, _p]),
+    "rag_rows_to_shadow16": (C.c_int, [_p, _i64, _i32, _i32, _i32, _f32, _p, _i32, _p, _p, _p]),
     "rag_tf32_shadow_dpad": (_i32, [_i32]),
     "rag_rows_to_tf32": (C.c_int, [_p, _i64, _i32, _i32, _f32, _p, _i32, _p]),
     "rag_cosine_similarity_workspace": (_sz, [_i64, _i64]),
     "rag_cosine_similarity_f32": (C.c_int, [_p, _i64, _p, _i64, _i32, _u32, _p, _p, _sz, _p]),
     "rag_cosine_topk_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),
-    "rag_cosine_topk_f32": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _i64, _p, _p, _p, _sz, _p]),
+    "rag_cosine_topk_f32": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _i64, _p, _p, _p, _sz, _p]),
+    "rag_cosine_topk_stat_offsets": (C.c_int, [_i64, _i64, _i32, _i32, _i32, _p]),
+    "rag_tc_set_option": (C.c_int, [C.c_char_p, _i32]),
     "rag_topk_masked_f32": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _u32, _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "rag_cosine2_topk_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "rag_cosine2_topk_f32": (C.c_int, [_p, _p, _i32, _f32, _p, _p, _i32, _f32, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
@@ -82,8 +87,8 @@ def load() -> C.CDLL:
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
                 fn.restype, fn.argtypes = res, args
-            if lib.rag_abi_version() != 1:
-                raise RuntimeError(f"ragraph_b200: ABI version {lib.rag_abi_version()} != 1")
+            if lib.rag_abi_version() != ABI_VERSION:
+                raise RuntimeError(f"ragraph_b200: ABI version {lib.rag_abi_version()} != {ABI_VERSION}")
             _lib = lib
     return _lib
 
@@ -92,6 +97,11 @@ def check(status: int, what: str) -> None:
     if status != RAG_OK:
         lib = load()
         raise RagError(f"{what}: {lib.rag_status_string(status).decode()}: {lib.rag_last_error().decode()}")
+
+
+def tc_set_option(name: str, value: int) -> None:
+    """process-wide tuning / test hook of the tensor-core retrieval path (see rag_tc_set_option); value < 0 = default"""
+    check(load().rag_tc_set_option(name.encode(), int(value)), "tc_set_option")
 
 
 def launch_count() -> int:

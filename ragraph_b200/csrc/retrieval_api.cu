@@ -13,8 +13,9 @@ bool topk_tc_available(int d, int k);
 bool topk_tc_tf32_available(int d, int k);
 int topk_tc_tf32_dpad(int d);
 int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const void* keys_shadow,
-                int64_t N, int d, int k, int mode, uint32_t flags, int64_t idx_offset, float* out_scores,
-                int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s);
+                const float* shadow_err, int64_t N, int d, int k, int mode, uint32_t flags, int64_t idx_offset,
+                float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s);
+void topk_tc_stat_offsets(int64_t Q, int64_t N, int d, int k, int mode, size_t* out);
 
 // out[r, :] = [ wa * xa[r]/max(|xa[r]|,eps)  (padded to da4) | wb * xb[r]/max(|xb[r]|,eps) (padded to db4) ]
 __global__ void __launch_bounds__(256) concat_normalized_kernel(const float* __restrict__ xa, int da, float wa,
@@ -52,7 +53,8 @@ static int check_topk_args(const char* fn, const float* q, int64_t Q, const floa
 
 extern "C" int rag_sim_mode_supported(int32_t mode, int32_t d, int32_t k) {
   if (mode == RAG_SIM_FP32) return (d >= 1 && k >= 1 && k <= RAG_MAX_K) ? 1 : 0;
-  if (mode == RAG_SIM_BF16 || mode == RAG_SIM_BF16_REFINE) return rag::topk_tc_available(d, k) ? 1 : 0;
+  if (mode == RAG_SIM_BF16 || mode == RAG_SIM_BF16_REFINE || mode == RAG_SIM_F16 || mode == RAG_SIM_F16_REFINE)
+    return rag::topk_tc_available(d, k) ? 1 : 0;
   if (mode == RAG_SIM_TF32) return rag::topk_tc_tf32_available(d, k) ? 1 : 0;
   return 0;
 }
@@ -66,9 +68,15 @@ extern "C" size_t rag_cosine_topk_workspace(int64_t Q, int64_t N, int32_t d, int
   return rag::topk_tc_workspace(Q, N, d, k, mode);
 }
 
+extern "C" int rag_cosine_topk_stat_offsets(int64_t Q, int64_t N, int32_t d, int32_t k, int32_t mode, size_t* offsets_out) {
+  RAG_REQUIRE(offsets_out, RAG_EINVAL, "cosine_topk_stat_offsets: null pointer");
+  rag::topk_tc_stat_offsets(Q, N, d, k, mode, offsets_out);
+  return RAG_OK;
+}
+
 extern "C" int rag_cosine_topk_f32(const float* q, int64_t Q, const float* keys, const float* key_inv_norm,
-                                   const void* keys_shadow, int64_t N, int32_t d, int32_t k, int32_t mode,
-                                   uint32_t flags, int64_t idx_offset, float* out_scores, int64_t* out_idx,
+                                   const void* keys_shadow, const float* shadow_err, int64_t N, int32_t d, int32_t k,
+                                   int32_t mode, uint32_t flags, int64_t idx_offset, float* out_scores, int64_t* out_idx,
                                    void* workspace, size_t workspace_bytes, rag_stream_t stream) {
   int st = check_topk_args("cosine_topk", q, Q, keys, N, d, k, out_scores, out_idx);
   if (st || Q == 0) return st;
@@ -80,9 +88,11 @@ extern "C" int rag_cosine_topk_f32(const float* q, int64_t Q, const float* keys,
     case RAG_SIM_TF32:
     case RAG_SIM_BF16:
     case RAG_SIM_BF16_REFINE:
-      RAG_REQUIRE(keys_shadow, RAG_EINVAL, "cosine_topk: mode %d needs the key shadow (rag_rows_to_bf16 / rag_rows_to_tf32)", mode);
-      return rag::topk_tc_run(q, Q, keys, key_inv_norm, keys_shadow, N, d, k, mode, flags, idx_offset, out_scores,
-                              out_idx, workspace, workspace_bytes, s);
+    case RAG_SIM_F16:
+    case RAG_SIM_F16_REFINE:
+      RAG_REQUIRE(keys_shadow, RAG_EINVAL, "cosine_topk: mode %d needs the key shadow (rag_rows_to_shadow16 / rag_rows_to_tf32)", mode);
+      return rag::topk_tc_run(q, Q, keys, key_inv_norm, keys_shadow, shadow_err, N, d, k, mode, flags, idx_offset,
+                              out_scores, out_idx, workspace, workspace_bytes, s);
     default:
       return rag::fail(RAG_EINVAL, "cosine_topk: unknown mode %d", mode);
   }

@@ -26,8 +26,10 @@
 // certifies the row iff its k-th exact score > max_split t_split + EPS.  Uncertified rows (ties or dense
 // clusters at the boundary) are recomputed by the fp32 kernel, so results always equal RAG_SIM_FP32.
 #include <cuda.h>
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
+#include <cstring>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -46,7 +48,15 @@ constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;     // SS kernel: 8 epilogue warps + TMA + MMA
 constexpr int TS_THREADS = (TC_EPI_WARPS + 3) * 32;     // TS kernel: 8 epilogue warps + TMA + 2 MMA issuers
 constexpr int TC_PQ = 4;               // per-row pending-candidate queue depth (drained after the TMEM hand-back)
-constexpr float TC_EPS = 0.00390625f + 0.0009765625f;   // 2^-8 (bf16 x bf16, unit vectors) + 2^-10 slack (fp32 sums)
+// Score error bound of the 16-bit filter, per query row: eps_row = err_q[row] + err_k + TC_SLACK, where err_q / err_k are
+// the MEASURED rounding-error norms of the operand images (rows_to_16_kernel; Cauchy-Schwarz) or, without them, the
+// element-wise worst case u per operand (u = 2^-8 bf16, 2^-11 fp16).  TC_SLACK covers what the norms do not: the fp32
+// accumulation inside the tensor core (<= d products of magnitude <= 1, truncating adds: < 2^-16 for d <= 256), the
+// (1 + 2^-7) factor of ||kh||, and the few-ulp difference between the refine kernel's fp32 score and the ideal one.
+constexpr float TC_SLACK = 3.0517578125e-05f;           // 2^-15
+constexpr float TC_U_BF16 = 0.00390625f;                // 2^-8
+constexpr float TC_U_F16 = 0.00048828125f;              // 2^-11
+constexpr int TC_SPILL_MAX = 1024;                      // pass-2 candidates per row (second tensor-core pass)
 constexpr unsigned long long TC_TIMEOUT_CYCLES = 20000000000ull;   // ~10 s: trap instead of hanging the GPU
 
 // profiling trace: built only with -DRAG_TC_TRACE_BUILD=1 (python -m ragraph_b200.build --trace); the production
@@ -188,8 +198,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   return ((uint64_t)hi << 32) | lo;
 }
-// instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
+// instruction descriptor: D=f32, A=B=bf16 (format code 1; fp16 = 0), both K-major, N=128, M=128
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t TC_IDESC_F16 = (1u << 4) | (0u << 7) | (0u << 10) | ((TC_BN >> 3) << 17) | ((128u >> 4) << 24);
 // same shape with A = B = tf32 (format code 2 in bits [7,10) and [10,13))
 constexpr uint32_t TC_IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_BN >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -243,6 +254,16 @@ struct TcArgs {
   int premax; int pre_tiles; int pre_groups;
   float* gmax; const float* thr0;
   float* overflow;                 // TS kernel: [CTAs][8 warps][32 lanes][128] scores parked when a warp's hit queue overflows
+  uint32_t idesc;                  // tcgen05 instruction descriptor (operand format bf16 / fp16 / tf32 is a run-time field)
+  // ---- second pass (TS kernel, `collect`): the rows refine could not certify, as a device-side list ----
+  // row_map[i] = query row of compact row i, *n_rows_dev = how many; the CTA derives (query tile, key split) geometry from
+  // that count on the device (no host sync), CTAs beyond it exit at once.  thr0 is then indexed by COMPACT row and taken
+  // as is (thr_exact): a fixed threshold = exact k-th score - error bound.  Every score above it is a candidate: a full
+  // append buffer is spilled to spill_{s,i}[compact row][spill_cap] (slot from an atomic per-row counter) instead of
+  // being compacted against a top-k' list, so the pass returns ALL keys that can still belong to the exact top k.
+  const int32_t* row_map; const int32_t* n_rows_dev;
+  int collect; int thr_exact;
+  float* spill_s; int32_t* spill_i; int32_t* spill_cnt; int spill_cap;
   int trace;                       // RAG_TC_DEBUG=3 or RAG_TC_TRACE=1: CTA 0 stamps clock64 at pipeline events (g_tc_trace)
   int trace_t0;                    // RAG_TC_TRACE_T0: first traced tile (window of 512)
   int no_tma;                      // RAG_TC_NOTMA=1 (experiment): the producer arrives without loading keys (garbage operands)
@@ -284,9 +305,10 @@ cosine_topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   const int tile1 = min(tile0 + a.tiles_per_split, a.n_tiles);
   const int n_my_tiles = max(tile1 - tile0, 0);
   constexpr int BOX_ELEMS = TF32 ? 32 : 64;                 // elements per 128-byte box row (TMA K coordinate step)
-  auto mma = [](uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accum) {
-    if constexpr (TF32) tc_mma_tf32(tmem_d, da, db, TC_IDESC_TF32, accum);
-    else tc_mma_bf16(tmem_d, da, db, TC_IDESC, accum);
+  const uint32_t idesc = a.idesc;
+  auto mma = [idesc](uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accum) {
+    if constexpr (TF32) tc_mma_tf32(tmem_d, da, db, idesc, accum);
+    else tc_mma_bf16(tmem_d, da, db, idesc, accum);
   };
 
   // ---- one-time setup ---------------------------------------------------------------------------
@@ -608,13 +630,33 @@ __device__ __forceinline__ float ts_compact_row(float* ls, int32_t* li, float* p
   }
 }
 
+// Second pass (TcArgs::collect): the threshold is fixed, so a full append buffer is not compacted against a list but
+// written out -- all `np` pending (score, key) pairs of CTA row `row` go to the row's global spill area at the slots an
+// atomic per-row counter hands out (key splits of the same row append concurrently).  Entries past spill_cap are dropped;
+// the counter keeps counting, which is how the refine pass sees the overflow.
+__device__ __forceinline__ void ts_spill_row(const float* ps, const int32_t* pi, int row, int np, int lane, const TcArgs& a,
+                                             int64_t crow) {
+  int base = 0;
+  if (lane == 0) base = atomicAdd(a.spill_cnt + crow, np);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (int p = lane; p < np; p += 32) {
+    const int o = base + p;
+    if (o < a.spill_cap) {
+      a.spill_s[crow * a.spill_cap + o] = ps[p * TS_LSTRIDE + row];
+      a.spill_i[crow * a.spill_cap + o] = pi[p * TS_LSTRIDE + row];
+    }
+  }
+  __syncwarp();
+}
+
 // Serve one queued hit (all 32 lanes): lane j takes score j of the 32-score chunk, compares it with the owner row's
 // current threshold, and the candidates append themselves at ballot-derived slots of the owner's buffer; a full buffer
 // is compacted on the spot.  Returns the owner's new (threshold, pending count); `owner` = the owner lane.
 struct TsServed { float thr; int np; int owner; };
 template <int KP>
 __device__ __forceinline__ TsServed ts_serve_entry(const float* ev, int key0, int meta, float* ls, int32_t* li, float* ps,
-                                                   int32_t* pi, int wrow0, float thr, int npend, int lane) {
+                                                   int32_t* pi, int wrow0, float thr, int npend, int lane, const TcArgs& a,
+                                                   int64_t crow0) {
   const int L = meta & 31, nv = meta >> 8;
   const float val = ev[lane];
   float thr_l = __shfl_sync(0xffffffffu, thr, L);
@@ -634,7 +676,8 @@ __device__ __forceinline__ TsServed ts_serve_entry(const float* ev, int key0, in
     cand = cand && !fit;
     if (__ballot_sync(0xffffffffu, cand) == 0) break;
     __syncwarp();                                           // buffer full with candidates left: compact the row, go on
-    thr_l = ts_compact_row<KP>(ls, li, ps, pi, orow, KP, lane);
+    if (a.collect) ts_spill_row(ps, pi, orow, KP, lane, a, crow0 + orow);
+    else thr_l = ts_compact_row<KP>(ls, li, ps, pi, orow, KP, lane);
     np = 0;
     cand = cand && val > thr_l;
   }
@@ -689,10 +732,24 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
   if (threadIdx.x == 0 && (smem_u32(smem_dyn) & 1023u) != 0) __trap();     // TMA SWIZZLE_128B boxes need 1 KB alignment
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qtile = blockIdx.x % a.n_qtiles;
-  const int split = blockIdx.x / a.n_qtiles;
-  const int tile0 = split * a.tiles_per_split;
-  const int tile1 = min(tile0 + a.tiles_per_split, a.n_tiles);
+  // (query tile, key split) geometry: from the host plan, or -- second pass -- from the device-side row count
+  int n_qtiles = a.n_qtiles, tiles_per_split = a.tiles_per_split;
+  int64_t Qn = a.Q;
+  if (!PRE && a.n_rows_dev) {
+    const int n = *a.n_rows_dev;                            // written by the refine kernel earlier on this stream
+    if (n <= 0) return;                                     // (uniform: the whole CTA leaves before any barrier / TMEM)
+    n_qtiles = (n + TC_ROWS - 1) / TC_ROWS;
+    int S = (int)gridDim.x / n_qtiles;                      // the launch has >= max(#SMs, worst-case query tiles) CTAs
+    S = max(1, min(S, a.n_tiles));
+    tiles_per_split = (a.n_tiles + S - 1) / S;
+    const int n_splits = (a.n_tiles + tiles_per_split - 1) / tiles_per_split;
+    if ((int)blockIdx.x >= n_qtiles * n_splits) return;
+    Qn = n;
+  }
+  const int qtile = blockIdx.x % n_qtiles;
+  const int split = blockIdx.x / n_qtiles;
+  const int tile0 = split * tiles_per_split;
+  const int tile1 = min(tile0 + tiles_per_split, a.n_tiles);
   const int n_my_tiles = PRE ? min(max(tile1 - tile0, 0), a.pre_tiles) : max(tile1 - tile0, 0);
 
   // ---- one-time setup ---------------------------------------------------------------------------
@@ -742,6 +799,7 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
       mbar_wait(&bars->a_full, 0);
       tc_fence_after();
       const uint32_t b_addr = smem_u32(sB);
+      const uint32_t idesc = a.idesc;
       int s = mw * KH; uint32_t ph = 0;
       while (s >= NSTAGE) { s -= NSTAGE; ph ^= 1; }
       for (int t = mw; t < n_my_tiles; t += NISS) {
@@ -778,7 +836,7 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
             for (int k4 = 0; k4 < 4; ++k4) {
               const uint64_t db = umma_desc(b_addr + sk * TC_BOX_BYTES + k4 * 32);
               tc_mma_bf16_ts(tmem_base + (uint32_t)(buf * TC_BN), tmem_base + A_COL0 + (uint32_t)((rb * KH + kh) * 32 + k4 * 8),
-                             db, TC_IDESC, (kh | k4) != 0 ? 1u : 0u);
+                             db, idesc, (kh | k4) != 0 ? 1u : 0u);
             }
             if (tr3 && rb == 0 && kh < 2) t3[3 + 2 * kh] = (unsigned int)clock64();
             if (++sk == NSTAGE) sk = 0;
@@ -807,14 +865,15 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
     const int64_t grow = (int64_t)qtile * TC_ROWS + row;
     // ---- one-time: this thread's normalised bf16 query row -> TMEM (the stationary A operand) ----
     {
-      const uint4* src = reinterpret_cast<const uint4*>(q_bf + grow * (int64_t)(KH * 64));
+      const int64_t srow = (!PRE && a.row_map && grow < Qn) ? (int64_t)a.row_map[grow] : grow;   // second pass: compact rows
+      const uint4* src = reinterpret_cast<const uint4*>(q_bf + srow * (int64_t)(KH * 64));
       const uint32_t a_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + A_COL0 + (uint32_t)(rb * KH * 32);
 #pragma unroll 1
       for (int c = 0; c < KH * 2; ++c) {                    // 16 columns = 32 bf16 per step
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint4 x = (grow < a.Q) ? __ldg(src + c * 4 + i) : make_uint4(0u, 0u, 0u, 0u);
+          const uint4 x = (grow < Qn) ? __ldg(src + c * 4 + i) : make_uint4(0u, 0u, 0u, 0u);
           w[4 * i] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
         }
         if (a.swap_halves) {
@@ -833,8 +892,10 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
     int npend = 0;                                          // candidates in this row's append buffer
     // KP-th best score at the last compaction of this row; starts at the pre-pass bound (one notch lower, so that keys
     // tying with the bound are still taken) or -inf
-    float thr = (!PRE && a.thr0 && grow < a.Q) ? a.thr0[grow] : -INFINITY;
-    if (thr > -INFINITY) thr = (thr > 0.f) ? thr * (1.0f - 1e-6f) : thr * (1.0f + 1e-6f) - 1e-30f;
+    float thr = (!PRE && a.thr0 && grow < Qn) ? a.thr0[grow] : -INFINITY;
+    if (thr > -INFINITY && !a.thr_exact) thr = (thr > 0.f) ? thr * (1.0f - 1e-6f) : thr * (1.0f + 1e-6f) - 1e-30f;
+    if (grow >= Qn) thr = INFINITY;                         // padding rows of the last query tile never produce a hit
+    const int64_t crow0 = (int64_t)qtile * TC_ROWS;         // compact (second pass) / plain global row of CTA row 0
     // pre-pass state: running maximum of the current tile group
     float gm = -INFINITY;
     int gi = 0;
@@ -848,7 +909,7 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
     auto process_one = [&]() {
       const float* ev = q_mine + (qhead % TS_QN) * TS_QSTRIDE;
       const TsServed r = ts_serve_entry<KP>(ev, __float_as_int(ev[32]), __float_as_int(ev[33]), list_s, list_i, pq_s, pq_i, wrow0,
-                                            thr, npend, lane);
+                                            thr, npend, lane, a, crow0);
       if (lane == r.owner) { npend = r.np; thr = r.thr; }
       ++qhead;
       __syncwarp();
@@ -937,7 +998,7 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
                   const int L = __ffs(m) - 1;
                   m &= m - 1;
                   const TsServed r = ts_serve_entry<KP>(ov + L * TC_BN + c * 32, tile_key0 + c * 32, L | (nvc << 8), list_s, list_i,
-                                                        pq_s, pq_i, wrow0, thr, npend, lane);
+                                                        pq_s, pq_i, wrow0, thr, npend, lane, a, crow0);
                   if (lane == r.owner) { npend = r.np; thr = r.thr; }
                   __syncwarp();
                 }
@@ -965,10 +1026,11 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
         const int L = __ffs(todo) - 1;
         todo &= todo - 1;
         const int np = __shfl_sync(0xffffffffu, npend, L);
-        ts_compact_row<KP>(list_s, list_i, pq_s, pq_i, wrow0 + L, np, lane);
+        if (a.collect) ts_spill_row(pq_s, pq_i, wrow0 + L, np, lane, a, crow0 + wrow0 + L);
+        else ts_compact_row<KP>(list_s, list_i, pq_s, pq_i, wrow0 + L, np, lane);
       }
     }
-    if (!PRE && grow < a.Q) {
+    if (!PRE && !a.collect && grow < a.Q) {
       float* ps = a.part_s + ((int64_t)split * a.Q + grow) * KP;
       int32_t* pi = a.part_i + ((int64_t)split * a.Q + grow) * KP;
 #pragma unroll
@@ -1026,7 +1088,10 @@ struct RefineArgs {
   int64_t idx_offset;
   float* out_scores; int64_t* out_idx;
   int32_t* fb_rows; int32_t* fb_count;   // uncertified rows (exact only)
-  const float* thr0;                     // nullable: pre-pass bound; keys never listed score <= thr0[row] (bf16)
+  const float* thr0;                     // nullable: pre-pass bound; keys never listed score <= thr0[row] (16-bit score)
+  // error bound of the 16-bit scores, per row: qerr[row] (nullable) + *kerr_max (nullable) + eps_fixed
+  const float* qerr; const float* kerr_max; float eps_fixed;
+  float* thr2;                           // per uncertified row (same slot as fb_rows): threshold of the second pass
 };
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -1042,7 +1107,8 @@ __device__ __forceinline__ float warp_max(float v) {
 //   pass 3: only candidates with s_bf16 >= tau - 2 EPS can be among the exact top k (the k candidates that define
 //           tau have exact scores >= tau - EPS, everything below the cut has exact score < tau - EPS), so only
 //           those are re-scored in fp32 from the master keys -- typically 15-30 of the 144+ candidates;
-//   certificate: k-th exact score > max_split t_split + EPS, else the row goes to the fp32 fallback list.
+//   certificate: k-th exact score > max_split t_split + EPS, else the row goes to the second-pass list together with
+//           thr2 = k-th exact score - EPS - 1e-6: every key that can still enter the exact top k scores above it.
 __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -1052,7 +1118,9 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
   float* ap = reinterpret_cast<float*>(reinterpret_cast<int64_t*>(smem_raw) + (size_t)wpb * a.k) + (size_t)wpb * a.k +
               (size_t)warp * total;
   const int nd = (a.d + 31) >> 5;                              // <= 8 (tensor-core shapes have d <= 256)
+  const float kerr = a.kerr_max ? __ldg(a.kerr_max) : 0.f;
   for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < a.Q; row += (int64_t)gridDim.x * wpb) {
+    const float eps = (a.qerr ? __ldg(a.qerr + row) : 0.f) + kerr + a.eps_fixed;
     for (int p = lane; p < a.k; p += 32) { lv[p] = -FLT_MAX; li[p] = INT64_MAX; }
     // ---- pass 1 ------------------------------------------------------------------------------------
     float tmax = -INFINITY;
@@ -1089,7 +1157,7 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
       cnt += __reduce_add_sync(0xffffffffu, n);
       prev = m;
     }
-    const float cut = (cnt >= a.k) ? (a.exact ? prev - 2.0f * TC_EPS : prev) : -INFINITY;
+    const float cut = (cnt >= a.k) ? (a.exact ? prev - 2.0f * eps : prev) : -INFINITY;
     // ---- pass 3 ------------------------------------------------------------------------------------
     float qreg[8];
     const float qinv = a.q_inv_norm ? __ldg(a.q_inv_norm + row) : 1.0f;
@@ -1140,12 +1208,88 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
       }
     }
     const float kth = lv[a.k - 1];
-    const bool certified = !a.exact || (li[a.k - 1] != INT64_MAX && kth > tmax + TC_EPS);
+    const bool have_k = li[a.k - 1] != INT64_MAX;
+    const bool certified = !a.exact || (have_k && kth > tmax + eps);
     for (int p = lane; p < a.k; p += 32) {
       a.out_scores[row * a.k + p] = lv[p];
       a.out_idx[row * a.k + p] = (li[p] == INT64_MAX) ? (int64_t)-1 : li[p] + a.idx_offset;
     }
-    if (!certified && lane == 0) a.fb_rows[atomicAdd(a.fb_count, 1)] = (int32_t)row;
+    if (!certified && lane == 0) {
+      const int slot = atomicAdd(a.fb_count, 1);
+      a.fb_rows[slot] = (int32_t)row;
+      a.thr2[slot] = have_k ? kth - eps - 1e-6f : -INFINITY;
+    }
+    __syncwarp();
+  }
+}
+
+
+// ---- refine of the second pass: exact fp32 re-score of EVERYTHING the collect pass returned ----------------
+// One warp per uncertified row (compact slot).  The collect pass delivered every key whose 16-bit score exceeds
+// thr2 = (k-th exact score of the first refine) - eps - 1e-6, so a key it did not deliver has an exact score below that
+// k-th score: the best k of the delivered set are the exact top k -- unless the row's spill area overflowed, in which
+// case the row goes to the fp32 kernel's list (dense ties beyond TC_SPILL_MAX: adversarial libraries only).
+struct Refine2Args {
+  const float* q; const float* keys; const float* q_inv_norm; const float* key_inv_norm;
+  int d; int k; int64_t idx_offset;
+  const int32_t* rows; const int32_t* n_rows_dev;
+  const float* spill_s; const int32_t* spill_i; const int32_t* spill_cnt; int spill_cap;
+  float* out_scores; int64_t* out_idx;
+  int32_t* fb_rows; int32_t* fb_count;
+};
+
+__global__ void __launch_bounds__(256) refine2_kernel(const Refine2Args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  int64_t* li = reinterpret_cast<int64_t*>(smem_raw) + (size_t)warp * a.k;
+  float* lv = reinterpret_cast<float*>(reinterpret_cast<int64_t*>(smem_raw) + (size_t)wpb * a.k) + (size_t)warp * a.k;
+  const int n = *a.n_rows_dev;
+  const int nd = (a.d + 31) >> 5;
+  for (int slot = blockIdx.x * wpb + warp; slot < n; slot += gridDim.x * wpb) {
+    const int64_t row = a.rows[slot];
+    const int cnt = a.spill_cnt[slot];
+    if (cnt > a.spill_cap) {
+      if (lane == 0) a.fb_rows[atomicAdd(a.fb_count, 1)] = (int32_t)row;
+      continue;
+    }
+    for (int p = lane; p < a.k; p += 32) { lv[p] = -FLT_MAX; li[p] = INT64_MAX; }
+    __syncwarp();
+    float qreg[8];
+    const float qinv = a.q_inv_norm ? __ldg(a.q_inv_norm + row) : 1.0f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int e = lane + 32 * t;
+      qreg[t] = (t < nd && e < a.d) ? __ldg(a.q + row * a.d + e) * qinv : 0.f;
+    }
+    const int32_t* ci = a.spill_i + (size_t)slot * a.spill_cap;
+    for (int c0 = 0; c0 < cnt; c0 += 4) {
+      float sc[4]; int64_t id[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        id[u] = (c0 + u < cnt) ? (int64_t)ci[c0 + u] : -1;     // plain loads: written by the collect pass on this stream
+        float dot = 0.f;
+        if (id[u] >= 0) {
+          const float* kr = a.keys + id[u] * a.d;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int e = lane + 32 * t;
+            if (t < nd && e < a.d) dot = fmaf(qreg[t], __ldg(kr + e), dot);
+          }
+        }
+        sc[u] = dot;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (id[u] >= 0) sc[u] = warp_sum(sc[u]) * (a.key_inv_norm ? __ldg(a.key_inv_norm + id[u]) : 1.0f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (id[u] >= 0 && ranks_before(sc[u], id[u], lv[a.k - 1], li[a.k - 1]))
+          warp_sorted_insert<int64_t>(lv, li, a.k, sc[u], id[u], lane);
+    }
+    for (int p = lane; p < a.k; p += 32) {
+      a.out_scores[row * a.k + p] = lv[p];
+      a.out_idx[row * a.k + p] = (li[p] == INT64_MAX) ? (int64_t)-1 : li[p] + a.idx_offset;
+    }
     __syncwarp();
   }
 }
@@ -1184,9 +1328,37 @@ static int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int d_
 struct TcPlan {
   int kh, kp, nstage, n_qtiles, n_splits, tiles_per_split, n_tiles, d_pad;
   size_t smem;
-  size_t off_qbf, off_qinv, off_ps, off_pi, off_fb, off_fbn, off_gmax, off_thr0, off_ovf, off_f32, total;
+  size_t off_qbf, off_qinv, off_qerr, off_ps, off_pi, off_fb, off_zero, off_thr2, off_fb2, off_gmax, off_thr0, off_ovf,
+      off_spill_s, off_spill_i, off_f32, total;
+  int64_t n_zero;                     // 32-bit words cleared by the prologue: {pass-2 row count, fp32 row count, pad} + spill counters
+  int spill_cap;
   int pre_tiles, pre_groups;          // threshold pre-pass (0 tiles = off)
 };
+constexpr int TC_ZERO_HDR = 64;       // words in front of the per-row spill counters
+
+// Process-wide tuning / test hooks (rag_tc_set_option); the environment is read ONCE, when the first call needs them.
+struct TcOptions {
+  int variant = 0;                    // 0 auto, 1 = SS kernel wherever it is instantiated, 2 = TS kernel
+  int prepass = 1;
+  int prepass_min_tiles = 1024;
+  int prepass_div = 64;
+  int kp = 0;                         // 0 auto, 16 / 32 = candidate-list length per (row, split) where the shape allows
+  int pass2 = 1;                      // 0: uncertified rows go straight to the fp32 kernel (the round-1 behaviour)
+};
+static TcOptions tc_env_defaults() {
+  TcOptions o;
+  if (const char* e = getenv("RAG_TC_VARIANT")) o.variant = (e[0] == 's' && e[1] == 's') ? 1 : ((e[0] == 't' && e[1] == 's') ? 2 : 0);
+  if (const char* e = getenv("RAG_TC_PREPASS")) o.prepass = (e[0] == '0') ? 0 : 1;
+  if (const char* e = getenv("RAG_TC_PREPASS_MIN_TILES")) { if (atoi(e) >= 64) o.prepass_min_tiles = atoi(e); }
+  if (const char* e = getenv("RAG_TC_PREPASS_DIV")) { if (atoi(e) >= 4) o.prepass_div = atoi(e); }
+  if (const char* e = getenv("RAG_TC_KP")) { if (atoi(e) == 16 || atoi(e) == 32) o.kp = atoi(e); }
+  if (const char* e = getenv("RAG_TC_PASS2")) o.pass2 = (e[0] == '0') ? 0 : 1;
+  return o;
+}
+static TcOptions& tc_opts() {
+  static TcOptions o = tc_env_defaults();
+  return o;
+}
 
 // SS kernel shapes (query tile resident in shared memory)
 static bool tc_shape_ok_ss(int d, int k) {
@@ -1206,17 +1378,18 @@ bool tc_shape_ok_tf32(int d, int k) { return d >= 1 && k >= 1 && ((d <= 64 && k 
 // TS kernel wins once a CTA streams many key tiles (12.5 M keys x 4096 queries: parity; 100 M: +6 %), because its hit
 // handling is built for the sparse steady state behind the pre-pass bound; short streams are one long warm-up phase, where
 // the SS kernel's lane-parallel list updates are 2-3x faster.  Default: TS from 8192 tiles per CTA, and for the shapes SS
-// does not instantiate.  RAG_TC_VARIANT=ss|ts forces one (A/B measurements, tests).
+// does not instantiate.  rag_tc_set_option("variant", 1|2) forces one (A/B measurements, tests).
 constexpr int TS_MIN_TILES_PER_SPLIT = 8192;
 static bool tc_use_ts(int d, int k, int tiles_per_split) {
   const bool ss_ok = tc_shape_ok_ss(d, k);
-  const char* e = getenv("RAG_TC_VARIANT");
-  if (e && e[0] == 's' && e[1] == 's') return !ss_ok;
-  if (e && e[0] == 't' && e[1] == 's') return true;
+  const int v = tc_opts().variant;
+  if (v == 1) return !ss_ok;
+  if (v == 2) return true;
   return !ss_ok || tiles_per_split >= TS_MIN_TILES_PER_SPLIT;
 }
 
 static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = false) {
+  const TcOptions& o = tc_opts();
   TcPlan p{};
   if (tf32) {
     p.d_pad = d <= 32 ? 32 : (d <= 64 ? 64 : 128);   // fp32 elements; the shadow is padded to the SS instantiations 1, 2, 4
@@ -1227,6 +1400,7 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = f
     if (!ts && p.kh == 3) p.kh = 4;          // SS instantiations: 1, 2, 4
   }
   p.kp = (k <= 10) ? 16 : 32;
+  if (o.kp == 32 && !tf32 && d <= 128) p.kp = 32;   // wider lists certify more rows of a clustered library in the first pass
   // shared memory: (SS: A 2*KH boxes +) NSTAGE boxes + lists + barriers + 1 KB alignment slack  <= 227 KB
   // SS: lists + meta + pending queues; TS: sorted lists + append buffers (stride 257) + 16 B alignment slack
   const int list_bytes = ts ? 2 * p.kp * TS_LSTRIDE * 8 + TS_QUEUE_BYTES + 16 : p.kp * TC_ROWS * 8 + TC_ROWS * 4 + TC_PQ * TC_ROWS * 8;
@@ -1246,28 +1420,34 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = f
   if (s > p.n_tiles) s = p.n_tiles;
   p.tiles_per_split = (p.n_tiles + s - 1) / s;
   p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  int64_t sc = ((int64_t)1 << 26) / (Q > 0 ? Q : 1);
+  p.spill_cap = (int)(sc > TC_SPILL_MAX ? TC_SPILL_MAX : (sc < 64 ? 64 : sc));
+  p.n_zero = TC_ZERO_HDR + Q;
   size_t off = 0;
   p.off_qbf = off; off += align_up((size_t)p.n_qtiles * TC_ROWS * p.d_pad * (tf32 ? 4 : 2), 256);
   p.off_qinv = off; off += align_up((size_t)Q * 4, 256);
+  p.off_qerr = off; off += align_up((size_t)Q * 4, 256);
   p.off_ps = off; off += align_up((size_t)p.n_splits * Q * p.kp * 4, 256);
   p.off_pi = off; off += align_up((size_t)p.n_splits * Q * p.kp * 4, 256);
   p.off_fb = off; off += align_up((size_t)Q * 4, 256);
-  p.off_fbn = off; off += 256;
+  p.off_zero = off; off += align_up((size_t)p.n_zero * 4, 256);
+  p.off_thr2 = off; off += align_up((size_t)Q * 4, 256);
+  p.off_fb2 = off; off += align_up((size_t)Q * 4, 256);
   // threshold pre-pass (TS kernel): 1/64 of every split, worthwhile once a split has >= 1024 tiles; G = n_splits * groups
   // group maxima per row, G >= 2 * kp so that the kp-th largest of them sits near the middle of their distribution
   p.pre_tiles = 0; p.pre_groups = 0;
-  int pre_min = 1024;
-  { const char* e = getenv("RAG_TC_PREPASS_MIN_TILES"); if (e && atoi(e) >= 64) pre_min = atoi(e); }   // tests lower it
-  if (ts && p.tiles_per_split >= pre_min) {
+  if (ts && p.tiles_per_split >= o.prepass_min_tiles) {
     int g = (2 * p.kp + p.n_splits - 1) / p.n_splits;
     if (g < 1) g = 1;
-    int div = 64;
-    { const char* e = getenv("RAG_TC_PREPASS_DIV"); if (e && atoi(e) >= 4) div = atoi(e); }                    // experiments
-    if ((int64_t)g * p.n_splits <= 256 && g <= p.tiles_per_split / div) { p.pre_tiles = p.tiles_per_split / div; p.pre_groups = g; }
+    if ((int64_t)g * p.n_splits <= 256 && g <= p.tiles_per_split / o.prepass_div) { p.pre_tiles = p.tiles_per_split / o.prepass_div; p.pre_groups = g; }
   }
   p.off_gmax = off; off += align_up((size_t)p.pre_groups * p.n_splits * Q * 4, 256);
   p.off_thr0 = off; off += align_up((size_t)Q * 4, 256);
-  p.off_ovf = off; off += ts ? align_up((size_t)p.n_qtiles * p.n_splits * TC_EPI_WARPS * 32 * TC_BN * 4, 256) : 0;
+  // hit-queue overflow area: one slice per CTA of the largest TS launch (the second pass runs max(#SMs, query tiles) CTAs)
+  const int64_t ts_ctas = std::max<int64_t>((int64_t)p.n_qtiles * p.n_splits, std::max<int64_t>(sm_count(), p.n_qtiles));
+  p.off_ovf = off; off += ts ? align_up((size_t)ts_ctas * TC_EPI_WARPS * 32 * TC_BN * 4, 256) : 0;
+  p.off_spill_s = off; off += (ts && !tf32) ? align_up((size_t)Q * p.spill_cap * 4, 256) : 0;
+  p.off_spill_i = off; off += (ts && !tf32) ? align_up((size_t)Q * p.spill_cap * 4, 256) : 0;
   p.off_f32 = off; off += topk_f32_rows_workspace(Q, N, d, k);
   p.total = off;
   return p;
@@ -1280,7 +1460,15 @@ int topk_tc_tf32_dpad(int d) { return d <= 32 ? 32 : (d <= 64 ? 64 : 128); }
 size_t topk_tc_workspace(int64_t Q, int64_t N, int d, int k, int mode) {
   if (mode == RAG_SIM_TF32) return tc_shape_ok_tf32(d, k) ? tc_plan(Q, N, d, k, false, true).total : 256;
   if (!tc_shape_ok(d, k)) return 256;
-  return tc_plan(Q, N, d, k, true).total;   // offsets do not depend on the variant
+  return tc_plan(Q, N, d, k, true).total;   // offsets do not depend on the variant (the TS layout is the superset)
+}
+
+void topk_tc_stat_offsets(int64_t Q, int64_t N, int d, int k, int mode, size_t* out) {
+  out[0] = out[1] = 0;
+  if ((mode != RAG_SIM_BF16_REFINE && mode != RAG_SIM_F16_REFINE) || !tc_shape_ok(d, k) || Q <= 0 || N <= 0) return;
+  const TcPlan p = tc_plan(Q, N, d, k, true);
+  out[0] = p.off_zero;
+  out[1] = p.off_zero + 4;
 }
 
 template <int KH, int NSTAGE, int KP, bool TF32 = false>
@@ -1294,21 +1482,37 @@ static int launch_filter(const CUtensorMap& mq, const CUtensorMap& mk, const TcA
 }
 
 template <int KH, int NSTAGE, int KP, bool PRE>
-static int launch_filter_ts(const CUtensorMap& mk, const uint16_t* q_bf, const TcArgs& a, const TcPlan& p, cudaStream_t s) {
+static int launch_filter_ts(const CUtensorMap& mk, const uint16_t* q_bf, const TcArgs& a, const TcPlan& p, unsigned grid,
+                            cudaStream_t s) {
   static_assert(sizeof(TsBarriers) <= TS_BAR_BYTES, "barrier block");
   auto kern = cosine_topk_ts_kernel<KH, NSTAGE, KP, PRE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(cosine_topk_ts_kernel)");
-  kern<<<(unsigned)(p.n_qtiles * p.n_splits), TS_THREADS, p.smem, s>>>(mk, q_bf, a);
+  kern<<<grid, TS_THREADS, p.smem, s>>>(mk, q_bf, a);
   RAG_LAUNCH_OK("cosine_topk_ts_kernel");
   return RAG_OK;
 }
 
+// one TS launch of plan p: the pre-pass instantiation when ta.premax, else the main / collect kernel
+static int run_ts(const CUtensorMap& mk, const uint16_t* q_bf, const TcArgs& ta, const TcPlan& p, unsigned grid, cudaStream_t s) {
+#define RAG_TS_CASE(KH_, NS_, KP_) \
+  if (p.kh == KH_ && p.nstage == NS_ && p.kp == KP_) \
+    return ta.premax ? launch_filter_ts<KH_, NS_, KP_, true>(mk, q_bf, ta, p, grid, s) : launch_filter_ts<KH_, NS_, KP_, false>(mk, q_bf, ta, p, grid, s);
+  RAG_TS_CASE(1, 9, 16) RAG_TS_CASE(2, 9, 16) RAG_TS_CASE(3, 9, 16) RAG_TS_CASE(4, 9, 16)
+  RAG_TS_CASE(1, 4, 32) RAG_TS_CASE(2, 4, 32)
+#undef RAG_TS_CASE
+  return fail(RAG_EUNSUPPORTED, "cosine_topk: no tensor-core instantiation for kh=%d nstage=%d kp=%d", p.kh, p.nstage, p.kp);
+}
+
+int rows_to_16_launch(const float* x, int64_t rows, int d, int fmt, int normalize, float eps, uint16_t* out, int d_pad,
+                      float* inv_out, float* err_rows, float* err_max, uint32_t* zero_words, int64_t n_zero, cudaStream_t s);
+
 int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const void* keys_shadow,
-                int64_t N, int d, int k, int mode, uint32_t flags, int64_t idx_offset, float* out_scores,
-                int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
+                const float* shadow_err, int64_t N, int d, int k, int mode, uint32_t flags, int64_t idx_offset,
+                float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
   const bool tf32 = (mode == RAG_SIM_TF32);
-  const uint16_t* keys_bf16 = static_cast<const uint16_t*>(keys_shadow);
+  const bool f16 = (mode == RAG_SIM_F16 || mode == RAG_SIM_F16_REFINE);
+  const bool exact = (mode == RAG_SIM_BF16_REFINE || mode == RAG_SIM_F16_REFINE);
   RAG_REQUIRE(!(flags & RAG_SIM_DOT), RAG_EUNSUPPORTED, "cosine_topk: the tensor-core modes implement cosine only");
   if (tf32)
     RAG_REQUIRE(tc_shape_ok_tf32(d, k), RAG_EUNSUPPORTED,
@@ -1318,24 +1522,42 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
                 "cosine_topk: tensor-core modes cover d <= 128 with k <= 26 and d <= 256 with k <= 10 (d=%d k=%d)", d, k);
   RAG_REQUIRE(key_inv_norm, RAG_EINVAL, "cosine_topk: the tensor-core modes need key_inv_norm (rag_row_inv_norm_f32)");
   RAG_REQUIRE(aligned16(keys_shadow), RAG_EALIGN, "cosine_topk: the key shadow must be 16-byte aligned");
-  const bool ts = !tf32 && tc_use_ts(d, k, tc_plan(Q, N, d, k, true).tiles_per_split);
-  TcPlan p = tc_plan(Q, N, d, k, ts, tf32);
-  RAG_REQUIRE(ws_bytes >= p.total, RAG_EWORKSPACE, "cosine_topk: workspace %zu < %zu bytes", ws_bytes, p.total);
+  const TcPlan pts = tc_plan(Q, N, d, k, true, false);           // TS plan: workspace layout + the second pass
+  const bool ts = !tf32 && tc_use_ts(d, k, pts.tiles_per_split);
+  const TcPlan p = tf32 ? tc_plan(Q, N, d, k, false, true) : (ts ? pts : tc_plan(Q, N, d, k, false, false));
+  const size_t need = tf32 ? p.total : pts.total;
+  RAG_REQUIRE(ws_bytes >= need, RAG_EWORKSPACE, "cosine_topk: workspace %zu < %zu bytes", ws_bytes, need);
   RAG_REQUIRE(ws && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, RAG_EALIGN, "cosine_topk: workspace must be 256-byte aligned");
-  RAG_REQUIRE(p.smem <= (size_t)max_smem_optin(), RAG_EUNSUPPORTED, "cosine_topk: needs %zu bytes of shared memory", p.smem);
+  RAG_REQUIRE(p.smem <= (size_t)max_smem_optin() && pts.smem <= (size_t)max_smem_optin(), RAG_EUNSUPPORTED,
+              "cosine_topk: needs %zu bytes of shared memory", p.smem);
+  // every offset below comes from the layout plan L: the TS plan for the 16-bit modes (its list areas are at least as
+  // large as the SS kernel's: same kp, n_splits), the tf32 plan otherwise
+  const TcPlan& L = tf32 ? p : pts;
   unsigned char* w = static_cast<unsigned char*>(ws);
-  uint16_t* q_bf = reinterpret_cast<uint16_t*>(w + p.off_qbf);
-  float* qinv = reinterpret_cast<float*>(w + p.off_qinv);
+  uint16_t* q_bf = reinterpret_cast<uint16_t*>(w + L.off_qbf);
+  float* qinv = reinterpret_cast<float*>(w + L.off_qinv);
+  float* qerr = reinterpret_cast<float*>(w + L.off_qerr);
+  int32_t* zero = reinterpret_cast<int32_t*>(w + L.off_zero);
+  int32_t* fb_count = zero;            // rows for the second pass
+  int32_t* fb2_count = zero + 1;       // rows for the fp32 kernel
+  int32_t* spill_cnt = zero + TC_ZERO_HDR;
   const int d_pad_keys = tf32 ? topk_tc_tf32_dpad(d) : (d + 63) / 64 * 64;        // layout of the caller's shadow
   RAG_REQUIRE(p.d_pad == d_pad_keys, RAG_EUNSUPPORTED, "internal: d_pad mismatch");
 
-  int st = tf32 ? rag_rows_to_tf32(q, Q, d, 1, 1e-12f, reinterpret_cast<float*>(q_bf), p.d_pad, s)
-                : rag_rows_to_bf16(q, Q, d, 1, 1e-12f, q_bf, p.d_pad, s);
-  if (st) return st;
-  st = rag_row_inv_norm_f32(q, Q, d, 1e-12f, qinv, s);
-  if (st) return st;
-  cudaError_t e = cudaMemsetAsync(w + p.off_fbn, 0, 4, s);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(fb_count)");
+  int st;
+  if (tf32) {
+    st = rag_rows_to_tf32(q, Q, d, 1, 1e-12f, reinterpret_cast<float*>(q_bf), p.d_pad, s);
+    if (st) return st;
+    st = rag_row_inv_norm_f32(q, Q, d, 1e-12f, qinv, s);
+    if (st) return st;
+    cudaError_t e = cudaMemsetAsync(zero, 0, 8, s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(fb_count)");
+  } else {
+    // ONE prologue launch: normalised 16-bit query image, inverse norms, rounding-error norms, device counters cleared
+    st = rows_to_16_launch(q, Q, d, f16 ? RAG_FMT_F16 : RAG_FMT_BF16, 1, 1e-12f, q_bf, p.d_pad, qinv, qerr, nullptr,
+                           reinterpret_cast<uint32_t*>(zero), L.n_zero, s);
+    if (st) return st;
+  }
 
   CUtensorMap mq, mk;
   st = make_map_bf16(&mk, keys_shadow, N, p.d_pad, TC_BN, tf32);
@@ -1344,6 +1566,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   TcArgs a{};
   a.Q = Q; a.N = N; a.n_qtiles = p.n_qtiles; a.n_splits = p.n_splits; a.tiles_per_split = p.tiles_per_split;
   a.n_tiles = p.n_tiles; a.kp = p.kp;
+  a.idesc = tf32 ? TC_IDESC_TF32 : (f16 ? TC_IDESC_F16 : TC_IDESC);
   // Diagnostic switches (tools/ only: MMA-only ceilings, pipeline trace, operand experiments).  They change or void the
   // results, so they are honoured only in a process started with RAG_DIAG=1 (read once); production calls never look.
   static const bool diag = [] { const char* e = getenv("RAG_DIAG"); return e && atoi(e) != 0; }();
@@ -1354,34 +1577,25 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
     { const char* nt = getenv("RAG_TC_NOTMA"); a.no_tma = nt ? atoi(nt) : 0; }
     { const char* sw = getenv("RAG_TS_SWAP"); a.swap_halves = sw ? atoi(sw) : 0; }
   }
-  a.part_s = reinterpret_cast<float*>(w + p.off_ps);
-  a.part_i = reinterpret_cast<int32_t*>(w + p.off_pi);
-  a.overflow = reinterpret_cast<float*>(w + p.off_ovf);
+  a.part_s = reinterpret_cast<float*>(w + L.off_ps);
+  a.part_i = reinterpret_cast<int32_t*>(w + L.off_pi);
+  a.overflow = reinterpret_cast<float*>(w + L.off_ovf);
   if (ts) {
-    auto run_ts = [&](const TcArgs& ta) -> int {
-#define RAG_TS_CASE(KH_, NS_, KP_) \
-  if (p.kh == KH_ && p.nstage == NS_ && p.kp == KP_) \
-    return ta.premax ? launch_filter_ts<KH_, NS_, KP_, true>(mk, q_bf, ta, p, s) : launch_filter_ts<KH_, NS_, KP_, false>(mk, q_bf, ta, p, s);
-      RAG_TS_CASE(1, 9, 16) RAG_TS_CASE(2, 9, 16) RAG_TS_CASE(3, 9, 16) RAG_TS_CASE(4, 9, 16)
-      RAG_TS_CASE(1, 4, 32) RAG_TS_CASE(2, 4, 32)
-#undef RAG_TS_CASE
-      return fail(RAG_EUNSUPPORTED, "cosine_topk: no tensor-core instantiation for kh=%d nstage=%d kp=%d", p.kh, p.nstage, p.kp);
-    };
-    const char* pp = getenv("RAG_TC_PREPASS");
-    if (p.pre_tiles > 0 && !(pp && pp[0] == '0') && a.debug == 0) {
+    const unsigned grid = (unsigned)(p.n_qtiles * p.n_splits);
+    if (p.pre_tiles > 0 && tc_opts().prepass && a.debug == 0) {
       // threshold pre-pass over the first 1/64 of every split (group maxima only), then the per-row bound
       TcArgs pre = a;
       pre.premax = 1; pre.pre_tiles = p.pre_tiles; pre.pre_groups = p.pre_groups;
-      pre.gmax = reinterpret_cast<float*>(w + p.off_gmax);
+      pre.gmax = reinterpret_cast<float*>(w + L.off_gmax);
       pre.trace = 0;
-      st = run_ts(pre);
+      st = run_ts(mk, q_bf, pre, p, grid, s);
       if (st) return st;
-      float* thr0 = reinterpret_cast<float*>(w + p.off_thr0);
+      float* thr0 = reinterpret_cast<float*>(w + L.off_thr0);
       sample_threshold_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, s>>>(pre.gmax, p.pre_groups * p.n_splits, Q, p.kp, thr0);
       RAG_LAUNCH_OK("sample_threshold_kernel");
       a.thr0 = thr0;
     }
-    st = run_ts(a);
+    st = run_ts(mk, q_bf, a, p, grid, s);
   } else {
     st = make_map_bf16(&mq, q_bf, Q, p.d_pad, 128, tf32);
     if (st) return st;
@@ -1399,11 +1613,16 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   RefineArgs r{};
   r.q = q; r.keys = keys; r.q_inv_norm = qinv; r.key_inv_norm = key_inv_norm;
   r.Q = Q; r.N = N; r.d = d; r.k = k; r.kp = p.kp; r.n_splits = p.n_splits;
-  r.part_s = a.part_s; r.part_i = a.part_i; r.exact = (mode == RAG_SIM_BF16_REFINE) ? 1 : 0;
+  r.part_s = a.part_s; r.part_i = a.part_i; r.exact = exact ? 1 : 0;
   r.idx_offset = idx_offset; r.out_scores = out_scores; r.out_idx = out_idx;
-  r.fb_rows = reinterpret_cast<int32_t*>(w + p.off_fb);
-  r.fb_count = reinterpret_cast<int32_t*>(w + p.off_fbn);
+  r.fb_rows = reinterpret_cast<int32_t*>(w + L.off_fb);
+  r.fb_count = fb_count;
   r.thr0 = a.thr0;
+  r.thr2 = reinterpret_cast<float*>(w + L.off_thr2);
+  const float u = f16 ? TC_U_F16 : TC_U_BF16;
+  r.qerr = tf32 ? nullptr : qerr;
+  r.kerr_max = shadow_err;
+  r.eps_fixed = TC_SLACK + (shadow_err ? 0.f : u);
   const int total_c = p.n_splits * p.kp;
   const int wpb = (total_c <= 1024) ? 8 : 2;                    // per-warp smem: k*12 + total*4 bytes (< 48 KB per CTA)
   int64_t blocks = (Q + wpb - 1) / wpb;
@@ -1411,10 +1630,41 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   if (blocks > cap) blocks = cap;
   refine_kernel<<<(unsigned)blocks, wpb * 32, (size_t)wpb * (k * 12 + total_c * 4), s>>>(r);
   RAG_LAUNCH_OK("refine_kernel");
-  if (mode != RAG_SIM_BF16_REFINE) return RAG_OK;
-  // rows whose certificate failed are recomputed in fp32 (device-side row list; usually empty)
-  return topk_f32_run_rows(q, Q, keys, key_inv_norm, qinv, N, d, k, idx_offset, r.fb_rows, r.fb_count, out_scores,
-                           out_idx, w + p.off_f32, ws_bytes - p.off_f32, s);
+  if (!exact) return RAG_OK;
+
+  const int32_t* fp32_rows = r.fb_rows;
+  const int32_t* fp32_count = fb_count;
+  if (tc_opts().pass2 && a.debug == 0) {
+    // ---- second pass: the uncertified rows (device-side list, usually empty: the CTAs read the count and leave) rescan
+    //      the shard on the tensor cores with the fixed threshold thr2 and return EVERY key above it ----
+    TcArgs c = a;
+    c.thr0 = r.thr2; c.thr_exact = 1; c.collect = 1; c.premax = 0; c.trace = 0;
+    c.row_map = r.fb_rows; c.n_rows_dev = fb_count;
+    c.spill_s = reinterpret_cast<float*>(w + L.off_spill_s);
+    c.spill_i = reinterpret_cast<int32_t*>(w + L.off_spill_i);
+    c.spill_cnt = spill_cnt; c.spill_cap = pts.spill_cap;
+    c.kp = pts.kp;
+    const unsigned grid2 = (unsigned)std::max(sm_count(), pts.n_qtiles);
+    st = run_ts(mk, q_bf, c, pts, grid2, s);
+    if (st) return st;
+    Refine2Args r2{};
+    r2.q = q; r2.keys = keys; r2.q_inv_norm = qinv; r2.key_inv_norm = key_inv_norm;
+    r2.d = d; r2.k = k; r2.idx_offset = idx_offset;
+    r2.rows = r.fb_rows; r2.n_rows_dev = fb_count;
+    r2.spill_s = c.spill_s; r2.spill_i = c.spill_i; r2.spill_cnt = spill_cnt; r2.spill_cap = pts.spill_cap;
+    r2.out_scores = out_scores; r2.out_idx = out_idx;
+    r2.fb_rows = reinterpret_cast<int32_t*>(w + L.off_fb2); r2.fb_count = fb2_count;
+    int64_t b2 = (Q + 7) / 8;
+    const int64_t cap2 = (int64_t)sm_count() * 8;
+    if (b2 > cap2) b2 = cap2;
+    refine2_kernel<<<(unsigned)b2, 256, (size_t)8 * k * 12, s>>>(r2);
+    RAG_LAUNCH_OK("refine2_kernel");
+    fp32_rows = r2.fb_rows;
+    fp32_count = fb2_count;
+  }
+  // rows still open (spill overflow: more than spill_cap near-ties) are recomputed by the fp32 kernel
+  return topk_f32_run_rows(q, Q, keys, key_inv_norm, qinv, N, d, k, idx_offset, fp32_rows, fp32_count, out_scores,
+                           out_idx, w + L.off_f32, ws_bytes - L.off_f32, s);
 }
 
 }  // namespace rag
@@ -1425,4 +1675,18 @@ extern "C" RAG_API int rag_tc_trace_read(unsigned long long* host_out) {
   if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host_out + 4 * 512, rag::g_tc_trace2, sizeof(unsigned int) * 2 * 512);
   if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host_out + 4 * 512 + 512, rag::g_tc_trace3, sizeof(unsigned int) * 16 * 256);
   return e == cudaSuccess ? RAG_OK : rag::cuda_fail(e, "rag_tc_trace_read");
+}
+
+extern "C" RAG_API int rag_tc_set_option(const char* name, int32_t value) {
+  if (!name) return rag::fail(RAG_EINVAL, "tc_set_option: null name");
+  rag::TcOptions& o = rag::tc_opts();
+  const rag::TcOptions dflt;
+  if (!strcmp(name, "variant")) o.variant = (value >= 0 && value <= 2) ? value : dflt.variant;
+  else if (!strcmp(name, "prepass")) o.prepass = value < 0 ? dflt.prepass : (value != 0);
+  else if (!strcmp(name, "prepass_min_tiles")) o.prepass_min_tiles = value >= 64 ? value : dflt.prepass_min_tiles;
+  else if (!strcmp(name, "prepass_div")) o.prepass_div = value >= 4 ? value : dflt.prepass_div;
+  else if (!strcmp(name, "kp")) o.kp = (value == 16 || value == 32) ? value : dflt.kp;
+  else if (!strcmp(name, "pass2")) o.pass2 = value < 0 ? dflt.pass2 : (value != 0);
+  else return rag::fail(RAG_EINVAL, "tc_set_option: unknown option '%s'", name);
+  return RAG_OK;
 }

@@ -107,6 +107,24 @@ def _(x, normalize=True, eps=1e-12):
     return x.new_empty((x.shape[0], round_up(x.shape[1], 64)), dtype=torch.bfloat16)
 
 
+def rows_to_shadow16(x: Tensor, fmt: int = L.FMT_F16, normalize: bool = True, eps: float = 1e-12,
+                     err_max: Optional[Tensor] = None, want_row_err: bool = False):
+    """16-bit shadow [rows, round_up(d, 64)] (fmt FMT_F16 -> float16, FMT_BF16 -> bfloat16) plus the rounding-error norms of
+    the exactness certificate: ``err_max`` (float32 [1], zero-initialised by the caller, max-accumulated) and, if
+    ``want_row_err``, the per-row norms.  Returns (shadow, row_err or None)."""
+    _need_cuda(x, err_max)
+    x = _f32c(x, "rows_to_shadow16")
+    d_pad = round_up(x.shape[1], 64)
+    out = torch.empty((x.shape[0], d_pad), dtype=torch.float16 if fmt == L.FMT_F16 else torch.bfloat16, device=x.device)
+    row_err = torch.empty(x.shape[0], dtype=torch.float32, device=x.device) if want_row_err else None
+    if err_max is not None and (err_max.dtype != torch.float32 or err_max.numel() != 1):
+        raise RuntimeError("rows_to_shadow16: err_max must be a float32 tensor with one element")
+    with torch.cuda.device(x.device):
+        L.check(L.load().rag_rows_to_shadow16(_p(x), x.shape[0], x.shape[1], fmt, int(normalize), eps, _p(out), d_pad,
+                                              _p(row_err), _p(err_max), _stream()), "rows_to_shadow16")
+    return out, row_err
+
+
 def tf32_shadow_dpad(d: int) -> int:
     """columns of the tf32 key shadow for embedding dim d (32, 64 or 128; 0 = d not covered by RAG_SIM_TF32)"""
     return int(L.load().rag_tf32_shadow_dpad(d))
@@ -155,13 +173,12 @@ def _(q, keys, flags=0):
     return q.new_empty((q.shape[0], keys.shape[0]))
 
 
-@torch.library.custom_op("ragraph::cosine_topk", mutates_args=())
-def cosine_topk(q: Tensor, keys: Tensor, k: int, key_inv_norm: Optional[Tensor] = None,
-                keys_bf16: Optional[Tensor] = None, mode: int = 0, flags: int = 0,
-                idx_offset: int = 0) -> Tuple[Tensor, Tensor]:
-    """Fused similarity + top-k.  Returns (scores[Q,k] f32 desc, idx[Q,k] int64).  ``keys_bf16`` is the key shadow of
-    the tensor-core modes: rows_to_bf16(keys) for SIM_BF16 / SIM_BF16_REFINE, rows_to_tf32(keys) for SIM_TF32."""
-    _need_cuda(q, keys, key_inv_norm, keys_bf16)
+_SHADOW_DTYPE = {L.SIM_BF16: torch.bfloat16, L.SIM_BF16_REFINE: torch.bfloat16, L.SIM_F16: torch.float16,
+                 L.SIM_F16_REFINE: torch.float16}
+
+
+def _cosine_topk_impl(q, keys, k, key_inv_norm, keys_shadow, mode, flags, idx_offset, shadow_err, want_stats):
+    _need_cuda(q, keys, key_inv_norm, keys_shadow, shadow_err)
     q, keys = _f32c(q, "cosine_topk"), _f32c(keys, "cosine_topk")
     if q.dim() != 2 or keys.dim() != 2 or q.shape[1] != keys.shape[1]:
         raise RuntimeError(f"cosine_topk: shapes {tuple(q.shape)} vs {tuple(keys.shape)}")
@@ -170,28 +187,57 @@ def cosine_topk(q: Tensor, keys: Tensor, k: int, key_inv_norm: Optional[Tensor] 
         key_inv_norm = _f32c(key_inv_norm, "key_inv_norm")
         if key_inv_norm.numel() != N:
             raise RuntimeError("cosine_topk: key_inv_norm must have N entries")
-    if keys_bf16 is not None and mode == L.SIM_TF32:
-        if keys_bf16.dtype != torch.float32 or tuple(keys_bf16.shape) != (N, tf32_shadow_dpad(d)) \
-                or not keys_bf16.is_contiguous():
+    if keys_shadow is not None and mode == L.SIM_TF32:
+        if keys_shadow.dtype != torch.float32 or tuple(keys_shadow.shape) != (N, tf32_shadow_dpad(d)) \
+                or not keys_shadow.is_contiguous():
             raise RuntimeError("cosine_topk: SIM_TF32 needs the contiguous [N, tf32_shadow_dpad(d)] fp32 shadow (rows_to_tf32)")
-    elif keys_bf16 is not None:
-        if keys_bf16.dtype != torch.bfloat16 or tuple(keys_bf16.shape) != (N, round_up(d, 64)) \
-                or not keys_bf16.is_contiguous():
-            raise RuntimeError("cosine_topk: keys_bf16 must be the contiguous [N, round_up(d,64)] bf16 shadow")
+    elif keys_shadow is not None:
+        want = _SHADOW_DTYPE.get(mode, keys_shadow.dtype)
+        if keys_shadow.dtype != want or tuple(keys_shadow.shape) != (N, round_up(d, 64)) or not keys_shadow.is_contiguous():
+            raise RuntimeError(f"cosine_topk: mode {mode} needs the contiguous [N, round_up(d,64)] {want} shadow "
+                               f"(rows_to_shadow16), got {keys_shadow.dtype} {tuple(keys_shadow.shape)}")
+    if shadow_err is not None and (shadow_err.dtype != torch.float32 or shadow_err.numel() != 1):
+        raise RuntimeError("cosine_topk: shadow_err must be the float32 [1] err_max of rows_to_shadow16")
     scores = torch.empty((Q, k), dtype=torch.float32, device=q.device)
     idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
     lib = L.load()
     ws = _workspace(lib.rag_cosine_topk_workspace(Q, N, d, k, mode), q.device)
     with torch.cuda.device(q.device):
-        L.check(lib.rag_cosine_topk_f32(_p(q), Q, _p(keys), _p(key_inv_norm), _p(keys_bf16), N, d, k, mode, flags,
-                                        idx_offset, _p(scores), _p(idx), _p(ws), ws.numel(), _stream()),
+        L.check(lib.rag_cosine_topk_f32(_p(q), Q, _p(keys), _p(key_inv_norm), _p(keys_shadow), _p(shadow_err), N, d, k,
+                                        mode, flags, idx_offset, _p(scores), _p(idx), _p(ws), ws.numel(), _stream()),
                 "cosine_topk")
-    return scores, idx
+    if not want_stats:
+        return scores, idx
+    offs = (C.c_size_t * 2)()
+    L.check(lib.rag_cosine_topk_stat_offsets(Q, N, d, k, mode, offs), "cosine_topk_stat_offsets")
+    if offs[0] == 0 and offs[1] == 0:
+        stats = torch.zeros(2, dtype=torch.int32, device=q.device)
+    else:
+        stats = torch.stack([ws[offs[0]:offs[0] + 4].view(torch.int32)[0], ws[offs[1]:offs[1] + 4].view(torch.int32)[0]])
+    return scores, idx, stats
+
+
+@torch.library.custom_op("ragraph::cosine_topk", mutates_args=())
+def cosine_topk(q: Tensor, keys: Tensor, k: int, key_inv_norm: Optional[Tensor] = None,
+                keys_bf16: Optional[Tensor] = None, mode: int = 0, flags: int = 0,
+                idx_offset: int = 0, shadow_err: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """Fused similarity + top-k.  Returns (scores[Q,k] f32 desc, idx[Q,k] int64).  ``keys_bf16`` is the key shadow of
+    the tensor-core modes: rows_to_shadow16(keys, FMT_F16) for SIM_F16 / SIM_F16_REFINE, rows_to_bf16(keys) for SIM_BF16 /
+    SIM_BF16_REFINE, rows_to_tf32(keys) for SIM_TF32; ``shadow_err`` = that shadow's err_max (tightens the certificate)."""
+    return _cosine_topk_impl(q, keys, k, key_inv_norm, keys_bf16, mode, flags, idx_offset, shadow_err, False)
 
 
 @cosine_topk.register_fake
-def _(q, keys, k, key_inv_norm=None, keys_bf16=None, mode=0, flags=0, idx_offset=0):
+def _(q, keys, k, key_inv_norm=None, keys_bf16=None, mode=0, flags=0, idx_offset=0, shadow_err=None):
     return q.new_empty((q.shape[0], k)), q.new_empty((q.shape[0], k), dtype=torch.int64)
+
+
+def cosine_topk_with_stats(q: Tensor, keys: Tensor, k: int, key_inv_norm: Optional[Tensor] = None,
+                           keys_shadow: Optional[Tensor] = None, mode: int = 0, flags: int = 0, idx_offset: int = 0,
+                           shadow_err: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """cosine_topk plus an int32 [2] device tensor {rows that took the second tensor-core pass, rows that fell back to the
+    fp32 kernel} (zeros for modes without a certificate)."""
+    return _cosine_topk_impl(q, keys, k, key_inv_norm, keys_shadow, mode, flags, idx_offset, shadow_err, True)
 
 
 @torch.library.custom_op("ragraph::topk_masked", mutates_args=())

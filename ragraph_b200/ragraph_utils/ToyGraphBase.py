@@ -48,7 +48,8 @@ class ToyGraphBase:
         self._cap = 0
         self._label_dtype = label_dtype
         self._keys = self._values = self._labels = self._positions = None
-        self._inv_norm = self._keys_bf16 = self._keys_tf32 = None
+        self._inv_norm = self._keys_tf32 = None
+        self._shadow16 = {}                   # FMT_F16 / FMT_BF16 -> (shadow [n, d_pad], err_max float32 [1])
         self._derived_rows = 0                # rows [0, _derived_rows) of inv_norm / bf16 shadow are valid
         self._class_ids = None                # argmax of the label rows (few-shot fusion), valid for _class_rows rows
         self._class_rows = 0
@@ -74,7 +75,8 @@ class ToyGraphBase:
         if self.variant == "node_fewshot":           # position codes only feed the two-metric score
             self._positions = grow(self._positions, (cap, self.num_anchors), torch.float32)
         self._inv_norm = grow(self._inv_norm, (cap,), torch.float32)
-        self._keys_bf16 = self._keys_tf32 = None   # rebuilt lazily at the size in use
+        self._keys_tf32 = None                      # rebuilt lazily at the size in use
+        self._shadow16 = {}
         self._cap = cap
 
     def add_entries(self, keys: Tensor, values: Tensor, labels: Tensor, positions: Optional[Tensor] = None) -> None:
@@ -158,22 +160,32 @@ class ToyGraphBase:
         for features, adj, labels in resource_graphs:
             self._build_toy_graph_base(features, adj, labels)
 
-    def _refresh_derived(self, want_bf16: bool, want_tf32: bool = False) -> None:
+    def _refresh_derived(self, fmt16: Optional[int] = None, want_tf32: bool = False) -> None:
         n = self._n
         if self._derived_rows < n:
             lo = self._derived_rows
             self._inv_norm[lo:n].copy_(ops.row_inv_norm(self._keys[lo:n]))
             self._derived_rows = n
-            self._keys_bf16 = self._keys_tf32 = None
-        if want_bf16 and (self._keys_bf16 is None or self._keys_bf16.shape[0] != n):
-            self._keys_bf16 = ops.rows_to_bf16(self._keys[:n], True)
+            self._keys_tf32 = None
+            self._shadow16 = {}
+        if fmt16 is not None and (fmt16 not in self._shadow16 or self._shadow16[fmt16][0].shape[0] != n):
+            # normalised 16-bit image of the keys + the largest rounding-error norm of a row (certificate bound)
+            err = torch.zeros(1, dtype=torch.float32, device=self.device)
+            shadow, _ = ops.rows_to_shadow16(self._keys[:n], fmt16, True, err_max=err)
+            self._shadow16 = {fmt16: (shadow, err)}            # one 16-bit shadow at a time (25.6 GB at 100 M x 128)
         if want_tf32 and (self._keys_tf32 is None or self._keys_tf32.shape[0] != n):
             self._keys_tf32 = ops.rows_to_tf32(self._keys[:n], True)
 
-    def _shadow(self, mode: int) -> Optional[Tensor]:
-        """the key shadow the similarity mode reads (None for the fp32 path), refreshed for the rows in use"""
-        self._refresh_derived(mode in (L.SIM_BF16, L.SIM_BF16_REFINE), mode == L.SIM_TF32)
-        return self._keys_tf32 if mode == L.SIM_TF32 else (self._keys_bf16 if mode != L.SIM_FP32 else None)
+    _FMT_OF_MODE = {L.SIM_BF16: L.FMT_BF16, L.SIM_BF16_REFINE: L.FMT_BF16, L.SIM_F16: L.FMT_F16, L.SIM_F16_REFINE: L.FMT_F16}
+
+    def _shadow(self, mode: int) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+        """(key shadow, its err_max) the similarity mode reads -- (None, None) for the fp32 path -- refreshed for the rows
+        in use"""
+        fmt = self._FMT_OF_MODE.get(mode)
+        self._refresh_derived(fmt, mode == L.SIM_TF32)
+        if mode == L.SIM_TF32:
+            return self._keys_tf32, None
+        return self._shadow16[fmt] if fmt is not None else (None, None)
 
     # reference attribute names (views of the rows in use)
     @property
@@ -187,7 +199,7 @@ class ToyGraphBase:
         return None if self._positions is None else self._positions[:self._n]
     @property
     def key_inv_norm(self) -> Tensor:
-        self._refresh_derived(False)
+        self._refresh_derived()
         return self._inv_norm[:self._n]
 
     def class_ids(self) -> Tensor:
@@ -275,14 +287,19 @@ class ToyGraphBase:
         print("label count distribution", torch.sum(self.resource_labels, dim=0))
 
     # ---- retrieval ------------------------------------------------------------------------
+    # Measured crossover (B200, profiles/r1_midsize_ab.jsonl, r2_small_shapes.jsonl): the tensor-core filter + fp32 refine
+    # beats the fp32 CUDA-core kernel from a few thousand keys once there is a query tile's worth of rows (cfg1: 2 708 x
+    # 10.8 k x 256: 0.19 ms vs 1.07 ms); below that the single-launch small-problem kernel serves retrieve() directly.
+    TC_MIN_KEYS, TC_MIN_QUERIES = 4096, 16
+
     def _pick_mode(self, Q: int, k: Optional[int] = None) -> int:
         if self.mode is not None:
             return self.mode
-        # tensor-core filter + fp32 refine pays off once the scan is large; both are exact-match
+        # tensor-core filter (fp16 operands) + fp32 refine: exact-match like the fp32 kernel
         k = self.retrieve_num if k is None else k
-        big = self._n >= 65536 and Q >= 16
-        ok = big and L.load().rag_sim_mode_supported(L.SIM_BF16_REFINE, self.emb_size, k)
-        return L.SIM_BF16_REFINE if ok else L.SIM_FP32
+        big = self._n >= self.TC_MIN_KEYS and Q >= self.TC_MIN_QUERIES
+        ok = big and L.load().rag_sim_mode_supported(L.SIM_F16_REFINE, self.emb_size, k)
+        return L.SIM_F16_REFINE if ok else L.SIM_FP32
 
     def topk(self, search_keys: Tensor, k: int, search_positions: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         """(scores[Q,k], indices[Q,k] int64): torch.topk(cosine(search_keys, resource_keys), k) fused."""
@@ -295,8 +312,8 @@ class ToyGraphBase:
         if k > L.RAG_MAX_K:
             return self._topk_large(search_keys, k)
         mode = self._pick_mode(search_keys.shape[0], k)
-        shadow = self._shadow(mode)
-        return ops.direct(ops.cosine_topk)(search_keys, self.resource_keys, k, self._inv_norm[:self._n], shadow, mode)
+        shadow, err = self._shadow(mode)
+        return ops.direct(ops.cosine_topk)(search_keys, self.resource_keys, k, self._inv_norm[:self._n], shadow, mode, 0, 0, err)
 
     def _topk_large(self, search_keys: Tensor, k: int, budget_bytes: int = 1 << 30) -> Tuple[Tensor, Tensor]:
         """k > RAG_MAX_K (the edge variant's vanilla configs ask for retrieve_num = 100000, i.e. most of the library,

@@ -28,7 +28,7 @@ def test_header_symbols_all_exported_and_bound():
         assert hasattr(lib, n), f"{n} declared in include/ragraph_b200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(names)
-    assert lib.rag_abi_version() == 1
+    assert lib.rag_abi_version() == _lib.ABI_VERSION == 2
     assert lib.rag_status_string(-3) == b"RAG_EUNSUPPORTED"
 
 

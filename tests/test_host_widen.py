@@ -76,7 +76,7 @@ def cpu_ops(monkeypatch):
     table = {
         "csr_spmm": _spmm, "csr_from_dense": _csr_from_dense, "csr_from_coo": _csr_from_coo,
         "gather_rows": lambda table, idx: table[idx], "gather_reduce": _gather_reduce,
-        "cosine_topk": lambda q, keys, k, inv=None, sh=None, mode=0, flags=0, off=0: torch.topk(O.cosine_similarity(q, keys), k),
+        "cosine_topk": lambda q, keys, k, inv=None, sh=None, mode=0, flags=0, off=0, err=None: torch.topk(O.cosine_similarity(q, keys), k),
         "cosine2_topk": lambda qa, ka, wa, qb, kb, wb, k: torch.topk(
             wa * O.cosine_similarity(qa, ka) + wb * O.cosine_similarity(qb, kb), k),
         "row_inv_norm": lambda x, eps=1e-12: 1.0 / x.norm(dim=1).clamp_min(eps),
