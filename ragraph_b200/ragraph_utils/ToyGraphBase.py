@@ -54,6 +54,10 @@ class ToyGraphBase:
         self._class_ids = None                # argmax of the label rows (few-shot fusion), valid for _class_rows rows
         self._class_rows = 0
         self.shard_lo = 0                     # global index of local row 0 (key-row sharded libraries)
+        # diagnostics: with collect_stats the next topk() leaves an int32 [2] device tensor in last_stats = {rows that took
+        # the second tensor-core pass, rows recomputed by the fp32 kernel} (no host sync; read it when convenient)
+        self.collect_stats = False
+        self.last_stats: Optional[Tensor] = None
         self._reserve(capacity)
 
     # ---- store ---------------------------------------------------------------------------
@@ -78,6 +82,17 @@ class ToyGraphBase:
         self._keys_tf32 = None                      # rebuilt lazily at the size in use
         self._shadow16 = {}
         self._cap = cap
+
+    def clear(self, release: bool = False) -> None:
+        """Forget every library row (capacity is kept unless ``release``): the store can be refilled in place."""
+        self._n = 0
+        self._derived_rows = 0
+        self._class_ids, self._class_rows = None, 0
+        self._keys_tf32 = None
+        self._shadow16 = {}
+        if release:
+            self._keys = self._values = self._labels = self._positions = self._inv_norm = None
+            self._cap = 0
 
     def add_entries(self, keys: Tensor, values: Tensor, labels: Tensor, positions: Optional[Tensor] = None) -> None:
         """Append library rows (the torch.cat of ToyGraphBase.py:116-119)."""
@@ -311,9 +326,18 @@ class ToyGraphBase:
                                                 search_keys, self.resource_keys, self.semantic_weight, k)
         if k > L.RAG_MAX_K:
             return self._topk_large(search_keys, k)
+        return self.topk_local(search_keys, k, 0)
+
+    def topk_local(self, search_keys: Tensor, k: int, idx_offset: int = 0) -> Tuple[Tensor, Tensor]:
+        """fused similarity + top-k over the rows of THIS store; returned indices = idx_offset + local row"""
         mode = self._pick_mode(search_keys.shape[0], k)
         shadow, err = self._shadow(mode)
-        return ops.direct(ops.cosine_topk)(search_keys, self.resource_keys, k, self._inv_norm[:self._n], shadow, mode, 0, 0, err)
+        if self.collect_stats:
+            s, i, self.last_stats = ops.cosine_topk_with_stats(search_keys, self.resource_keys, k, self._inv_norm[:self._n],
+                                                               shadow, mode, 0, idx_offset, err)
+            return s, i
+        return ops.direct(ops.cosine_topk)(search_keys, self.resource_keys, k, self._inv_norm[:self._n], shadow, mode, 0,
+                                           idx_offset, err)
 
     def _topk_large(self, search_keys: Tensor, k: int, budget_bytes: int = 1 << 30) -> Tuple[Tensor, Tensor]:
         """k > RAG_MAX_K (the edge variant's vanilla configs ask for retrieve_num = 100000, i.e. most of the library,

@@ -43,11 +43,7 @@ def owner_of(idx: Tensor, n_rows: int, world: int) -> Tensor:
 
 
 def _default_local_topk(store, q, k):
-    from . import ops
-    mode = store._pick_mode(q.shape[0], k)
-    shadow, err = store._shadow(mode)
-    return ops.direct(ops.cosine_topk)(q, store.resource_keys, k, store._inv_norm[:len(store)], shadow, mode, 0,
-                                       store.shard_lo, err)
+    return store.topk_local(q, k, store.shard_lo)
 
 
 def _default_merge(scores, idx, k):
