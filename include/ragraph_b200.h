@@ -70,6 +70,10 @@ enum rag_shadow_fmt { RAG_FMT_BF16 = 0, RAG_FMT_F16 = 1 };
 #define RAG_SIM_DOT 1u /* skip L2 normalisation: plain dot product (edge eval top-k,
                           RAGraph_edge/utils/metrics.py:102-117) */
 
+#define RAG_SIM_WIDE_LISTS 2u /* tensor-core modes, d <= 128: 32-entry candidate lists per (row, key split) instead of 16 for
+                                 k <= 10 -- a clustered library then certifies in the first pass (about 12 % more time on a
+                                 Gaussian one); ignored where the shape has no such instantiation */
+
 /* epilogues of rag_csr_spmm_f32 (bit flags, applied in this order) */
 #define RAG_EPI_ROWNORM 1u /* divide row i by sum_j val[i,j]        (Propagation.py:15-16) */
 #define RAG_EPI_BIAS 2u    /* + bias[F]                              (layers/gcn.py:37-38)  */
@@ -142,15 +146,32 @@ RAG_API int rag_cosine_topk_f32(const float* q, int64_t Q, const float* keys, co
                         const void* keys_shadow, const float* shadow_err, int64_t N, int32_t d, int32_t k,
                         int32_t mode, uint32_t flags, int64_t idx_offset, float* out_scores, int64_t* out_idx,
                         void* workspace, size_t workspace_bytes, rag_stream_t stream);
-/* Byte offsets, inside the caller's workspace of the same (Q, N, d, k, mode), of two int32 counters the *_REFINE
- * modes leave behind: offsets_out[0] = rows that needed the second tensor-core pass, offsets_out[1] = rows that fell
- * back to the fp32 kernel.  Valid after the call's work has finished on the stream; 0/0 for other modes. */
+/* Byte offsets, inside the caller's workspace of the same (Q, N, d, k, mode), of three consecutive int32 counters the
+ * *_REFINE modes leave behind: offsets_out[0] = rows that needed the second tensor-core pass, offsets_out[1] = rows that
+ * fell back to the fp32 kernel, offsets_out[2] = rows whose certificate would fail under an 8x larger error bound (what a
+ * bf16 filter would have: lets a caller running fp16 decide whether bf16 would do).  Valid after the call's work has
+ * finished on the stream; all 0 for other modes. */
 RAG_API int rag_cosine_topk_stat_offsets(int64_t Q, int64_t N, int32_t d, int32_t k, int32_t mode, size_t* offsets_out);
 /* Process-wide tuning / test hooks of the tensor-core path, read from the environment ONCE at load (RAG_TC_VARIANT,
  * RAG_TC_PREPASS, RAG_TC_PREPASS_MIN_TILES, RAG_TC_PREPASS_DIV, RAG_TC_KP) and settable here: name without the RAG_TC_
  * prefix in lower case ("variant": 0 auto / 1 ss / 2 ts; "prepass": 0/1; "prepass_min_tiles"; "prepass_div"; "kp": 0 auto /
  * 16 / 32; "pass2": 0/1).  value < 0 restores the default.  Returns RAG_EINVAL for an unknown name. */
 RAG_API int rag_tc_set_option(const char* name, int32_t value);
+
+/* Small-problem retrieve in ONE launch (the reference's real call sites: RAGraph_graph/ragraph_utils/ToyGraphBase.py:56-87 --
+ * one pooled query against a few hundred library rows; the few-shot and noise branches): F.normalize + similarity + top-k +
+ * values[idx] + labels[idx] for Q <= 64, N <= 65536, k <= 16, Q*d <= 16384 (rag_retrieve_small_supported).
+ * key_inv_norm nullable (norms then formed on the fly); values / labels nullable together with their outputs; rows are
+ * copied bit exact (row sizes multiples of 4 bytes).  out_values [Q,k,value_row_bytes], out_labels [Q,k,label_row_bytes].
+ * The workspace (rag_retrieve_small_workspace bytes, 256-byte aligned) must be ZERO-FILLED once by the caller and may then
+ * be reused by successive calls on the same stream (the kernel re-arms its ticket); scores as the fp32 kernel (<= 1e-6). */
+RAG_API int rag_retrieve_small_supported(int64_t Q, int64_t N, int32_t d, int32_t k);
+RAG_API size_t rag_retrieve_small_workspace(int64_t Q, int64_t N, int32_t d, int32_t k);
+RAG_API int rag_retrieve_small_f32(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, int64_t N,
+                           int32_t d, int32_t k, uint32_t flags, const void* values, int64_t value_row_bytes,
+                           const void* labels, int64_t label_row_bytes, float* out_scores, int64_t* out_idx,
+                           void* out_values, void* out_labels, void* workspace, size_t workspace_bytes,
+                           rag_stream_t stream);
 
 /* Top-k with per-query exclusion lists, fp32 path: query row r never returns the key indices
  * mask_col[mask_rowptr[r] .. mask_rowptr[r+1]) (global indices, i.e. including idx_offset; any order).  With

@@ -121,8 +121,7 @@ class RAGraphFewShot(nn.Module):
             rag_embedding = torch.sum(rag_embeddings, dim=1)
             hidden_embedding = query_embeddings * (1 - self.retrieve_weight) + rag_embedding * self.retrieve_weight
         else:
-            hidden_embedding = ops.gather_reduce(base.resource_values, idx, L.REDUCE_SUM, query_embeddings,
-                                                 self.retrieve_weight)
+            hidden_embedding = base.gather_reduce_blend(idx, L.REDUCE_SUM, query_embeddings, self.retrieve_weight)
         decode_logits = self.pretrain_model.decode(hidden_embedding, adj)
         label_logits = decode_logits * (1 - self.label_weight) + rag_logits * self.label_weight
         if self.graph_level:

@@ -18,6 +18,7 @@ RAG_MAX_K = 128
 SIM_FP32, SIM_TF32, SIM_BF16, SIM_BF16_REFINE, SIM_F16, SIM_F16_REFINE = 0, 1, 2, 3, 4, 5
 FMT_BF16, FMT_F16 = 0, 1
 SIM_DOT = 1
+SIM_WIDE_LISTS = 2
 EPI_ROWNORM, EPI_BIAS, EPI_RELU, EPI_PRELU, EPI_BLEND, EPI_ACCUM = 1, 2, 4, 8, 16, 32
 REDUCE_SUM, REDUCE_MEAN = 0, 1
 ACT_NONE, ACT_ELU = 0, 1
@@ -44,6 +45,9 @@ SIGNATURES = {
     "rag_cosine_topk_f32": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _i64, _p, _p, _p, _sz, _p]),
     "rag_cosine_topk_stat_offsets": (C.c_int, [_i64, _i64, _i32, _i32, _i32, _p]),
     "rag_tc_set_option": (C.c_int, [C.c_char_p, _i32]),
+    "rag_retrieve_small_supported": (C.c_int, [_i64, _i64, _i32, _i32]),
+    "rag_retrieve_small_workspace": (_sz, [_i64, _i64, _i32, _i32]),
+    "rag_retrieve_small_f32": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _u32, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "rag_topk_masked_f32": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _u32, _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "rag_cosine2_topk_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "rag_cosine2_topk_f32": (C.c_int, [_p, _p, _i32, _f32, _p, _p, _i32, _f32, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),

@@ -81,6 +81,15 @@ class CSRGraph:
         from .autograd import spmm_epilogue
         return spmm_epilogue(self, x, epilogue, **kw)
 
+    def to_dense(self) -> Tensor:
+        """dense [n_rows, n_cols] float32 matrix (duplicate entries add up) -- for the consumers that are dense by nature
+        (Augmentation's random edge rewrite, PositionAwareEncoder's all-pairs distances, sub-adjacency extraction on toy
+        graphs of a few dozen nodes)."""
+        val = self.val if self.val is not None else torch.ones(self.nnz, dtype=torch.float32, device=self.col.device)
+        out = torch.zeros((self.n_rows, self.n_cols), dtype=torch.float32, device=self.col.device)
+        out.index_put_((self.row_ids(), self.col.to(torch.int64)), val, accumulate=True)
+        return out
+
     def row_ids(self) -> Tensor:
         """int64 [nnz]: the row of every stored entry."""
         counts = self.rowptr[1:] - self.rowptr[:-1]
@@ -111,6 +120,17 @@ class CSRGraph:
 
 
 _dense_cache: dict = {}
+
+
+def as_dense(adj) -> Tensor:
+    """dense 2-D view of any accepted adjacency (CSRGraph, torch sparse, dense [n,n] or [1,n,n])"""
+    if isinstance(adj, CSRGraph):
+        return adj.to_dense()
+    if isinstance(adj, Tensor):
+        if adj.layout != torch.strided:
+            return adj.to_dense()
+        return adj[0] if adj.dim() == 3 and adj.shape[0] == 1 else adj
+    raise TypeError(f"adjacency must be a dense/sparse tensor or CSRGraph, got {type(adj)}")
 
 
 def as_csr(adj) -> CSRGraph:

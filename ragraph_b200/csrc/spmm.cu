@@ -59,7 +59,7 @@ __device__ __forceinline__ float apply_epi(float y, float inv_deg_num, bool rown
                                            float alpha, float blend, float blend_w, float accum) {
   if (rownorm) y = y / inv_deg_num;                       // (sum a_ij x_j) / deg_i ; 0/0 -> NaN as torch
   if (epi & RAG_EPI_BIAS) y += b;
-  if (epi & RAG_EPI_RELU) y = fmaxf(y, 0.f);
+  if (epi & RAG_EPI_RELU) y = (y > 0.f || y != y) ? y : 0.f;    // torch.relu keeps NaN (fmaxf would turn a 0/0 row into 0)
   if (epi & RAG_EPI_PRELU) y = y >= 0.f ? y : alpha * y;
   if (epi & RAG_EPI_BLEND) y = y * (1.0f - blend_w) + blend * blend_w;
   if (epi & RAG_EPI_ACCUM) y += accum;

@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(TK_THREADS, 2) cosine_topk_f32_kernel(const To
             }
           }
         }
+        __syncwarp();                             // every lane has read thr[row] (racecheck: intra-warp WAR)
         if (lane == 0) thr[row] = t;
       }
       __syncthreads();

@@ -578,6 +578,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 //    KP-1.  A frozen threshold admits candidates at the rate it had when it was set, so a row is compacted about once
 //    per doubling of the keys seen, instead of one replace-min list update per candidate.
 constexpr int TS_LSTRIDE = TC_ROWS + 1;
+// append-buffer length for a list of KP entries: 32-entry lists keep a 16-entry buffer -- the 33 KB that saves are two more
+// pipeline stages (7 instead of 4 + 1), and a compaction every 16 candidates is what the 16-entry lists do anyway
+__host__ __device__ constexpr int ts_kpb(int kp) { return kp == 32 ? 16 : kp; }
 constexpr int TS_QN = 16;                 // hit-queue entries per epilogue warp
 constexpr int TS_QSTRIDE = 36;            // 32 scores + first key index + (owner lane | valid columns << 8), 16 B aligned
 constexpr int TS_QUEUE_BYTES = TC_EPI_WARPS * TS_QN * TS_QSTRIDE * 4;
@@ -657,6 +660,7 @@ template <int KP>
 __device__ __forceinline__ TsServed ts_serve_entry(const float* ev, int key0, int meta, float* ls, int32_t* li, float* ps,
                                                    int32_t* pi, int wrow0, float thr, int npend, int lane, const TcArgs& a,
                                                    int64_t crow0) {
+  constexpr int KPB = ts_kpb(KP);
   const int L = meta & 31, nv = meta >> 8;
   const float val = ev[lane];
   float thr_l = __shfl_sync(0xffffffffu, thr, L);
@@ -667,17 +671,17 @@ __device__ __forceinline__ TsServed ts_serve_entry(const float* ev, int key0, in
     const unsigned cm = __ballot_sync(0xffffffffu, cand);
     if (cm == 0) break;
     const int pos = np + __popc(cm & ((1u << lane) - 1u));
-    const bool fit = cand && pos < KP;
+    const bool fit = cand && pos < KPB;
     if (fit) {
       ps[pos * TS_LSTRIDE + orow] = val;
       pi[pos * TS_LSTRIDE + orow] = key0 + lane;
     }
-    np = min(np + __popc(cm), KP);
+    np = min(np + __popc(cm), KPB);
     cand = cand && !fit;
     if (__ballot_sync(0xffffffffu, cand) == 0) break;
     __syncwarp();                                           // buffer full with candidates left: compact the row, go on
-    if (a.collect) ts_spill_row(ps, pi, orow, KP, lane, a, crow0 + orow);
-    else thr_l = ts_compact_row<KP>(ls, li, ps, pi, orow, KP, lane);
+    if (a.collect) ts_spill_row(ps, pi, orow, KPB, lane, a, crow0 + orow);
+    else thr_l = ts_compact_row<KP>(ls, li, ps, pi, orow, KPB, lane);
     np = 0;
     cand = cand && val > thr_l;
   }
@@ -724,10 +728,11 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
   unsigned char* sB = smem_dyn;
   float* list_s = reinterpret_cast<float*>(smem_dyn + NSTAGE * TC_BOX_BYTES);
   int32_t* list_i = reinterpret_cast<int32_t*>(list_s + KP * TS_LSTRIDE);
+  constexpr int KPB = ts_kpb(KP);
   float* pq_s = reinterpret_cast<float*>(list_i + KP * TS_LSTRIDE);
-  int32_t* pq_i = reinterpret_cast<int32_t*>(pq_s + KP * TS_LSTRIDE);
-  float* queue = reinterpret_cast<float*>(pq_i + KP * TS_LSTRIDE);        // [8 warps][TS_QN][TS_QSTRIDE]
-  constexpr int BAR_OFF = (NSTAGE * TC_BOX_BYTES + 4 * KP * TS_LSTRIDE * 4 + TS_QUEUE_BYTES + 15) / 16 * 16;
+  int32_t* pq_i = reinterpret_cast<int32_t*>(pq_s + KPB * TS_LSTRIDE);
+  float* queue = reinterpret_cast<float*>(pq_i + KPB * TS_LSTRIDE);       // [8 warps][TS_QN][TS_QSTRIDE]
+  constexpr int BAR_OFF = (NSTAGE * TC_BOX_BYTES + 2 * (KP + KPB) * TS_LSTRIDE * 4 + TS_QUEUE_BYTES + 15) / 16 * 16;
   TsBarriers* bars = reinterpret_cast<TsBarriers*>(smem_dyn + BAR_OFF);
   if (threadIdx.x == 0 && (smem_u32(smem_dyn) & 1023u) != 0) __trap();     // TMA SWIZZLE_128B boxes need 1 KB alignment
 
@@ -1092,6 +1097,9 @@ struct RefineArgs {
   // error bound of the 16-bit scores, per row: qerr[row] (nullable) + *kerr_max (nullable) + eps_fixed
   const float* qerr; const float* kerr_max; float eps_fixed;
   float* thr2;                           // per uncertified row (same slot as fb_rows): threshold of the second pass
+  // diagnostics for the caller's format policy: rows whose certificate margin would not survive an error bound
+  // loose_mult times larger (fp16 -> bf16 is 8x) are counted in *loose_count
+  float loose_mult; int32_t* loose_count;
 };
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -1214,6 +1222,7 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
       a.out_scores[row * a.k + p] = lv[p];
       a.out_idx[row * a.k + p] = (li[p] == INT64_MAX) ? (int64_t)-1 : li[p] + a.idx_offset;
     }
+    if (a.exact && a.loose_count && lane == 0 && !(have_k && kth > tmax + a.loose_mult * eps)) atomicAdd(a.loose_count, 1);
     if (!certified && lane == 0) {
       const int slot = atomicAdd(a.fb_count, 1);
       a.fb_rows[slot] = (int32_t)row;
@@ -1388,7 +1397,8 @@ static bool tc_use_ts(int d, int k, int tiles_per_split) {
   return !ss_ok || tiles_per_split >= TS_MIN_TILES_PER_SPLIT;
 }
 
-static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = false) {
+// kp_req: candidate-list length asked for by the call (RAG_SIM_WIDE_LISTS -> 32; 0 = by k); the process-wide option wins
+static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = false, int kp_req = 0) {
   const TcOptions& o = tc_opts();
   TcPlan p{};
   if (tf32) {
@@ -1400,16 +1410,18 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = f
     if (!ts && p.kh == 3) p.kh = 4;          // SS instantiations: 1, 2, 4
   }
   p.kp = (k <= 10) ? 16 : 32;
-  if (o.kp == 32 && !tf32 && d <= 128) p.kp = 32;   // wider lists certify more rows of a clustered library in the first pass
+  // wider lists certify more rows of a clustered library in the first pass (d <= 128: the shared-memory budget)
+  if (!tf32 && d <= 128 && (o.kp == 32 || (o.kp == 0 && kp_req == 32))) p.kp = 32;
+  const int kp_layout = (!tf32 && d <= 128) ? 32 : p.kp;      // workspace areas are sized for the widest lists of the shape
   // shared memory: (SS: A 2*KH boxes +) NSTAGE boxes + lists + barriers + 1 KB alignment slack  <= 227 KB
   // SS: lists + meta + pending queues; TS: sorted lists + append buffers (stride 257) + 16 B alignment slack
-  const int list_bytes = ts ? 2 * p.kp * TS_LSTRIDE * 8 + TS_QUEUE_BYTES + 16 : p.kp * TC_ROWS * 8 + TC_ROWS * 4 + TC_PQ * TC_ROWS * 8;
+  const int list_bytes = ts ? (p.kp + ts_kpb(p.kp)) * TS_LSTRIDE * 8 + TS_QUEUE_BYTES + 16 : p.kp * TC_ROWS * 8 + TC_ROWS * 4 + TC_PQ * TC_ROWS * 8;
   const int a_boxes = ts ? 0 : 2 * p.kh;
   const int bar_bytes = ts ? TS_BAR_BYTES : 256;
   const int slack = ts ? 0 : 1024;           // SS aligns its window by hand; TS declares the 1 KB alignment
   const int budget = 232448 - slack - bar_bytes - list_bytes - a_boxes * TC_BOX_BYTES;
   p.nstage = budget / TC_BOX_BYTES;
-  const int cap = ts ? (p.kp == 16 ? 9 : 4) : 8;
+  const int cap = ts ? (p.kp == 16 ? 9 : 7) : 8;
   if (p.nstage > cap) p.nstage = cap;
   if (p.nstage < 2) p.nstage = 2;
   p.smem = slack + (size_t)(a_boxes + p.nstage) * TC_BOX_BYTES + list_bytes + bar_bytes;
@@ -1427,8 +1439,8 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = f
   p.off_qbf = off; off += align_up((size_t)p.n_qtiles * TC_ROWS * p.d_pad * (tf32 ? 4 : 2), 256);
   p.off_qinv = off; off += align_up((size_t)Q * 4, 256);
   p.off_qerr = off; off += align_up((size_t)Q * 4, 256);
-  p.off_ps = off; off += align_up((size_t)p.n_splits * Q * p.kp * 4, 256);
-  p.off_pi = off; off += align_up((size_t)p.n_splits * Q * p.kp * 4, 256);
+  p.off_ps = off; off += align_up((size_t)p.n_splits * Q * kp_layout * 4, 256);
+  p.off_pi = off; off += align_up((size_t)p.n_splits * Q * kp_layout * 4, 256);
   p.off_fb = off; off += align_up((size_t)Q * 4, 256);
   p.off_zero = off; off += align_up((size_t)p.n_zero * 4, 256);
   p.off_thr2 = off; off += align_up((size_t)Q * 4, 256);
@@ -1441,7 +1453,7 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = f
     if (g < 1) g = 1;
     if ((int64_t)g * p.n_splits <= 256 && g <= p.tiles_per_split / o.prepass_div) { p.pre_tiles = p.tiles_per_split / o.prepass_div; p.pre_groups = g; }
   }
-  p.off_gmax = off; off += align_up((size_t)p.pre_groups * p.n_splits * Q * 4, 256);
+  p.off_gmax = off; off += align_up((size_t)((2 * kp_layout + p.n_splits - 1) / p.n_splits) * p.n_splits * Q * 4, 256);
   p.off_thr0 = off; off += align_up((size_t)Q * 4, 256);
   // hit-queue overflow area: one slice per CTA of the largest TS launch (the second pass runs max(#SMs, query tiles) CTAs)
   const int64_t ts_ctas = std::max<int64_t>((int64_t)p.n_qtiles * p.n_splits, std::max<int64_t>(sm_count(), p.n_qtiles));
@@ -1464,11 +1476,12 @@ size_t topk_tc_workspace(int64_t Q, int64_t N, int d, int k, int mode) {
 }
 
 void topk_tc_stat_offsets(int64_t Q, int64_t N, int d, int k, int mode, size_t* out) {
-  out[0] = out[1] = 0;
+  out[0] = out[1] = out[2] = 0;
   if ((mode != RAG_SIM_BF16_REFINE && mode != RAG_SIM_F16_REFINE) || !tc_shape_ok(d, k) || Q <= 0 || N <= 0) return;
   const TcPlan p = tc_plan(Q, N, d, k, true);
   out[0] = p.off_zero;
   out[1] = p.off_zero + 4;
+  out[2] = p.off_zero + 8;
 }
 
 template <int KH, int NSTAGE, int KP, bool TF32 = false>
@@ -1499,7 +1512,7 @@ static int run_ts(const CUtensorMap& mk, const uint16_t* q_bf, const TcArgs& ta,
   if (p.kh == KH_ && p.nstage == NS_ && p.kp == KP_) \
     return ta.premax ? launch_filter_ts<KH_, NS_, KP_, true>(mk, q_bf, ta, p, grid, s) : launch_filter_ts<KH_, NS_, KP_, false>(mk, q_bf, ta, p, grid, s);
   RAG_TS_CASE(1, 9, 16) RAG_TS_CASE(2, 9, 16) RAG_TS_CASE(3, 9, 16) RAG_TS_CASE(4, 9, 16)
-  RAG_TS_CASE(1, 4, 32) RAG_TS_CASE(2, 4, 32)
+  RAG_TS_CASE(1, 7, 32) RAG_TS_CASE(2, 7, 32)
 #undef RAG_TS_CASE
   return fail(RAG_EUNSUPPORTED, "cosine_topk: no tensor-core instantiation for kh=%d nstage=%d kp=%d", p.kh, p.nstage, p.kp);
 }
@@ -1514,6 +1527,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   const bool f16 = (mode == RAG_SIM_F16 || mode == RAG_SIM_F16_REFINE);
   const bool exact = (mode == RAG_SIM_BF16_REFINE || mode == RAG_SIM_F16_REFINE);
   RAG_REQUIRE(!(flags & RAG_SIM_DOT), RAG_EUNSUPPORTED, "cosine_topk: the tensor-core modes implement cosine only");
+  RAG_REQUIRE(!(flags & ~(RAG_SIM_DOT | RAG_SIM_WIDE_LISTS)), RAG_EINVAL, "cosine_topk: unknown flag bits 0x%x", flags);
   if (tf32)
     RAG_REQUIRE(tc_shape_ok_tf32(d, k), RAG_EUNSUPPORTED,
                 "cosine_topk: the tf32 mode covers d <= 64 with k <= 26 and d <= 128 with k <= 10 (d=%d k=%d)", d, k);
@@ -1522,9 +1536,10 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
                 "cosine_topk: tensor-core modes cover d <= 128 with k <= 26 and d <= 256 with k <= 10 (d=%d k=%d)", d, k);
   RAG_REQUIRE(key_inv_norm, RAG_EINVAL, "cosine_topk: the tensor-core modes need key_inv_norm (rag_row_inv_norm_f32)");
   RAG_REQUIRE(aligned16(keys_shadow), RAG_EALIGN, "cosine_topk: the key shadow must be 16-byte aligned");
-  const TcPlan pts = tc_plan(Q, N, d, k, true, false);           // TS plan: workspace layout + the second pass
+  const int kp_req = (flags & RAG_SIM_WIDE_LISTS) ? 32 : 0;
+  const TcPlan pts = tc_plan(Q, N, d, k, true, false, kp_req);   // TS plan: workspace layout + the second pass
   const bool ts = !tf32 && tc_use_ts(d, k, pts.tiles_per_split);
-  const TcPlan p = tf32 ? tc_plan(Q, N, d, k, false, true) : (ts ? pts : tc_plan(Q, N, d, k, false, false));
+  const TcPlan p = tf32 ? tc_plan(Q, N, d, k, false, true) : (ts ? pts : tc_plan(Q, N, d, k, false, false, kp_req));
   const size_t need = tf32 ? p.total : pts.total;
   RAG_REQUIRE(ws_bytes >= need, RAG_EWORKSPACE, "cosine_topk: workspace %zu < %zu bytes", ws_bytes, need);
   RAG_REQUIRE(ws && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, RAG_EALIGN, "cosine_topk: workspace must be 256-byte aligned");
@@ -1623,6 +1638,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   r.qerr = tf32 ? nullptr : qerr;
   r.kerr_max = shadow_err;
   r.eps_fixed = TC_SLACK + (shadow_err ? 0.f : u);
+  r.loose_mult = 8.0f; r.loose_count = zero + 2;
   const int total_c = p.n_splits * p.kp;
   const int wpb = (total_c <= 1024) ? 8 : 2;                    // per-warp smem: k*12 + total*4 bytes (< 48 KB per CTA)
   int64_t blocks = (Q + wpb - 1) / wpb;

@@ -71,14 +71,22 @@ class EdgeAggregator:
         self.num_nodes = num_nodes
         self.deterministic = deterministic
         self._key = None
+        self._refs = None
         self._csr: Optional[CSRGraph] = None
 
     def csr(self, edges: Tensor, edge_norm: Tensor) -> CSRGraph:
+        # The cache entry keeps STRONG references to the tensors it was built from: a key made of addresses alone would
+        # match a different tensor that the caching allocator placed at a recycled address (a per-forward time-encoded
+        # edge_norm, equal-length edge-dropout samples) and silently reuse a stale CSR.
         key = (edges.data_ptr(), edges._version, edges.shape[0], edge_norm.data_ptr(), edge_norm._version)
-        if key != self._key:
+        if key != self._key or self._refs is None or self._refs[0] is not edges or self._refs[1] is not edge_norm:
             self._csr = CSRGraph.from_coo(edges, edge_norm, self.num_nodes, self.num_nodes, self.deterministic)
             self._key = key
+            self._refs = (edges, edge_norm)
         return self._csr
+
+    def invalidate(self) -> None:
+        self._key = self._csr = self._refs = None
 
     def __call__(self, all_emb: Tensor, edges: Tensor, edge_norm: Tensor, **epi) -> Tensor:
         return self.csr(edges, edge_norm).spmm(all_emb, **epi)

@@ -208,12 +208,12 @@ def _cosine_topk_impl(q, keys, k, key_inv_norm, keys_shadow, mode, flags, idx_of
                 "cosine_topk")
     if not want_stats:
         return scores, idx
-    offs = (C.c_size_t * 2)()
+    offs = (C.c_size_t * 3)()
     L.check(lib.rag_cosine_topk_stat_offsets(Q, N, d, k, mode, offs), "cosine_topk_stat_offsets")
     if offs[0] == 0 and offs[1] == 0:
-        stats = torch.zeros(2, dtype=torch.int32, device=q.device)
+        stats = torch.zeros(3, dtype=torch.int32, device=q.device)
     else:
-        stats = torch.stack([ws[offs[0]:offs[0] + 4].view(torch.int32)[0], ws[offs[1]:offs[1] + 4].view(torch.int32)[0]])
+        stats = ws[offs[0]:offs[0] + 12].view(torch.int32)         # the three counters are consecutive; view keeps ws alive
     return scores, idx, stats
 
 
@@ -235,9 +235,50 @@ def _(q, keys, k, key_inv_norm=None, keys_bf16=None, mode=0, flags=0, idx_offset
 def cosine_topk_with_stats(q: Tensor, keys: Tensor, k: int, key_inv_norm: Optional[Tensor] = None,
                            keys_shadow: Optional[Tensor] = None, mode: int = 0, flags: int = 0, idx_offset: int = 0,
                            shadow_err: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
-    """cosine_topk plus an int32 [2] device tensor {rows that took the second tensor-core pass, rows that fell back to the
-    fp32 kernel} (zeros for modes without a certificate)."""
+    """cosine_topk plus an int32 [3] device tensor {rows that took the second tensor-core pass, rows that fell back to the
+    fp32 kernel, rows whose certificate would fail under an 8x error bound} (zeros for modes without a certificate)."""
     return _cosine_topk_impl(q, keys, k, key_inv_norm, keys_shadow, mode, flags, idx_offset, shadow_err, True)
+
+
+def retrieve_small_supported(Q: int, N: int, d: int, k: int) -> bool:
+    return bool(L.load().rag_retrieve_small_supported(Q, N, d, k))
+
+
+def retrieve_small_workspace(Q: int, N: int, d: int, k: int, device) -> Tensor:
+    """zero-filled scratch for retrieve_small (reusable across calls of the same or smaller shape on one stream)"""
+    return torch.zeros(max(int(L.load().rag_retrieve_small_workspace(Q, N, d, k)), 256), dtype=torch.uint8, device=device)
+
+
+def retrieve_small(q: Tensor, keys: Tensor, k: int, values: Optional[Tensor], labels: Optional[Tensor], ws: Tensor,
+                   key_inv_norm: Optional[Tensor] = None, flags: int = 0):
+    """ToyGraphBase.retrieve for a small problem in ONE launch: returns (scores [Q,k], idx [Q,k], values[idx], labels[idx]).
+    All tensors CUDA + contiguous (fp32 q / keys; any 4-byte-multiple row type for values / labels); ``ws`` from
+    retrieve_small_workspace.  Host-lean on purpose: this path exists to beat launch latency."""
+    if not (q.is_cuda and keys.is_cuda and q.dtype == torch.float32 and keys.dtype == torch.float32
+            and q.is_contiguous() and keys.is_contiguous() and q.dim() == 2 and keys.dim() == 2 and q.shape[1] == keys.shape[1]):
+        raise RuntimeError("retrieve_small: contiguous CUDA float32 q [Q,d] and keys [N,d] expected (no CPU fallback)")
+    Q, d = q.shape
+    N = keys.shape[0]
+    dev = q.device
+    scores = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    ov = ol = None
+    vb = lb = 0
+    if values is not None:
+        if not values.is_contiguous():
+            raise RuntimeError("retrieve_small: values must be contiguous")
+        ov = torch.empty((Q, k) + tuple(values.shape[1:]), dtype=values.dtype, device=dev)
+        vb = _row_bytes(values)
+    if labels is not None:
+        if not labels.is_contiguous():
+            raise RuntimeError("retrieve_small: labels must be contiguous")
+        ol = torch.empty((Q, k) + tuple(labels.shape[1:]), dtype=labels.dtype, device=dev)
+        lb = _row_bytes(labels)
+    with torch.cuda.device(dev):
+        L.check(L.load().rag_retrieve_small_f32(q.data_ptr(), Q, keys.data_ptr(), _p(key_inv_norm), N, d, k, flags, _p(values), vb,
+                                                _p(labels), lb, scores.data_ptr(), idx.data_ptr(), _p(ov), _p(ol), ws.data_ptr(),
+                                                ws.numel(), _stream()), "retrieve_small")
+    return scores, idx, ov, ol
 
 
 @torch.library.custom_op("ragraph::topk_masked", mutates_args=())

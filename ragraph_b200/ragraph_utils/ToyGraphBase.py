@@ -24,20 +24,28 @@ from .. import ops
 class ToyGraphBase:
     def __init__(self, pretrain_model=None, num_class: int = 3, emb_size: int = 256, query_graph_hop: int = 3,
                  device: Optional[torch.device] = None, variant: str = "node", capacity: int = 1024,
-                 mode: Optional[int] = None, label_dtype: torch.dtype = torch.float32) -> None:
+                 mode: Optional[int] = None, label_dtype: torch.dtype = torch.float32,
+                 retrieve_num: Optional[int] = None) -> None:
         assert variant in ("node", "graph", "node_fewshot")
         self.variant = variant
         # inference-phase knobs, same names and defaults as the reference (:22-29)
         # construct-phase knobs (:17-18; graph variant RAGraph_graph/.../ToyGraphBase.py:20-21): 0 disables
         self.num_inverse_sample = 0 if variant == "graph" else 10
         self.num_augment_scale = 0 if variant == "graph" else 3
-        self.retrieve_num = num_class + 1 if variant != "graph" else min(3, num_class + 1)
+        # node: C + 1 (:22); graph / graph few-shot: min(3, C + 1) (RAGraph_graph/.../ToyGraphBase.py:25); node few-shot: a
+        # constructor argument the caller sets to 5 (RAGraph_node_fewshot/.../ToyGraphBase.py:16,22, RAGraph.py:17,41)
+        if retrieve_num is not None:
+            self.retrieve_num = int(retrieve_num)
+        else:
+            self.retrieve_num = {"node": num_class + 1, "graph": min(3, num_class + 1), "node_fewshot": 5}[variant]
         self.noise_retrieve_num = 1
         self.num_anchors = 10
         self.dis_q = 10
         self.structure_weight = 0.001 if variant == "node_fewshot" else 0.0
         self.semantic_weight = 0.999
-        self.noise_std = 0.1
+        # only the graph variants add Gaussian noise to the retrieved values, with std 0.01 (RAGraph_graph/.../ToyGraphBase.py:
+        # 27,131-134; RAGraph_graph_fewshot the same); the node variants append random rows instead and never read it
+        self.noise_std = 0.01 if variant == "graph" else 0.1
         self.toy_graph_hop = query_graph_hop - 1
         self.pretrain_model = pretrain_model
         self.mode = mode                      # None = pick per library size (see _pick_mode)
@@ -58,6 +66,10 @@ class ToyGraphBase:
         # the second tensor-core pass, rows recomputed by the fp32 kernel} (no host sync; read it when convenient)
         self.collect_stats = False
         self.last_stats: Optional[Tensor] = None
+        self._pol_free = []
+        self._policy_reset()
+        self._small_ws: Optional[Tensor] = None   # zero-filled scratch of the single-launch small-problem kernel
+        self._small_plan = {}                     # (Q, n, k) -> workspace bytes, or 0 if the shape is not covered
         self._reserve(capacity)
 
     # ---- store ---------------------------------------------------------------------------
@@ -90,6 +102,7 @@ class ToyGraphBase:
         self._class_ids, self._class_rows = None, 0
         self._keys_tf32 = None
         self._shadow16 = {}
+        self._policy_reset()
         if release:
             self._keys = self._values = self._labels = self._positions = self._inv_norm = None
             self._cap = 0
@@ -142,6 +155,11 @@ class ToyGraphBase:
         from ..sampling import InverseSampling
         from .Augmentation import Augmentation
         from .PositionAwareEncoder import PositionAwareEncoder
+        from ..csr import CSRGraph, as_dense
+        # the build's random edge rewrite, sub-adjacency extraction and position codes are dense by nature and run on toy
+        # graphs of a few dozen nodes: a CSR adjacency (what utility.process_tu_dataset returns) is densified once here
+        if isinstance(adj, CSRGraph) or (isinstance(adj, Tensor) and adj.layout != torch.strided):
+            adj = as_dense(adj)
         for aug_features, aug_adj in Augmentation.augment_graph(self.num_augment_scale, features, adj):
             # few-shot backbones expose the first GCN layer as ``encode`` (RAGraph_node_fewshot/.../ToyGraphBase.py:92)
             embed = getattr(self.pretrain_model, "encode", None) if self.variant == "node_fewshot" else None
@@ -328,16 +346,73 @@ class ToyGraphBase:
             return self._topk_large(search_keys, k)
         return self.topk_local(search_keys, k, 0)
 
+    # ---- filter-format policy of the automatic mode --------------------------------------------------------------
+    # Every tensor-core configuration returns the same exact answer; they differ in speed per data distribution (B200,
+    # 100 M x 128, profiles/r2_ab_fmt_kp_100m.jsonl): on spread-out (Gaussian) keys a bf16 filter is ~5 % faster than fp16
+    # (narrower multipliers, higher clock under the 1 kW cap: 72.3 vs 76.3 ms), on a clustered library bf16 cannot certify a
+    # single row (5.7 s per batch through the fp32 kernel) while fp16 settles it on the tensor cores (126 ms; 94 ms with
+    # 32-entry candidate lists).  A store therefore STARTS safe (fp16, 16-entry lists) and adapts from the counters each call
+    # leaves behind (read back asynchronously, never a host sync): many rows in the second pass -> wide lists; two calls in
+    # a row whose certificates would also hold under a bf16-sized error bound -> bf16; a bf16 call with second-pass rows ->
+    # back to fp16 for good.  Only large scans adapt (the format is noise below ~4 G scores per call).
+    ADAPT_MIN_SCORES = 1 << 32
+
+    def _policy_reset(self) -> None:
+        self._pol = {"fmt": L.FMT_F16, "wide": False, "locked": False, "calm": 0, "gen": 0}
+        self._pol_pending = []
+
+    def _policy_poll(self) -> None:
+        while self._pol_pending and self._pol_pending[0][0].query():
+            _, host, Q, gen, wide_ok = self._pol_pending.pop(0)
+            self._pol_free.append(host)
+            p = self._pol
+            if gen != p["gen"]:
+                continue                                    # measured under a configuration that is already history
+            n2, _, loose = (int(x) for x in host.tolist())
+            if p["fmt"] == L.FMT_BF16:
+                if n2 > 0.02 * Q:
+                    p.update(fmt=L.FMT_F16, locked=True, calm=0, gen=p["gen"] + 1)
+            elif n2 > 0.02 * Q and not p["wide"] and wide_ok:
+                p.update(wide=True, calm=0, gen=p["gen"] + 1)
+            elif n2 == 0 and loose == 0 and not p["locked"] and not p["wide"]:
+                p["calm"] += 1
+                if p["calm"] >= 2:
+                    p.update(fmt=L.FMT_BF16, calm=0, gen=p["gen"] + 1)
+            else:
+                p["calm"] = 0
+
+    def auto_state(self) -> dict:
+        """what the automatic mode currently runs (reporting)"""
+        p = self._pol
+        return {"filter": "bf16" if p["fmt"] == L.FMT_BF16 else "fp16", "wide_lists": bool(p["wide"])}
+
     def topk_local(self, search_keys: Tensor, k: int, idx_offset: int = 0) -> Tuple[Tensor, Tensor]:
         """fused similarity + top-k over the rows of THIS store; returned indices = idx_offset + local row"""
         mode = self._pick_mode(search_keys.shape[0], k)
+        Q = search_keys.shape[0]
+        flags = 0
+        adapt = self.mode is None and mode == L.SIM_F16_REFINE and Q * self._n >= self.ADAPT_MIN_SCORES
+        if adapt:
+            self._policy_poll()
+            if self._pol["fmt"] == L.FMT_BF16:
+                mode = L.SIM_BF16_REFINE
+            if self._pol["wide"]:
+                flags = L.SIM_WIDE_LISTS
         shadow, err = self._shadow(mode)
+        if not (adapt or self.collect_stats):
+            return ops.direct(ops.cosine_topk)(search_keys, self.resource_keys, k, self._inv_norm[:self._n], shadow, mode,
+                                               flags, idx_offset, err)
+        s, i, stats = ops.cosine_topk_with_stats(search_keys, self.resource_keys, k, self._inv_norm[:self._n], shadow, mode,
+                                                 flags, idx_offset, err)
         if self.collect_stats:
-            s, i, self.last_stats = ops.cosine_topk_with_stats(search_keys, self.resource_keys, k, self._inv_norm[:self._n],
-                                                               shadow, mode, 0, idx_offset, err)
-            return s, i
-        return ops.direct(ops.cosine_topk)(search_keys, self.resource_keys, k, self._inv_norm[:self._n], shadow, mode, 0,
-                                           idx_offset, err)
+            self.last_stats = stats
+        if adapt and len(self._pol_pending) < 4:
+            host = self._pol_free.pop() if self._pol_free else torch.empty(3, dtype=torch.int32).pin_memory()
+            host.copy_(stats, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pol_pending.append((ev, host, Q, self._pol["gen"], self.emb_size <= 128 and k <= 10))
+        return s, i
 
     def _topk_large(self, search_keys: Tensor, k: int, budget_bytes: int = 1 << 30) -> Tuple[Tensor, Tensor]:
         """k > RAG_MAX_K (the edge variant's vanilla configs ask for retrieve_num = 100000, i.e. most of the library,
@@ -362,10 +437,36 @@ class ToyGraphBase:
         (PositionAwareEncoder, random anchors from the CPU generator); None for the single-metric variants."""
         if search_positions is not None or self.variant != "node_fewshot" or self.structure_weight == 0.0:
             return search_positions
-        if not (isinstance(search_adj, Tensor) and search_adj.layout == torch.strided):
+        from ..csr import CSRGraph, as_dense
+        if isinstance(search_adj, CSRGraph) or (isinstance(search_adj, Tensor) and search_adj.layout != torch.strided):
+            search_adj = as_dense(search_adj)
+        if not isinstance(search_adj, Tensor):
             return None
         from .PositionAwareEncoder import PositionAwareEncoder
         return PositionAwareEncoder.encode_position_aware_code(search_adj, self.num_anchors, self.dis_q)
+
+    def _small_retrieve(self, search_keys: Tensor, k: int):
+        """The reference's real shapes (one pooled graph query against a few hundred rows, RAGraph_graph/.../ToyGraphBase.py:
+        56-87) are launch-latency problems: normalise + scores + top-k + both gathers run as ONE kernel when the shape fits
+        (Q <= 64, N <= 65 536, k <= 16) and no similarity mode was forced.  Returns (values[idx], labels[idx]) or None."""
+        if self.mode is not None or self.collect_stats or (self.variant == "node_fewshot" and self.structure_weight != 0.0):
+            return None
+        n, Q = self._n, search_keys.shape[0]
+        key = (Q, n, k)
+        need = self._small_plan.get(key)
+        if need is None:
+            ok = ops.retrieve_small_supported(Q, n, self.emb_size, k) and search_keys.dtype == torch.float32
+            need = int(L.load().rag_retrieve_small_workspace(Q, n, self.emb_size, k)) if ok else 0
+            if len(self._small_plan) > 256:
+                self._small_plan.clear()
+            self._small_plan[key] = need
+        if need == 0 or not search_keys.is_cuda:
+            return None
+        if self._small_ws is None or self._small_ws.numel() < need:
+            self._small_ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+        _, _, emb, lab = ops.retrieve_small(search_keys.contiguous(), self._keys[:n], k, self._values[:n], self._labels[:n],
+                                            self._small_ws)
+        return emb, lab
 
     def retrieve(self, search_keys: Tensor, search_adj, add_noise: bool, search_positions: Optional[Tensor] = None):
         """Same contract as the reference: returns (rag_embeddings[Q,k',d], rag_labels[Q,k',C]).
@@ -376,10 +477,14 @@ class ToyGraphBase:
             search_keys = search_keys.unsqueeze(0)
         search_positions = self.query_positions(search_adj, search_positions)
         retrieve_num = 2 * self.retrieve_num if add_noise else self.retrieve_num
-        _, topk_indices = self.topk(search_keys, retrieve_num, search_positions)
         gather_rows = ops.direct(ops.gather_rows)
-        rag_embeddings = gather_rows(self.resource_values, topk_indices)
-        rag_labels = gather_rows(self.resource_labels, topk_indices)
+        small = self._small_retrieve(search_keys, retrieve_num) if search_positions is None else None
+        if small is not None:
+            rag_embeddings, rag_labels = small
+        else:
+            _, topk_indices = self.topk(search_keys, retrieve_num, search_positions)
+            rag_embeddings = gather_rows(self.resource_values, topk_indices)
+            rag_labels = gather_rows(self.resource_labels, topk_indices)
         if add_noise:
             if self.variant == "graph":
                 noise = torch.normal(mean=0, std=self.noise_std, size=rag_embeddings.shape).to(rag_embeddings.device)
@@ -391,6 +496,18 @@ class ToyGraphBase:
                 rag_labels = torch.cat([rag_labels, gather_rows(self.resource_labels, noise_indices)], dim=1)
         return rag_embeddings, rag_labels
 
+    def gather_reduce_blend(self, idx: Tensor, reduce: int = L.REDUCE_SUM, blend_in: Optional[Tensor] = None,
+                            blend_w: float = 0.0) -> Tensor:
+        """(1 - w) * blend_in + w * reduce_k values[idx] -- one fused launch when nothing needs a gradient.  The library rows
+        carry no grad (the reference detaches them, preprompt.py:62), but ``blend_in`` does when the backbone is fine-tuned
+        (few-shot: encode() is trainable, RAGraph_node_fewshot/RAGraph.py:47-69): then only the gather + reduce runs in the
+        kernel and the convex blend is ordinary differentiable torch, so d loss / d blend_in = (1 - w) * dY flows."""
+        gather_reduce = ops.direct(ops.gather_reduce)
+        if blend_in is not None and blend_in.requires_grad and torch.is_grad_enabled():
+            rag = gather_reduce(self.resource_values, idx, reduce)
+            return blend_in * (1.0 - blend_w) + rag * blend_w
+        return gather_reduce(self.resource_values, idx, reduce, blend_in, blend_w)
+
     def retrieve_fused(self, search_keys: Tensor, k: Optional[int] = None, reduce: int = L.REDUCE_SUM,
                        blend_in: Optional[Tensor] = None, blend_w: float = 0.0):
         """The reduction every caller applies next, without the [Q,k,d] round trip: returns
@@ -400,7 +517,7 @@ class ToyGraphBase:
         k = self.retrieve_num if k is None else k
         _, idx = self.topk(search_keys, k)
         gather_reduce = ops.direct(ops.gather_reduce)
-        emb = gather_reduce(self.resource_values, idx, reduce, blend_in, blend_w)
+        emb = self.gather_reduce_blend(idx, reduce, blend_in, blend_w)
         labels = self.resource_labels if self.resource_labels.dtype == torch.float32 else self.resource_labels.float()
         lab = gather_reduce(labels, idx, L.REDUCE_MEAN)
         return emb, lab, idx

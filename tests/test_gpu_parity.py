@@ -24,7 +24,7 @@ def test_library_loaded_and_counts_launches():
     before = L.launch_count()
     ops.row_inv_norm(torch.randn(10, 8, device=DEV))
     assert L.launch_count() == before + 1
-    assert L.load().rag_abi_version() == 1
+    assert L.load().rag_abi_version() == L.ABI_VERSION
 
 
 # ------------------------------------------------------------------------------------------ gathers
@@ -488,3 +488,54 @@ def test_large_properties():
     ones = gcsr.spmm(torch.ones(n, F, device=DEV))[:, 0]
     rowsum = torch.zeros(n, device=DEV, dtype=torch.float64).index_add_(0, dst, w.double())
     assert (ones.double() - rowsum).abs().max() / rowsum.abs().max() < 1e-5
+
+
+# ---- single-launch small-problem retrieve (the reference's real shapes) ------------------------------------------------
+@pytest.mark.parametrize("Q,N,d,C,k", [(1, 480, 256, 6, 3), (1, 7, 256, 2, 3), (5, 333, 100, 3, 4), (64, 65536, 256, 3, 8),
+                                       (17, 9000, 64, 7, 16), (3, 40, 30, 2, 6), (64, 5000, 128, 3, 1)])
+def test_retrieve_small_matches_reference_calls(Q, N, d, C, k):
+    """rag_retrieve_small_f32 == F.normalize + matmul + torch.topk + values[idx] + labels[idx] (ToyGraphBase.py:47-81): index
+    sets identical up to ties within 1e-6 (fp64 arbiter), scores within 1e-5, gathered rows bit exact; int64 labels too."""
+    g = torch.Generator().manual_seed(Q * 131 + N)
+    q = torch.randn(Q, d, generator=g); keys = torch.randn(N, d, generator=g)
+    keys[N // 2] = keys[0]; keys[min(3, N - 1)] = 0.0
+    vals = torch.randn(N, d, generator=g)
+    labs = torch.nn.functional.one_hot(torch.randint(0, C, (N,), generator=g), C)           # int64, like the graph variant
+    qd, kd, vd, ld = q.cuda(), keys.cuda(), vals.cuda(), labs.cuda()
+    assert ops.retrieve_small_supported(Q, N, d, k)
+    ws = ops.retrieve_small_workspace(Q, N, d, k, "cuda")
+    for rep in range(3):                                                                   # the ticket re-arms itself
+        s, i, ev, el = ops.retrieve_small(qd, kd, k, vd, ld, ws)
+    S64 = O.cosine_similarity_f64(q.numpy(), keys.numpy())
+    ok, bad = O.topk_sets_match(i.cpu().numpy(), S64, k)
+    assert ok, bad[:5]
+    assert np.max(np.abs(s.cpu().numpy() - np.take_along_axis(S64, i.cpu().numpy(), axis=1))) < 1e-5
+    assert torch.equal(ev.cpu(), vals[i.cpu()]) and torch.equal(el.cpu(), labs[i.cpu()])
+    inv = ops.row_inv_norm(kd)
+    s2, i2, _, _ = ops.retrieve_small(qd, kd, k, None, None, ws, key_inv_norm=inv)
+    assert torch.equal(i2, i) and float((s2 - s).abs().max()) < 1e-6
+    s0, i0 = ops.cosine_topk(qd, kd, k)                                                      # fp32 kernel
+    assert float((s0 - s).abs().max()) < 2e-6
+
+
+def test_toygraphbase_small_path_equals_large_path():
+    """retrieve() through the single-launch kernel == retrieve() through topk + gathers (mode forced), graph and node variants,
+    add_noise branch included (same CPU RNG draws)."""
+    import ragraph_b200 as R
+    g = torch.Generator().manual_seed(3)
+    N, d, C = 480, 256, 6
+    keys = torch.nn.functional.normalize(torch.randn(N, d, generator=g), dim=-1).cuda()
+    vals = torch.randn(N, d, generator=g).cuda()
+    labs = torch.nn.functional.one_hot(torch.randint(0, C, (N,), generator=g), C).cuda()
+    for variant, q in (("graph", torch.randn(d, generator=g).cuda()), ("node", torch.randn(20, d, generator=g).cuda())):
+        outs = []
+        for mode in (None, L.SIM_FP32):
+            base = R.ToyGraphBase(None, C, d, 3, variant=variant, mode=mode, label_dtype=torch.int64)
+            base.add_entries(keys, vals, labs)
+            for noise in (False, True):
+                torch.manual_seed(11)
+                outs.append(base.retrieve(q, None, noise))
+        for (e_a, l_a), (e_b, l_b) in zip(outs[:2], outs[2:]):
+            assert e_a.shape == e_b.shape and l_a.dtype == l_b.dtype
+            assert torch.equal(l_a, l_b)
+            assert torch.equal(e_a, e_b)            # same CPU RNG draws (seeded above) on top of bit-exact gathers

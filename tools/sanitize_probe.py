@@ -1,0 +1,35 @@
+"""Small-shape pass through every kernel of the tensor-core retrieval path (SS filter, TS filter + pre-pass, refine, second
+pass + refine2, fp32 fallback, gathers) for compute-sanitizer:
+    compute-sanitizer --tool memcheck|racecheck|synccheck python tools/sanitize_probe.py
+Shapes are tiny so that the 10-100x sanitizer slowdown stays in seconds; results are checked against the fp32 kernel."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ragraph_b200 import _lib as L, ops
+
+dev = "cuda"
+g = torch.Generator().manual_seed(0)
+d, k = 128, 10
+cent = torch.randn(6, d, generator=g)
+N, Q = 24000, 300
+keys = (cent[torch.randint(0, 6, (N,), generator=g)] + 0.1 * torch.randn(N, d, generator=g)).to(dev)
+q = (cent[torch.randint(0, 6, (Q,), generator=g)] + 0.1 * torch.randn(Q, d, generator=g)).to(dev)
+keys[100:140] = keys[7]                                   # duplicates: ties + spill
+inv = ops.row_inv_norm(keys)
+s0, i0 = ops.cosine_topk(q, keys, k, inv)
+L.tc_set_option("prepass_min_tiles", 64)
+for mode, fmt in ((L.SIM_F16_REFINE, L.FMT_F16), (L.SIM_BF16_REFINE, L.FMT_BF16)):
+    err = torch.zeros(1, device=dev)
+    sh, _ = ops.rows_to_shadow16(keys, fmt, True, err_max=err)
+    for variant in (1, 2):
+        L.tc_set_option("variant", variant)
+        s, i, st = ops.cosine_topk_with_stats(q, keys, k, inv, sh, mode, shadow_err=err)
+        torch.cuda.synchronize()
+        assert float((s - s0).abs().max()) < 2e-6, (mode, variant)
+        print(f"mode {mode} variant {variant}: ok, pass2 rows {int(st[0])}, fp32 rows {int(st[1])}", flush=True)
+vals = torch.randn(N, d, device=dev)
+out = ops.gather_rows(vals, i0)
+assert torch.equal(out, vals[i0])
+red = ops.gather_reduce(vals, i0, 0)
+torch.cuda.synchronize()
+print("sanitize_probe done", flush=True)
