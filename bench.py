@@ -438,6 +438,9 @@ def main():
         q_host = make_queries(Q_BATCH, DIM, dev, kind=kind)
         q_dev = q_host.to(dev)
         out = {}
+        for _ in range(warmup):
+            sr.retrieve(q_dev, TOPK, copy=False)
+            torch.cuda.synchronize()        # untimed: lets the store's filter-format policy see each call's counters and settle
         # ---- parity first: the answer of the path that is about to be timed -----------------------------
         store.collect_stats = True
         emb, lab, scores, idx = sr.retrieve(q_dev, TOPK, copy=True)
@@ -465,7 +468,6 @@ def main():
         k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for _ in range(warmup):
             sr.retrieve(q_dev, TOPK, copy=False)
-            torch.cuda.synchronize()        # untimed: lets the store's filter-format policy see each call's counters and settle
         D.barrier()
         state0 = store.auto_state() if args.mode < 0 else None
         launches0 = L.launch_count()
@@ -724,18 +726,22 @@ def bench_cfg3(dev, args, peaks):
         if kind != "gauss":
             fill_library_shard(store, 0, N, d, N_CLASS, dev, kind)
         q = make_queries(Q_BATCH, d, dev, kind=kind).to(dev)
-        mode = store._pick_mode(Q_BATCH, TOPK)
-        shadow, err = store._shadow(mode)
-        s, i, st = ops.cosine_topk_with_stats(q, store.resource_keys, TOPK, store.key_inv_norm, shadow, mode, shadow_err=err)
+        for _ in range(4):                                       # lets the filter-format policy settle (untimed)
+            store.topk_local(q, TOPK)
+            torch.cuda.synchronize()
+        store.collect_stats = True
+        s, i = store.topk_local(q, TOPK)
+        store.collect_stats = False
+        st = store.last_stats.tolist()
         rows = torch.arange(0, Q_BATCH, 32, device=dev)
         s0, i0 = ops.cosine_topk(q[rows].contiguous(), store.resource_keys, TOPK, store.key_inv_norm)
         differ = (i[rows] != i0).any(dim=1)
         tie_ok = bool(((s[rows] - s0).abs().max(dim=1).values[differ] < 1e-6).all()) if bool(differ.any()) else True
         assert float((s[rows] - s0).abs().max()) < 2e-6 and tie_ok, "cfg3 parity vs the fp32 kernel failed"
-        ms = timeit_events(lambda: ops.cosine_topk(q, store.resource_keys, TOPK, store.key_inv_norm, shadow, mode, 0, 0, err),
-                           max(5, args.steps), 3)
+        state = store.auto_state()
+        ms = timeit_events(lambda: store.topk_local(q, TOPK), max(5, args.steps), 2)
         tf = 2.0 * Q_BATCH * N * d / ms / 1e9
-        out[kind] = {"ms": ms, "qps": Q_BATCH / ms * 1e3, "tflops": tf, "frac_of_peak": tf / peaks["bf16"],
+        out[kind] = {"ms": ms, "qps": Q_BATCH / ms * 1e3, "tflops": tf, "frac_of_peak": tf / peaks["bf16"], "filter": state,
                      "pass2_rows": int(st[0]), "fallback_rows": int(st[1]),
                      "parity": {"rows": int(rows.numel()), "vs": "fp32 kernel", "rows_with_tie_swaps": int(differ.sum()),
                                 "max_score_diff": float((s[rows] - s0).abs().max())}}

@@ -578,9 +578,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 //    KP-1.  A frozen threshold admits candidates at the rate it had when it was set, so a row is compacted about once
 //    per doubling of the keys seen, instead of one replace-min list update per candidate.
 constexpr int TS_LSTRIDE = TC_ROWS + 1;
-// append-buffer length for a list of KP entries: 32-entry lists keep a 16-entry buffer -- the 33 KB that saves are two more
-// pipeline stages (7 instead of 4 + 1), and a compaction every 16 candidates is what the 16-entry lists do anyway
-__host__ __device__ constexpr int ts_kpb(int kp) { return kp == 32 ? 16 : kp; }
+// append-buffer length for a list of KP entries.  Measured (B200, 100 M x 128, profiles/r2_ab_fmt_kp_100m.jsonl): a 16-entry
+// buffer under 32-entry lists buys three more pipeline stages (7 instead of 4) but doubles the compactions -- 107.6 ms vs
+// 85.8 ms on Gaussian keys, 121 vs 93.9 ms clustered: selection work, not pipeline depth, is what wide lists cost.
+__host__ __device__ constexpr int ts_kpb(int kp) { return kp; }
 constexpr int TS_QN = 16;                 // hit-queue entries per epilogue warp
 constexpr int TS_QSTRIDE = 36;            // 32 scores + first key index + (owner lane | valid columns << 8), 16 B aligned
 constexpr int TS_QUEUE_BYTES = TC_EPI_WARPS * TS_QN * TS_QSTRIDE * 4;
@@ -1421,7 +1422,7 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = f
   const int slack = ts ? 0 : 1024;           // SS aligns its window by hand; TS declares the 1 KB alignment
   const int budget = 232448 - slack - bar_bytes - list_bytes - a_boxes * TC_BOX_BYTES;
   p.nstage = budget / TC_BOX_BYTES;
-  const int cap = ts ? (p.kp == 16 ? 9 : 7) : 8;
+  const int cap = ts ? (p.kp == 16 ? 9 : 4) : 8;
   if (p.nstage > cap) p.nstage = cap;
   if (p.nstage < 2) p.nstage = 2;
   p.smem = slack + (size_t)(a_boxes + p.nstage) * TC_BOX_BYTES + list_bytes + bar_bytes;
@@ -1512,7 +1513,7 @@ static int run_ts(const CUtensorMap& mk, const uint16_t* q_bf, const TcArgs& ta,
   if (p.kh == KH_ && p.nstage == NS_ && p.kp == KP_) \
     return ta.premax ? launch_filter_ts<KH_, NS_, KP_, true>(mk, q_bf, ta, p, grid, s) : launch_filter_ts<KH_, NS_, KP_, false>(mk, q_bf, ta, p, grid, s);
   RAG_TS_CASE(1, 9, 16) RAG_TS_CASE(2, 9, 16) RAG_TS_CASE(3, 9, 16) RAG_TS_CASE(4, 9, 16)
-  RAG_TS_CASE(1, 7, 32) RAG_TS_CASE(2, 7, 32)
+  RAG_TS_CASE(1, 4, 32) RAG_TS_CASE(2, 4, 32)
 #undef RAG_TS_CASE
   return fail(RAG_EUNSUPPORTED, "cosine_topk: no tensor-core instantiation for kh=%d nstage=%d kp=%d", p.kh, p.nstage, p.kp);
 }

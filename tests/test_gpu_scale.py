@@ -105,7 +105,7 @@ def test_production_dispatch_equals_full_fp32_scan_d128(lib128, n):
     """cfg4: the 1-GPU library and the 2 / 4 / 8-GPU shard sizes (prefixes of the same key matrix), automatic dispatch"""
     keys, q, shadow, err, inv = lib128
     st, swaps = _check(keys[:n], q, shadow[:n], err, inv[:n])
-    assert st == [0, 0], f"Gaussian keys must certify in the first pass: {st}"
+    assert st[:2] == [0, 0], f"Gaussian keys must certify in the first pass: {st}"
 
 
 @pytest.mark.parametrize("kind", ["gauss", "clustered", "dup5"])
@@ -117,7 +117,7 @@ def test_cfg3_10m_x_256_equals_full_fp32_scan(kind):
     shadow, _ = ops.rows_to_shadow16(keys, L.FMT_F16, True, err_max=err)
     st, swaps = _check(keys, q, shadow, err, ops.row_inv_norm(keys), n_rows=128, n_stock=16)
     if kind == "gauss":
-        assert st == [0, 0], st
+        assert st[:2] == [0, 0], st
     else:
         assert st[1] == 0, f"clustered rows must be settled by the second tensor-core pass, not the fp32 kernel: {st}"
 
