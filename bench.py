@@ -511,7 +511,8 @@ def main():
                 checksum[0] += float(host[b]["sc"][0, 0])        # ... (reads the pinned buffer)
                 main_stream.wait_event(done[b])                  # ... and its device block may be overwritten from here on
             q = q_host.to(dev, non_blocking=True)
-            emb, lab, sc, ix = sr.retrieve(q, TOPK, copy=False)
+            # copy i-1 must be complete before finish(i) releases the peers into step i+1 (same result-block parity)
+            emb, lab, sc, ix = sr.retrieve(q, TOPK, copy=False, wait_event=done[(i - 1) % nb])
             ready = torch.cuda.Event()
             ready.record(main_stream)
             with torch.cuda.stream(copy_stream):

@@ -213,7 +213,13 @@ extern "C" int rag_sharded_finish(const float* local_scores, const int64_t* loca
   a.target = (unsigned long long)step * XC_CTAS;
   a.out_s = out_scores; a.out_i = out_idx;
   const size_t smem = (size_t)(XC_THREADS / 32) * k * 12;
-  sharded_finish_kernel<<<XC_CTAS, XC_THREADS, smem, (cudaStream_t)stream>>>(a);
+  // The kernel's CTAs wait for one another (and for the peers) inside the launch: they must all be resident at once.
+  // A cooperative launch makes the driver guarantee that -- or fail the launch -- instead of leaving it to "128 CTAs
+  // surely fit 148 SMs", which a kernel running beside it on another stream could turn into a 10 s spin-and-trap.
+  void* kargs[] = {const_cast<XchgArgs*>(&a)};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(sharded_finish_kernel), dim3(XC_CTAS), dim3(XC_THREADS),
+                                              kargs, smem, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(sharded_finish_kernel)");
   RAG_LAUNCH_OK("sharded_finish_kernel");
   return RAG_OK;
 }

@@ -111,17 +111,30 @@ class ShardedRetriever:
         w = self._pws
         if w is not None and w.key[0] >= Q and w.key[1] >= k and w.key[2:] == (rba, rbb):
             return w
+        grp = self.group if self.group is not None else dist.group.WORLD
         try:
-            grp = self.group if self.group is not None else dist.group.WORLD
+            import torch.distributed._symmetric_memory  # noqa: F401  (absent from older torch builds)
+        except ImportError as e:
+            return self._no_p2p(e)
+        try:
             # every rank takes this branch for the same call (same Q, k, row sizes), so the rendezvous matches
             self._pws = _PeerWorkspace(grp, device, max(Q, w.key[0] if w else 0), max(k, w.key[1] if w else 0),
                                        self.world, self.rank, rba, rbb)
-        except Exception as e:                      # no P2P / symmetric memory on this box: NCCL formulation
-            import warnings
-            warnings.warn(f"ragraph_b200: peer-memory exchange unavailable ({e!r}); using the NCCL all-gather path")
-            self._p2p_disabled = True
-            self._pws = None
+        except (RuntimeError, NotImplementedError) as e:
+            # what symmetric-memory allocation / rendezvous raises on a box without peer access (no NVLink P2P, MIG, ...):
+            # fall back to the NCCL formulation, loudly.  Anything else (a bug in this library, a bad argument) propagates.
+            from ._lib import RagError
+            if isinstance(e, RagError):
+                raise
+            return self._no_p2p(e)
         return self._pws
+
+    def _no_p2p(self, e) -> None:
+        import warnings
+        warnings.warn(f"ragraph_b200: peer-memory exchange unavailable ({e!r}); using the NCCL all-gather path")
+        self._p2p_disabled = True
+        self._pws = None
+        return None
 
     def _finish_p2p(self, s: Tensor, i: Tensor, k: int, copy: bool):
         import ctypes as C
@@ -187,10 +200,13 @@ class ShardedRetriever:
         sel = own.reshape((1,) + tuple(idx.shape) + (1,) * (out.dim() - idx.dim()))
         return torch.gather(allr, 0, sel.expand((1,) + tuple(out.shape))).squeeze(0)
 
-    def retrieve(self, q: Tensor, k: Optional[int] = None, copy: bool = True, events=None):
+    def retrieve(self, q: Tensor, k: Optional[int] = None, copy: bool = True, events=None, wait_event=None):
         """(rag_embeddings[Q,k,d], rag_labels[Q,k,C], scores, idx) for the sharded library.
         copy=False returns views of the peer-memory result block (valid until the next-but-one call).
-        events = (start, end) CUDA events recorded around the LOCAL fused top-k (bench roofline)."""
+        events = (start, end) CUDA events recorded around the LOCAL fused top-k (bench roofline).
+        wait_event: a CUDA event the stream waits for between the local top-k and the finish kernel.  A caller that reads
+        the copy=False views of call i on ANOTHER stream (an overlapped device-to-host copy) must pass that read's event to
+        call i+1: finishing call i+1 is what lets the peers start call i+2, whose rows land in the block call i used."""
         if q.dim() == 1:
             q = q.unsqueeze(0)
         k = self.store.retrieve_num if k is None else k
@@ -199,6 +215,8 @@ class ShardedRetriever:
         s, i = self._local(q, k)
         if events:
             events[1].record()
+        if wait_event is not None:
+            torch.cuda.current_stream().wait_event(wait_event)
         if self._p2p_usable(q):
             out = self._finish_p2p(s, i, k, copy)
             if out is not None:

@@ -39,7 +39,7 @@ def main():
     full = R.ToyGraphBase(None, C, d, 3, device=dev, capacity=N, mode=L.SIM_FP32)
     full.add_entries(keys.to(dev), vals.to(dev), labs_f.to(dev))
     checked = 0
-    for mode in (L.SIM_BF16_REFINE, L.SIM_FP32):
+    for mode in (L.SIM_F16_REFINE, L.SIM_BF16_REFINE, L.SIM_FP32):
         for labs in (labs_f, labs_i):
             sr = R.ShardedRetriever(make(labs, mode), N)
             os.environ["RAG_P2P"] = "0"
@@ -74,6 +74,37 @@ def main():
             keep = e1.clone()
             sr.retrieve(torch.randn(128, d, generator=g).to(dev), 10, copy=False)
             assert torch.equal(e1, keep)
+    # ---- clustered library (second tensor-core pass on every rank) + the overlapped device-to-host copy pattern of
+    #      bench.py's e2e loop: results of call i are read on a side stream while call i+1 runs; call i+1 gets the
+    #      read's event (wait_event) so that no peer can overwrite the block being read -----------------------------
+    cent = torch.randn(16, d, generator=g)
+    ckeys = torch.nn.functional.normalize(cent[torch.randint(0, 16, (N,), generator=g)] + 0.1 * torch.randn(N, d, generator=g), dim=-1)
+    st = R.ToyGraphBase(None, C, d, 3, device=dev, capacity=hi - lo, mode=L.SIM_F16_REFINE)
+    st.add_entries(ckeys[lo:hi].to(dev), vals[lo:hi].to(dev), labs_f[lo:hi].to(dev))
+    sr = R.ShardedRetriever(st, N)
+    side = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    Qc, kc, steps = 512, 10, 6
+    qs = [(cent[torch.randint(0, 16, (Qc,), generator=g)] + 0.1 * torch.randn(Qc, d, generator=g)).to(dev) for _ in range(steps)]
+    host = [torch.empty((Qc, kc, d)).pin_memory() for _ in range(steps)]
+    host_i = [torch.empty((Qc, kc), dtype=torch.int64).pin_memory() for _ in range(steps)]
+    done = [None] * steps
+    keep = []
+    for t in range(steps):
+        emb, lab, s, i = sr.retrieve(qs[t], kc, copy=False, wait_event=done[t - 1] if t else None)
+        ready = torch.cuda.Event(); ready.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            host[t].copy_(emb, non_blocking=True); host_i[t].copy_(i, non_blocking=True)
+            done[t] = torch.cuda.Event(); done[t].record(side)
+        keep.append((emb, i))
+    torch.cuda.synchronize()
+    S64 = None
+    for t in range(steps):
+        ok, bad = O.topk_sets_match(host_i[t].numpy(), O.cosine_similarity_f64(qs[t].cpu(), ckeys), kc)
+        assert ok, ("clustered", t, bad[:3])
+        assert torch.equal(host[t].view(torch.int32), vals[host_i[t]].view(torch.int32)), ("overlapped copy", t)
+        checked += 1
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
