@@ -289,6 +289,16 @@ RAG_API int rag_scatter_softmax_f32(const float* src, const int64_t* index, int6
                             float span, const float* range_dev, const float* base, float mix_a, float mix_b, float* out,
                             void* workspace, size_t workspace_bytes, rag_stream_t stream);
 
+/* ---- 8f-3: edge-variant negative sampling on the device ---------------------------------- */
+/* out[m * n_neg + j] = an item drawn uniformly from [0, num_items) that is NOT in user users[m]'s history row
+ * hist_items[hist_rowptr[u] .. hist_rowptr[u+1]) (int64, SORTED ascending within the row) -- the distribution of the
+ * rejection loop in get_train_batch (RAGraph_edge/utils/dataloader.py:140-152: np.random.randint until the item is not
+ * in train_user_set[user]); counter-based RNG keyed by (seed, slot, attempt): the same seed gives the same draws, the
+ * numpy stream of the reference is not reproduced.  -1 if no admissible item turned up in 16 384 attempts. */
+RAG_API int rag_negative_sample(const int64_t* users, int64_t M, int32_t n_neg, const int64_t* hist_rowptr,
+                        const int64_t* hist_items, int64_t num_users, int64_t num_items, uint64_t seed, int64_t* out,
+                        rag_stream_t stream);
+
 /* ---- a9: downstream prompt + class-prototype scores (downprompt.py) ---------------------- */
 /* out[n,d] = act(w[d] * x[n,d]); act 0 = identity (RAGraph_graph/downprompt.py:197-209), 1 = ELU
  * (RAGraph_node/downprompt.py:118-130).  out may alias x. */

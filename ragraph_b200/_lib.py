@@ -65,6 +65,7 @@ SIGNATURES = {
     "rag_dense_fill_csr": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p]),
     "rag_scatter_softmax_workspace": (_sz, [_i64]),
     "rag_scatter_softmax_f32": (C.c_int, [_p, _p, _i64, _i64, _f32, _f32, _p, _p, _f32, _f32, _p, _p, _sz, _p]),
+    "rag_negative_sample": (C.c_int, [_p, _i64, _i32, _p, _p, _i64, _i64, C.c_uint64, _p, _p]),
     "rag_prompt_act_f32": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _p]),
     "rag_prototype_scores_f32": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _i32, _f32, _i32, _p, _p]),
 }

@@ -183,3 +183,28 @@ def rating_topk(user_emb: Tensor, item_emb: Tensor, k: int, hist_rowptr: Tensor,
     int64[nnz] hold the batch users' history lists back to back.  Returns item indices int64 [B, k] like
     ``torch.topk(batch_pred, k)[1]``; the [B, n_items] rating matrix and its .cpu() copy never exist."""
     return ops.topk_masked(user_emb, item_emb, k, hist_rowptr, hist_items, L.SIM_DOT)[1]
+
+
+def history_csr(train_user_dict, num_users: int, device) -> tuple:
+    """{user: [items]} (the reference's ``train_user_dict``, utils/dataloader.py:62-75) -> (hist_rowptr int64 [U+1],
+    hist_items int64 [nnz] sorted within each user) on ``device``: the form ``negative_sampling`` and ``rating_topk`` take."""
+    counts = torch.zeros(num_users, dtype=torch.int64)
+    rows = []
+    for u in range(num_users):
+        items = sorted(set(int(i) for i in train_user_dict.get(u, ())))
+        counts[u] = len(items)
+        rows.extend(items)
+    rowptr = torch.zeros(num_users + 1, dtype=torch.int64)
+    torch.cumsum(counts, 0, out=rowptr[1:])
+    return rowptr.to(device), torch.tensor(rows, dtype=torch.int64).to(device)
+
+
+def negative_sampling(users: Tensor, hist_rowptr: Tensor, hist_items: Tensor, num_items: int, n: int = 1,
+                      seed: Optional[int] = None) -> Tensor:
+    """``negative_sampling(user_item, train_user_set, n)`` of get_train_batch (RAGraph_edge/utils/dataloader.py:140-152) on the
+    device: for every user of the batch, n items uniform over the items outside the user's training history -- one kernel
+    instead of a Python rejection loop per pair.  Returns int64 [M * n] in the reference's order (user-major).  ``seed``
+    defaults to a draw from torch's CPU generator, so ``torch.manual_seed`` makes a run reproducible."""
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return ops.negative_sample(users, hist_rowptr, hist_items, num_items, n, seed).reshape(-1)

@@ -594,5 +594,21 @@ def _(x, proto, mode=0, w=None, act=0, eps=1e-8):
     return x.new_empty((x.shape[0], proto.shape[0]))
 
 
+def negative_sample(users: Tensor, hist_rowptr: Tensor, hist_items: Tensor, num_items: int, n_neg: int = 1,
+                    seed: int = 0) -> Tensor:
+    """int64 [M, n_neg]: per (user, slot) one item uniform over [0, num_items) outside the user's history row (CSR of SORTED
+    int64 item ids) -- get_train_batch's rejection sampler (RAGraph_edge/utils/dataloader.py:140-152) on the device."""
+    _need_cuda(users, hist_rowptr, hist_items)
+    if users.dtype != torch.int64 or hist_rowptr.dtype != torch.int64 or hist_items.dtype != torch.int64:
+        raise RuntimeError("negative_sample: users, hist_rowptr and hist_items must be int64")
+    users, hist_rowptr, hist_items = users.contiguous(), hist_rowptr.contiguous(), hist_items.contiguous()
+    M = users.numel()
+    out = torch.empty((M, n_neg), dtype=torch.int64, device=users.device)
+    with torch.cuda.device(users.device):
+        L.check(L.load().rag_negative_sample(_p(users), M, n_neg, _p(hist_rowptr), _p(hist_items), hist_rowptr.numel() - 1,
+                                             num_items, seed & 0xFFFFFFFFFFFFFFFF, _p(out), _stream()), "negative_sample")
+    return out
+
+
 def gather_oob_count() -> int:
     return int(L.load().rag_gather_oob_count())

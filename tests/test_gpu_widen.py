@@ -307,3 +307,103 @@ def test_fewshot_helpers_vs_oracle():
     assert torch.equal(pred[clear], ref_sim.argmax(1)[clear])
     loss = F_.fewshot_predict_loss(cu(support_logits), cu(support_labels), cu(logits), cu(torch.randint(0, C, (n,), generator=g)))
     assert bool(torch.isfinite(loss))
+
+
+# ---- 8f rank 3: host preprocessing on the device ------------------------------------------------------------------------
+def test_negative_sampling_distribution_and_exclusion():
+    """Device negative sampler vs the reference's rejection loop (RAGraph_edge/utils/dataloader.py:140-152): never an item
+    of the user's history, uniform over the rest (chi-square against the exact complement distribution, and against an
+    oracle run of the reference loop with numpy's generator), deterministic per seed, user-major order."""
+    import numpy as np
+    from ragraph_b200 import edge as E
+    rng = np.random.default_rng(0)
+    U, I = 50, 200
+    hist = {u: sorted(rng.choice(I, size=int(rng.integers(0, 150)), replace=False).tolist()) for u in range(U)}
+    hist[7] = list(range(I - 1))                                     # a user with ONE admissible item
+    rowptr, items = E.history_csr(hist, U, DEV)
+    users = torch.arange(U, device=DEV).repeat_interleave(400)
+    out = E.negative_sampling(users, rowptr, items, I, n=3, seed=123).reshape(-1, 3).cpu().numpy()
+    assert out.shape == (U * 400, 3) and out.min() >= 0 and out.max() < I
+    again = E.negative_sampling(users, rowptr, items, I, n=3, seed=123).reshape(-1, 3).cpu().numpy()
+    assert np.array_equal(out, again)
+    other = E.negative_sampling(users, rowptr, items, I, n=3, seed=124).reshape(-1, 3).cpu().numpy()
+    assert not np.array_equal(out, other)
+    uu = users.cpu().numpy()
+    for u in range(U):
+        got = out[uu == u].reshape(-1)
+        assert not set(got.tolist()) & set(hist[u]), u
+        allowed = np.setdiff1d(np.arange(I), np.array(hist[u], dtype=np.int64))
+        cnt = np.array([(got == a).sum() for a in allowed], dtype=np.float64)
+        exp = got.size / allowed.size
+        if allowed.size > 1:
+            chi2 = ((cnt - exp) ** 2 / exp).sum()
+            assert chi2 < allowed.size + 6 * np.sqrt(2 * allowed.size) + 10, (u, chi2, allowed.size)   # ~6 sigma
+    assert set(out[uu == 7].reshape(-1).tolist()) == {I - 1}
+    # the reference loop itself (numpy generator) on one user: same support, same uniformity
+    np.random.seed(0)
+    ref = []
+    for _ in range(1200):
+        while True:
+            neg = np.random.randint(low=0, high=I, size=1)[0]
+            if neg not in set(hist[3]):
+                break
+        ref.append(neg)
+    assert set(ref) <= set(np.setdiff1d(np.arange(I), hist[3]).tolist())
+
+
+def test_process_graph_batch_on_device_matches_reference_dense():
+    """process_graph_batch with CUDA inputs: CSR of D^-1/2 (A + I) D^-1/2 == the reference's dense block-diagonal matrix
+    (oracle restatement of process_tu_dataset, RAGraph_node/ragraph_utils/utility.py:30-72), and propagating over it equals
+    propagating over the dense adjacency."""
+    import numpy as np
+    from ragraph_b200 import process_graph_batch
+    rng = np.random.default_rng(1)
+    xs, eis = [], []
+    for n in (7, 12, 1, 30):
+        xs.append(torch.tensor(rng.random((n, 9)), dtype=torch.float32))
+        m = max(1, 2 * n)
+        e = rng.integers(0, n, size=(2, m))
+        eis.append(torch.tensor(np.concatenate([e, e[::-1]], axis=1)))           # symmetric, duplicates allowed
+    f0, adj0, l0 = O.process_tu_arrays([x.numpy() for x in xs], [e.numpy() for e in eis], 6)
+    feats, csr, labs = process_graph_batch([x.to(DEV) for x in xs], [e.to(DEV) for e in eis], 6)
+    assert feats.is_cuda and csr.rowptr.is_cuda
+    assert torch.equal(feats.cpu(), f0) and torch.equal(labs.cpu(), l0)
+    assert float((csr.to_dense().cpu() - adj0).abs().max()) < 1e-6
+    x = torch.randn(adj0.shape[0], 32)
+    got = R.Propagation.aggregate_k_hop_features(csr, x.to(DEV), 2).cpu()
+    ref = O.aggregate_k_hop_features(adj0, x, 2)
+    assert O.rel_err(got.numpy(), ref.numpy()) < 1e-5
+
+
+def test_fewshot_finetune_step_backpropagates_into_the_encoder(golden):
+    """The few-shot fine-tune optimises the backbone too (encode() = convs[0] is trainable, Adam over rag_model.parameters(),
+    RAGraph_node_fewshot/RAGraph.py:41-69): loss.backward() must reach the encoder through propagate -> blend -> decode.
+    The blend with the retrieved rows runs in torch when the encoder output requires grad (gather_reduce has no autograd
+    formula and the library rows carry none); gradient == the all-torch restatement of the same forward."""
+    g = golden("fewshot_forward_node")
+    m = _fewshot_model(g, False).train()
+    emb = torch.nn.Parameter(cu(g["emb_q"]).clone())            # stands for the trainable first GCN layer's output
+    m.pretrain_model.emb = emb
+    adj, logits, sp = cu(g["adj"]), cu(g["mean_fewshot_logits"]), cu(g["search_positions"])
+    out = m(None, adj, logits, sp)
+    loss = (out * torch.linspace(-1, 1, out.numel(), device=DEV).reshape(out.shape)).sum()
+    loss.backward()
+    assert emb.grad is not None and bool(torch.isfinite(emb.grad).all()) and float(emb.grad.abs().sum()) > 0
+    assert m.pretrain_model.layer.fc.weight.grad is not None
+    # all-torch restatement (dense adjacency, advanced indexing) of the same forward for the gradient
+    emb2 = cu(g["emb_q"]).clone().requires_grad_(True)
+    base = m.toy_graph_base
+    with torch.no_grad():
+        _, idx = base.topk(emb2.detach(), base.retrieve_num, sp)
+    a = adj / adj.sum(dim=1, keepdim=True)
+    qe = emb2
+    for _ in range(m.query_graph_hop):
+        qe = torch.relu(a @ qe)
+    hidden = qe * (1 - m.retrieve_weight) + base.resource_values[idx].sum(1) * m.retrieve_weight
+    layer = m.pretrain_model.layer
+    dec = torch.nn.functional.prelu(adj @ (hidden @ layer.fc.weight.t()) + layer.bias, layer.act.weight)
+    rag_logits = logits[torch.argmax(base.resource_labels[idx], dim=-1)].mean(1)
+    out2 = dec * (1 - m.label_weight) + rag_logits * m.label_weight
+    assert float((out2 - out).abs().max()) < 1e-5
+    (out2 * torch.linspace(-1, 1, out.numel(), device=DEV).reshape(out.shape)).sum().backward()
+    assert float((emb2.grad - emb.grad).abs().max()) < 1e-4 * float(emb2.grad.abs().max())
