@@ -716,10 +716,14 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
   constexpr int NBUF = (512 - A_COLS) / TC_BN;        // accumulator ring: 3 (d <= 128) or 2 (d <= 256)
   constexpr uint32_t A_COL0 = NBUF * TC_BN;
   static_assert(NBUF >= 2 && NBUF <= 3, "accumulator ring");
-  // issuer warps: 2 with the ring of 3; with NBUF = 2 (one buffer per row block, d > 128) consecutive tiles of a row
-  // block are serialised through ONE barrier, which only a single in-order waiter may follow by parity -- and a tile
-  // is 2048+ tensor cycles there, so one issuer keeps up
-  constexpr int NISS = (NBUF == 3) ? 2 : 1;
+  // Two issuer warps.  Ring of 3 (d <= 128): they take alternate key tiles.  Ring of 2 (d > 128: one buffer per row
+  // block): consecutive tiles of a row block are serialised through ONE barrier pair, which only a single in-order party
+  // may follow by parity -- so there the issuers split by ROW BLOCK (issuer r issues row block r of every tile and is the
+  // only producer of tmem_full[r] / consumer of tmem_empty[r]); a key stage is released when BOTH have committed their
+  // MMAs on it (empty barriers count 2).  Measured (r2_variant_ab.jsonl, 10 M x 256, epilogue disabled): one issuer has 32
+  // MMAs + 6 commits + 6 waits per 2048-cycle tile to get through and ran the pipe at 1 439 TFLOP/s against 1 631 at d = 128.
+  constexpr int NISS = 2;
+  constexpr bool ROWSPLIT = (NBUF == 2);
   static_assert(NSTAGE >= 2 * KH && NSTAGE <= 12, "row-block-major MMA order holds a tile's stages for the whole tile");
   // Offsets are taken from the extern array itself (no integer round trip), so every list / queue access below stays
   // in the shared address space (LDS/STS, not generic LD/ST).  The dynamic window starts 1 KB-aligned when the kernel
@@ -762,7 +766,7 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
   if (warp == TC_EPI_WARPS && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
     mbar_init(&bars->a_full, TC_EPI_WARPS);
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], ROWSPLIT ? 2 : 1); }
     for (int b = 0; b < NBUF; ++b)
       for (int r = 0; r < 2; ++r) { mbar_init(&bars->tmem_full[b][r], 1); mbar_init(&bars->tmem_empty[b][r], TC_EPI_WARPS / 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -806,9 +810,9 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
       tc_fence_after();
       const uint32_t b_addr = smem_u32(sB);
       const uint32_t idesc = a.idesc;
-      int s = mw * KH; uint32_t ph = 0;
+      int s = ROWSPLIT ? 0 : mw * KH; uint32_t ph = 0;
       while (s >= NSTAGE) { s -= NSTAGE; ph ^= 1; }
-      for (int t = mw; t < n_my_tiles; t += NISS) {
+      for (int t = ROWSPLIT ? 0 : mw; t < n_my_tiles; t += ROWSPLIT ? 1 : NISS) {
         const bool tr3 = TC_TRACE_ON(a) && blockIdx.x == 0 && (unsigned)(t - a.trace_t0) < 256u;
         unsigned int* t3 = g_tc_trace3 + 16 * (tr3 ? (t - a.trace_t0) : 0);
         if (tr3) t3[0] = (unsigned int)clock64();
@@ -823,8 +827,7 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
           }
           if (tr3) t3[2] = (unsigned int)clock64();
         }
-#pragma unroll
-        for (int rb = 0; rb < 2; ++rb) {
+        for (int rb = ROWSPLIT ? mw : 0; rb < (ROWSPLIT ? mw + 1 : 2); ++rb) {
           // use u = 2t + rb takes buffer u % NBUF; its previous user was use u - NBUF (row block (u - NBUF) & 1,
           // that row block's k'-th visit of the buffer): wait until its epilogue has drained it
           const uint32_t u = 2u * (uint32_t)t + (uint32_t)rb;
@@ -858,7 +861,7 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
         if (tr3) t3[10] = (unsigned int)clock64();
         if (TC_TRACE_ON(a) && blockIdx.x == 0 && (unsigned)(t - a.trace_t0) < 512u) g_tc_trace[4 * (t - a.trace_t0) + 1] = clock64();
         // hop over the other issuer's tile: KH stages
-        if (NISS == 2) {
+        if (!ROWSPLIT) {
           s += KH;
           if (s >= NSTAGE) { s -= NSTAGE; ph ^= 1; }
         }
@@ -901,6 +904,7 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
     float thr = (!PRE && a.thr0 && grow < Qn) ? a.thr0[grow] : -INFINITY;
     if (thr > -INFINITY && !a.thr_exact) thr = (thr > 0.f) ? thr * (1.0f - 1e-6f) : thr * (1.0f + 1e-6f) - 1e-30f;
     if (grow >= Qn) thr = INFINITY;                         // padding rows of the last query tile never produce a hit
+    if (a.debug == 4) thr = INFINITY;                       // RAG_DIAG experiment: filter runs, no hit is ever taken
     const int64_t crow0 = (int64_t)qtile * TC_ROWS;         // compact (second pass) / plain global row of CTA row 0
     // pre-pass state: running maximum of the current tile group
     float gm = -INFINITY;
@@ -962,7 +966,7 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
             if (grow < a.Q) a.gmax[((int64_t)split * a.pre_groups + gi) * a.Q + grow] = gm;
             gm = -INFINITY; ++gi; g_end += g_tiles;
           }
-        } else if (a.debug == 0) {
+        } else if (a.debug == 0 || a.debug == 4) {
           // fast path (registers only): four chunk maxima against the row threshold, ONE warp vote per tile
           const float c0 = chunk_max32(va), c1 = chunk_max32(vb), c2 = chunk_max32(vc), c3 = chunk_max32(vd);
           const bool h0 = c0 > thr, h1 = c1 > thr, h2 = c2 > thr, h3 = c3 > thr;

@@ -10,7 +10,7 @@ import json, os, sys
 os.environ["RAG_DIAG"] = "1"      # this tool uses the library's diagnostic switches (RAG_TC_DEBUG / trace / ...)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from ragraph_b200 import ops
+from ragraph_b200 import ops, _lib as L
 
 dev, Q, k = "cuda", 4096, 10
 
@@ -37,10 +37,10 @@ def run(N, d):
     inv = ops.row_inv_norm(keys); shadow = ops.rows_to_bf16(keys, True)
     flop = 2.0 * Q * N * d
     res = {}
-    for variant in ("ss", "ts"):
-        os.environ["RAG_TC_VARIANT"] = variant
+    for variant in VARIANTS:
+        L.tc_set_option("variant", {"ss": 1, "ts": 2}[variant])
         out = {"N": N, "d": d, "Q": Q, "k": k, "variant": variant}
-        for name, mode, dbg in (("exact_mode3", 3, None), ("raw_mode2", 2, None), ("mma_only", 2, "1"), ("mma_tmemld", 2, "2")):
+        for name, mode, dbg in (("exact_mode3", 3, None), ("raw_mode2", 2, None), ("mma_only", 2, "1"), ("mma_tmemld", 2, "2"), ("filter_no_hits", 2, "4")):
             if dbg is None:
                 os.environ.pop("RAG_TC_DEBUG", None)
             else:
@@ -50,12 +50,17 @@ def run(N, d):
         os.environ.pop("RAG_TC_DEBUG", None)
         res[variant] = ops.cosine_topk(q, keys, k, key_inv_norm=inv, keys_bf16=shadow, mode=3)
         print(json.dumps(out), flush=True)
-    same = all(bool(torch.equal(res["ss"][j], res["ts"][j])) for j in (0, 1))
-    print(json.dumps({"N": N, "d": d, "ss_equals_ts_mode3": same}), flush=True)
-    os.environ.pop("RAG_TC_VARIANT", None)
+    if len(res) == 2:
+        same = all(bool(torch.equal(res["ss"][j], res["ts"][j])) for j in (0, 1))
+        print(json.dumps({"N": N, "d": d, "ss_equals_ts_mode3": same}), flush=True)
+    L.tc_set_option("variant", -1)
 
+
+VARIANTS = ("ss", "ts")
 
 if __name__ == "__main__":
+    if "--ts" in sys.argv:
+        VARIANTS = ("ts",); sys.argv.remove("--ts")
     args = [int(x) for x in sys.argv[1:]]
     cfgs = list(zip(args[0::2], args[1::2])) or [(12_500_000, 128), (10_000_000, 256)]
     for N, d in cfgs:
