@@ -656,16 +656,20 @@ __device__ __forceinline__ void ts_spill_row(const float* ps, const int32_t* pi,
 // Serve one queued hit (all 32 lanes): lane j takes score j of the 32-score chunk, compares it with the owner row's
 // current threshold, and the candidates append themselves at ballot-derived slots of the owner's buffer; a full buffer
 // is compacted on the spot.  Returns the owner's new (threshold, pending count); `owner` = the owner lane.
-struct TsServed { float thr; int np; int owner; };
+struct TsServed { float thr; int np; int owner; float pmin; };
+// order-preserving float <-> int map (an involution), so that redux.sync's integer minimum is a float minimum
+__device__ __forceinline__ int f32_ordered(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float f32_unordered(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 template <int KP>
 __device__ __forceinline__ TsServed ts_serve_entry(const float* ev, int key0, int meta, float* ls, int32_t* li, float* ps,
-                                                   int32_t* pi, int wrow0, float thr, int npend, int lane, const TcArgs& a,
-                                                   int64_t crow0) {
+                                                   int32_t* pi, int wrow0, float thr, int npend, float pmin, int lane,
+                                                   const TcArgs& a, int64_t crow0) {
   constexpr int KPB = ts_kpb(KP);
   const int L = meta & 31, nv = meta >> 8;
   const float val = ev[lane];
   float thr_l = __shfl_sync(0xffffffffu, thr, L);
   int np = __shfl_sync(0xffffffffu, npend, L);
+  float pm = __shfl_sync(0xffffffffu, pmin, L);             // smallest score in the owner row's append buffer
   bool cand = val > thr_l && lane < nv;                     // columns >= nv are TMA zero fill past the library end
   const int orow = wrow0 + L;
   while (true) {
@@ -677,6 +681,7 @@ __device__ __forceinline__ TsServed ts_serve_entry(const float* ev, int key0, in
       ps[pos * TS_LSTRIDE + orow] = val;
       pi[pos * TS_LSTRIDE + orow] = key0 + lane;
     }
+    pm = fminf(pm, f32_unordered(__reduce_min_sync(0xffffffffu, fit ? f32_ordered(val) : 0x7fffffff)));
     np = min(np + __popc(cm), KPB);
     cand = cand && !fit;
     if (__ballot_sync(0xffffffffu, cand) == 0) break;
@@ -684,9 +689,18 @@ __device__ __forceinline__ TsServed ts_serve_entry(const float* ev, int key0, in
     if (a.collect) ts_spill_row(ps, pi, orow, KPB, lane, a, crow0 + orow);
     else thr_l = ts_compact_row<KP>(ls, li, ps, pi, orow, KPB, lane);
     np = 0;
+    pm = INFINITY;
     cand = cand && val > thr_l;
   }
-  return TsServed{thr_l, np, L};
+  // Tighten the threshold WITHOUT compacting: the (KP - np) best list entries together with the np pending candidates are
+  // KP distinct keys, every one of them >= min(ls[KP-1-np], pm) -- so the row's KP-th best is at least that.  A frozen
+  // threshold admits ~KP candidates per doubling of the keys seen; this one rises with every candidate and roughly halves the
+  // candidates a row takes over a stream (each costs this warp-serial serve).  An unfilled list holds -inf: no change.
+  if (!a.collect && np > 0) {
+    const float lsv = (np < KP) ? ls[(KP - 1 - np) * TS_LSTRIDE + orow] : INFINITY;
+    thr_l = fmaxf(thr_l, fminf(lsv, pm));
+  }
+  return TsServed{thr_l, np, L, pm};
 }
 __device__ __forceinline__ float chunk_max32(const uint32_t (&v)[32]) {
   float m1[11];
@@ -907,6 +921,7 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
     if (a.debug == 4) thr = INFINITY;                       // RAG_DIAG experiment: filter runs, no hit is ever taken
     const int64_t crow0 = (int64_t)qtile * TC_ROWS;         // compact (second pass) / plain global row of CTA row 0
     // pre-pass state: running maximum of the current tile group
+    float pmin = INFINITY;                                  // smallest score among this row's pending candidates
     float gm = -INFINITY;
     int gi = 0;
     const int g_tiles = PRE ? (n_my_tiles + a.pre_groups - 1) / a.pre_groups : 0;
@@ -919,8 +934,8 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
     auto process_one = [&]() {
       const float* ev = q_mine + (qhead % TS_QN) * TS_QSTRIDE;
       const TsServed r = ts_serve_entry<KP>(ev, __float_as_int(ev[32]), __float_as_int(ev[33]), list_s, list_i, pq_s, pq_i, wrow0,
-                                            thr, npend, lane, a, crow0);
-      if (lane == r.owner) { npend = r.np; thr = r.thr; }
+                                            thr, npend, pmin, lane, a, crow0);
+      if (lane == r.owner) { npend = r.np; thr = r.thr; pmin = r.pmin; }
       ++qhead;
       __syncwarp();
     };
@@ -932,6 +947,11 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
       // idle time is selection time: while the next accumulator is not ready, work off queued hits; the extra pass
       // t == n_my_tiles drains what is left (one call site keeps the kernel small)
       if (qhead != qtail) {
+        // Keep half of the queue free before the accumulator is pulled into registers: a tile's hits then always fit, and
+        // the parking path below (~2 300 cycles per hit: 16 KB to global memory and back) stays the rare case.  Measured
+        // (profiles/r2_ts_trace_12m5_before.txt): on a 10 851-tile stream the queue sat at 14-16 of 16 entries for thousands of
+        // tiles -- every hit overflowed, the warp fell further behind and never found the idle time that drains the queue.
+        while (qtail - qhead > (unsigned)(TS_QN / 2)) process_one();
         const uint32_t full_addr = smem_u32(&bars->tmem_full[buf][rb]);
         while (qhead != qtail && (t == n_my_tiles || !__any_sync(0xffffffffu, mbar_test(full_addr, full_par)))) process_one();
       }
@@ -1008,8 +1028,8 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
                   const int L = __ffs(m) - 1;
                   m &= m - 1;
                   const TsServed r = ts_serve_entry<KP>(ov + L * TC_BN + c * 32, tile_key0 + c * 32, L | (nvc << 8), list_s, list_i,
-                                                        pq_s, pq_i, wrow0, thr, npend, lane, a, crow0);
-                  if (lane == r.owner) { npend = r.np; thr = r.thr; }
+                                                        pq_s, pq_i, wrow0, thr, npend, pmin, lane, a, crow0);
+                  if (lane == r.owner) { npend = r.np; thr = r.thr; pmin = r.pmin; }
                   __syncwarp();
                 }
               }

@@ -50,12 +50,12 @@ def tf32():
         q = torch.randn(Q, d, generator=g, device=DEV)
         inv = ops.row_inv_norm(keys)
         sh32, sh16 = ops.rows_to_tf32(keys), ops.rows_to_bf16(keys)
-        os.environ["RAG_TC_VARIANT"] = "ss"
+        L.tc_set_option("variant", 1)
         res = {}
         for name, mode, sh in (("tf32", L.SIM_TF32, sh32), ("bf16", L.SIM_BF16, sh16), ("exact", L.SIM_BF16_REFINE, sh16)):
             ms = timeit(lambda: ops.cosine_topk(q, keys, k, inv, sh, mode), 5, 2)
             res[name] = (ms, ops.cosine_topk(q, keys, k, inv, sh, mode))
-        os.environ.pop("RAG_TC_VARIANT", None)
+        L.tc_set_option("variant", -1)
         ex = res["exact"][1][1]
         rec = {n: float((res[n][1][1].unsqueeze(2) == ex.unsqueeze(1)).any(2).float().mean()) for n in ("tf32", "bf16")}
         err = {n: float((res[n][1][0] - res["exact"][1][0]).abs().max()) for n in ("tf32", "bf16")}

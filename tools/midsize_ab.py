@@ -5,7 +5,7 @@
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from ragraph_b200 import ops
+from ragraph_b200 import ops, _lib as L
 
 dev = "cuda"
 SHAPES = [(4096, 240_000, 64, 10, "edge variant batch (modules/RAGraph.py:298-324)"),
@@ -34,11 +34,11 @@ for Q, N, d, k, what in SHAPES:
     inv = ops.row_inv_norm(keys); shadow = ops.rows_to_bf16(keys, True)
     out = {"Q": Q, "N": N, "d": d, "k": k, "what": what}
     out["fp32_ms"] = round(med(lambda: ops.cosine_topk(q, keys, k, key_inv_norm=inv)), 4)
-    for name, env in (("ss", {"RAG_TC_VARIANT": "ss"}), ("ts", {"RAG_TC_VARIANT": "ts"}),
-                      ("ts_pre64", {"RAG_TC_VARIANT": "ts", "RAG_TC_PREPASS_MIN_TILES": "64"})):
-        for kk in ("RAG_TC_VARIANT", "RAG_TC_PREPASS_MIN_TILES"):
-            os.environ.pop(kk, None)
-        os.environ.update(env)
+    for name, env in (("ss", {"variant": 1}), ("ts", {"variant": 2}), ("ts_pre64", {"variant": 2, "prepass_min_tiles": 64})):
+        for kk in ("variant", "prepass_min_tiles"):
+            L.tc_set_option(kk, -1)
+        for kk, vv in env.items():
+            L.tc_set_option(kk, vv)
         try:
             out[name + "_ms"] = round(med(lambda: ops.cosine_topk(q, keys, k, key_inv_norm=inv, keys_bf16=shadow, mode=3)), 4)
         except Exception as e:

@@ -17,7 +17,7 @@ for (Q, N, d, k) in [(256, 4096, 128, 10), (300, 9000, 64, 10), (300, 9000, 256,
     S = torch.nn.functional.normalize(q.double(), dim=-1) @ torch.nn.functional.normalize(keys.double(), dim=-1).T
     ref_s, ref_i = S.topk(k, dim=1)
     for variant, swap in (("ss", "0"), ("ts", "0"), ("ts", "1")):
-        os.environ["RAG_TC_VARIANT"] = variant; os.environ["RAG_TS_SWAP"] = swap
+        L.tc_set_option("variant", {"ss": 1, "ts": 2}[variant]); os.environ["RAG_TS_SWAP"] = swap
         try:
             s, i = ops.cosine_topk(q, keys, k, key_inv_norm=inv, keys_bf16=shadow, mode=L.SIM_BF16)
             torch.cuda.synchronize()
