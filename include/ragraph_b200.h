@@ -254,6 +254,12 @@ RAG_API int rag_csr_spmm_f32(const void* rowptr, int32_t ptr_is_64, const int32_
                      int64_t n_rows, int64_t n_src, int64_t nnz, const float* X, int32_t F,
                      uint32_t epilogue, const float* bias, const float* alpha, const float* blend_in,
                      float blend_w, const float* accum_in, float* Y, rag_stream_t stream);
+/* Feature-sliced schedule of rag_csr_spmm_f32.  When X is far larger than the 126 MB L2 (>= 512 MB) and source rows are
+ * reused (nnz >= 8 n_src), the call runs one launch per 32-float column slice of X / Y (row-major in and out, no workspace):
+ * the slice's rows of the frequently used sources stay in L2 between their uses, the (col, val) stream is re-read per slice.
+ * Same results up to the fp32 order of the partial sums.  Tuning / test hook: "slice" = -1 auto, 0 never, 32 / 64 / 128
+ * forced width; "l2_hints" = 0/1 (evict_last on the gathers, evict_first on the streams).  RAG_EINVAL for unknown names. */
+RAG_API int rag_spmm_set_option(const char* name, int32_t value);
 
 /* CSR construction on the device (no host round trip).
  * COO (edges[E,2] int64: [:,0]=src, [:,1]=dst as in modules/RAGraph.py:22-24) -> CSR by dst.

@@ -264,6 +264,19 @@ struct TcArgs {
   const int32_t* row_map; const int32_t* n_rows_dev;
   int collect; int thr_exact;
   float* spill_s; int32_t* spill_i; int32_t* spill_cnt; int spill_cap;
+  // ---- cross-split threshold sharing (TS kernel, main pass) ----
+  // The key splits of a query row only need what can reach the row's GLOBAL top k, but a CTA sees one split.  Every
+  // candidate a CTA accepts is mirrored into pool[(row * n_splits + split) * pool_slots + slot] (slot = its position in the
+  // append buffer: one key per slot, distinct keys in distinct slots at all times); the CTAs past the workers
+  // (blockIdx >= n_qtiles * n_splits: the SMs the (query tile, split) grid leaves idle) sweep the pool, take the k-th
+  // largest published score of a row -- a lower bound of the row's final k-th best 16-bit score, whatever subset of the
+  // candidates is visible -- and publish gthr[row] = that - g_margin(row); the workers fold gthr into their thresholds
+  // every few tiles.  A word of 0 means "nothing yet" (the prologue clears pool and gthr).  part_thr[split][row] = the
+  // threshold a CTA ended with (refine: every key the split did not list scores <= it).
+  uint32_t* pool; uint32_t* gthr; float* part_thr; int32_t* done;
+  int pool_slots; int n_mergers; int g_k; int g_sleep_div;
+  const float* g_qerr; const float* g_kerr; float g_eps_fixed; int g_exact;
+  uint32_t* hit_count;             // nullable diagnostic: (lane, chunk) hits queued by all epilogue warps of the launch
   int trace;                       // RAG_TC_DEBUG=3 or RAG_TC_TRACE=1: CTA 0 stamps clock64 at pipeline events (g_tc_trace)
   int trace_t0;                    // RAG_TC_TRACE_T0: first traced tile (window of 512)
   int no_tma;                      // RAG_TC_NOTMA=1 (experiment): the producer arrives without loading keys (garbage operands)
@@ -663,13 +676,14 @@ __device__ __forceinline__ float f32_unordered(int i) { return __int_as_float(i 
 template <int KP>
 __device__ __forceinline__ TsServed ts_serve_entry(const float* ev, int key0, int meta, float* ls, int32_t* li, float* ps,
                                                    int32_t* pi, int wrow0, float thr, int npend, float pmin, int lane,
-                                                   const TcArgs& a, int64_t crow0) {
+                                                   const TcArgs& a, int64_t crow0, int split, float gmargin) {
   constexpr int KPB = ts_kpb(KP);
   const int L = meta & 31, nv = meta >> 8;
   const float val = ev[lane];
   float thr_l = __shfl_sync(0xffffffffu, thr, L);
   int np = __shfl_sync(0xffffffffu, npend, L);
   float pm = __shfl_sync(0xffffffffu, pmin, L);             // smallest score in the owner row's append buffer
+  const float mg = __shfl_sync(0xffffffffu, gmargin, L);    // see below: what the shared bound keeps under the k-th best
   bool cand = val > thr_l && lane < nv;                     // columns >= nv are TMA zero fill past the library end
   const int orow = wrow0 + L;
   while (true) {
@@ -680,6 +694,9 @@ __device__ __forceinline__ TsServed ts_serve_entry(const float* ev, int key0, in
     if (fit) {
       ps[pos * TS_LSTRIDE + orow] = val;
       pi[pos * TS_LSTRIDE + orow] = key0 + lane;
+      // TcArgs::pool.  The shared bound is (k-th largest published score) - margin and thr_l >= it, so a score <= thr_l +
+      // margin cannot raise that k-th largest: only the others are worth a global store (dense clusters: very few)
+      if (a.pool && val > thr_l + mg) a.pool[((crow0 + orow) * a.n_splits + split) * KPB + pos] = __float_as_uint(val);
     }
     pm = fminf(pm, f32_unordered(__reduce_min_sync(0xffffffffu, fit ? f32_ordered(val) : 0x7fffffff)));
     np = min(np + __popc(cm), KPB);
@@ -687,7 +704,7 @@ __device__ __forceinline__ TsServed ts_serve_entry(const float* ev, int key0, in
     if (__ballot_sync(0xffffffffu, cand) == 0) break;
     __syncwarp();                                           // buffer full with candidates left: compact the row, go on
     if (a.collect) ts_spill_row(ps, pi, orow, KPB, lane, a, crow0 + orow);
-    else thr_l = ts_compact_row<KP>(ls, li, ps, pi, orow, KPB, lane);
+    else thr_l = fmaxf(thr_l, ts_compact_row<KP>(ls, li, ps, pi, orow, KPB, lane));   // (a shared bound may sit above the list)
     np = 0;
     pm = INFINITY;
     cand = cand && val > thr_l;
@@ -718,6 +735,77 @@ __device__ __forceinline__ void queue_put(float* entry, const uint32_t (&v)[32],
 #pragma unroll
   for (int j = 0; j < 8; ++j) e4[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   *reinterpret_cast<int2*>(entry + 32) = make_int2(key0, meta);
+}
+
+// ---- cross-split threshold sharing: the sweep run by the CTAs past the worker grid (TcArgs::pool) -------------------
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// One warp per query row and sweep: the row's n_splits * pool_slots published words (<= 32 * NREG) go to registers, the
+// k-th largest is found by removing the maximum (one instance: equal scores of distinct keys count separately) k times.
+// The workers never wait for this: a late, stale or missing gthr only costs them hits, never correctness, and the loop
+// ends when every worker CTA has counted itself in *done (or at once, when the workers already finished).
+template <int NREG>
+__device__ void ts_merger_loop(const TcArgs& a, int n_workers) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int words = a.n_splits * a.pool_slots;
+  const int64_t first = (int64_t)(blockIdx.x - n_workers) * nw + warp, stride = (int64_t)a.n_mergers * nw;
+  const float kerr = a.g_kerr ? __ldg(a.g_kerr) : 0.f;
+  const unsigned long long t_begin = clock64();
+  while (true) {
+    const int done = (int)ld_relaxed_u32(reinterpret_cast<const uint32_t*>(a.done));
+    for (int64_t row = first; row < a.Q; row += stride) {
+      const uint32_t* pr = a.pool + row * words;
+      float v[NREG];
+#pragma unroll
+      for (int t = 0; t < NREG; ++t) {
+        const int w = lane + 32 * t;
+        const uint32_t bits = (w < words) ? ld_relaxed_u32(pr + w) : 0u;
+        v[t] = bits ? __uint_as_float(bits) : -INFINITY;
+      }
+      float kth = -INFINITY;
+      for (int it = 0; it < a.g_k; ++it) {
+        float m = v[0];
+#pragma unroll
+        for (int t = 1; t < NREG; ++t) m = fmaxf(m, v[t]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        kth = m;
+        if (m == -INFINITY) break;
+        int mine = -1;
+#pragma unroll
+        for (int t = NREG - 1; t >= 0; --t) mine = (v[t] == m) ? t : mine;
+        const unsigned who = __ballot_sync(0xffffffffu, mine >= 0);
+        if (lane == __ffs(who) - 1) {
+#pragma unroll
+          for (int t = 0; t < NREG; ++t) if (t == mine) v[t] = -INFINITY;
+        }
+      }
+      if (lane == 0 && kth > -INFINITY) {
+        // exact modes: refine needs every key whose 16-bit score is within 2 eps of the k-th best (TcArgs::pool); raw
+        // modes: one notch below, so that keys tying with the k-th best are still taken
+        float g;
+        if (a.g_exact) g = kth - (2.0f * ((a.g_qerr ? __ldg(a.g_qerr + row) : 0.f) + kerr + a.g_eps_fixed) + 1e-6f);
+        else g = (kth > 0.f) ? kth * (1.0f - 1e-6f) : kth * (1.0f + 1e-6f) - 1e-30f;
+        const uint32_t old = a.gthr[row];                       // only this warp ever writes the word
+        if (g != 0.f && (old == 0u || g > __uint_as_float(old))) st_relaxed_u32(a.gthr + row, __float_as_uint(g));
+      }
+    }
+    if (done >= n_workers) break;
+    const unsigned long long el = clock64() - t_begin;
+    if (el > TC_TIMEOUT_CYCLES) __trap();
+    // Candidates arrive at a rate ~ 1/t, so the value of a fresh bound decays the same way: sleep a fixed fraction of the
+    // time elapsed between sweeps (an always-spinning sweep costs power the tensor pipe wants under the board's cap)
+    if (a.g_sleep_div > 0) {
+      unsigned long long ns = el / (unsigned long long)a.g_sleep_div;        // cycles ~ ns at 1-2 GHz
+      __nanosleep((unsigned)(ns > 100000ull ? 100000ull : ns));
+    }
+  }
 }
 
 // Epilogue: a warp pulls its whole 32 x 128 accumulator slice into registers (4 x tcgen05.ld.x32, one wait) and hands
@@ -769,6 +857,13 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
     const int n_splits = (a.n_tiles + tiles_per_split - 1) / tiles_per_split;
     if ((int)blockIdx.x >= n_qtiles * n_splits) return;
     Qn = n;
+  }
+  if constexpr (!PRE) {
+    if (a.n_mergers > 0 && (int)blockIdx.x >= a.n_qtiles * a.n_splits) {     // (uniform per CTA, before any barrier / TMEM)
+      if (a.n_splits * a.pool_slots <= 160) ts_merger_loop<5>(a, a.n_qtiles * a.n_splits);
+      else ts_merger_loop<16>(a, a.n_qtiles * a.n_splits);
+      return;
+    }
   }
   const int qtile = blockIdx.x % n_qtiles;
   const int split = blockIdx.x / n_qtiles;
@@ -922,6 +1017,7 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
     const int64_t crow0 = (int64_t)qtile * TC_ROWS;         // compact (second pass) / plain global row of CTA row 0
     // pre-pass state: running maximum of the current tile group
     float pmin = INFINITY;                                  // smallest score among this row's pending candidates
+    float gmargin = 0.f;                                    // cross-split sharing: k-th best minus this = the shared bound
     float gm = -INFINITY;
     int gi = 0;
     const int g_tiles = PRE ? (n_my_tiles + a.pre_groups - 1) / a.pre_groups : 0;
@@ -934,12 +1030,21 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
     auto process_one = [&]() {
       const float* ev = q_mine + (qhead % TS_QN) * TS_QSTRIDE;
       const TsServed r = ts_serve_entry<KP>(ev, __float_as_int(ev[32]), __float_as_int(ev[33]), list_s, list_i, pq_s, pq_i, wrow0,
-                                            thr, npend, pmin, lane, a, crow0);
+                                            thr, npend, pmin, lane, a, crow0, split, gmargin);
       if (lane == r.owner) { npend = r.np; thr = r.thr; pmin = r.pmin; }
       ++qhead;
       __syncwarp();
     };
+    // cross-split bound (TcArgs::pool): read every 4th tile, folded in one iteration later (the load's latency is off the
+    // tile loop's critical path); padding rows keep thr = +inf
+    uint32_t gbits = 0u;
+    const bool g_on = !PRE && a.gthr != nullptr && grow < Qn;
+    if (g_on && a.g_exact) gmargin = 2.0f * ((a.g_qerr ? __ldg(a.g_qerr + grow) : 0.f) + (a.g_kerr ? __ldg(a.g_kerr) : 0.f) + a.g_eps_fixed) + 1e-6f;
     for (int t = 0; t <= n_my_tiles; ++t) {
+      if (g_on) {
+        if (gbits) thr = fmaxf(thr, __uint_as_float(gbits));
+        if ((t & 3) == 0) gbits = ld_relaxed_u32(a.gthr + grow);
+      }
       // use u = 2t + rb -> buffer u % NBUF; this row block's (t / 3)-th visit of it (ring of 3), t-th (ring of 2)
       const uint32_t u = 2u * (uint32_t)t + (uint32_t)rb;
       const uint32_t buf = (NBUF == 2) ? (u & 1u) : (u % 3u);
@@ -1028,7 +1133,7 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
                   const int L = __ffs(m) - 1;
                   m &= m - 1;
                   const TsServed r = ts_serve_entry<KP>(ov + L * TC_BN + c * 32, tile_key0 + c * 32, L | (nvc << 8), list_s, list_i,
-                                                        pq_s, pq_i, wrow0, thr, npend, pmin, lane, a, crow0);
+                                                        pq_s, pq_i, wrow0, thr, npend, pmin, lane, a, crow0, split, gmargin);
                   if (lane == r.owner) { npend = r.np; thr = r.thr; pmin = r.pmin; }
                   __syncwarp();
                 }
@@ -1060,11 +1165,13 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
         else ts_compact_row<KP>(list_s, list_i, pq_s, pq_i, wrow0 + L, np, lane);
       }
     }
+    if (!PRE && a.hit_count && lane == 0) atomicAdd(a.hit_count, qtail);
     if (!PRE && !a.collect && grow < a.Q) {
       float* ps = a.part_s + ((int64_t)split * a.Q + grow) * KP;
       int32_t* pi = a.part_i + ((int64_t)split * a.Q + grow) * KP;
 #pragma unroll
       for (int p = 0; p < KP; ++p) { ps[p] = list_s[p * TS_LSTRIDE + row]; pi[p] = list_i[p * TS_LSTRIDE + row]; }
+      if (a.part_thr) a.part_thr[(int64_t)split * a.Q + grow] = thr;
     }
   }
 
@@ -1075,6 +1182,7 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+  if (!PRE && a.n_mergers > 0 && threadIdx.x == 0) atomicAdd(a.done, 1);   // lets the sweeping CTAs go (TcArgs::pool)
 }
 
 // ---- pre-pass threshold: thr0[row] = kp-th largest of the row's G group maxima ---------------------------
@@ -1119,6 +1227,7 @@ struct RefineArgs {
   float* out_scores; int64_t* out_idx;
   int32_t* fb_rows; int32_t* fb_count;   // uncertified rows (exact only)
   const float* thr0;                     // nullable: pre-pass bound; keys never listed score <= thr0[row] (16-bit score)
+  const float* part_thr;                 // nullable: [n_splits][Q] threshold each split ended with (cross-split sharing)
   // error bound of the 16-bit scores, per row: qerr[row] (nullable) + *kerr_max (nullable) + eps_fixed
   const float* qerr; const float* kerr_max; float eps_fixed;
   float* thr2;                           // per uncertified row (same slot as fb_rows): threshold of the second pass
@@ -1176,6 +1285,11 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
     }
     tmax = warp_max(tmax);
     if (a.thr0) tmax = fmaxf(tmax, __ldg(a.thr0 + row));
+    if (a.part_thr) {
+      float tp = -INFINITY;
+      for (int sp = lane; sp < a.n_splits; sp += 32) tp = fmaxf(tp, __ldg(a.part_thr + (size_t)sp * a.Q + row));
+      tmax = fmaxf(tmax, warp_max(tp));
+    }
     __syncwarp();
     // ---- pass 2 ------------------------------------------------------------------------------------
     float prev = INFINITY;
@@ -1364,9 +1478,12 @@ struct TcPlan {
   size_t smem;
   size_t off_qbf, off_qinv, off_qerr, off_ps, off_pi, off_fb, off_zero, off_thr2, off_fb2, off_gmax, off_thr0, off_ovf,
       off_spill_s, off_spill_i, off_f32, total;
+  int64_t n_zero_share;               // ... + gthr + candidate pool, when the call runs the cross-split sweep
   int64_t n_zero;                     // 32-bit words cleared by the prologue: {pass-2 row count, fp32 row count, pad} + spill counters
   int spill_cap;
   int pre_tiles, pre_groups;          // threshold pre-pass (0 tiles = off)
+  // cross-split threshold sharing (TcArgs::pool): sweeping CTAs on the SMs the worker grid leaves idle (0 = off)
+  int n_mergers; size_t off_gthr, off_pool, off_pthr;
 };
 constexpr int TC_ZERO_HDR = 64;       // words in front of the per-row spill counters
 
@@ -1378,6 +1495,9 @@ struct TcOptions {
   int prepass_div = 64;
   int kp = 0;                         // 0 auto, 16 / 32 = candidate-list length per (row, split) where the shape allows
   int pass2 = 1;                      // 0: uncertified rows go straight to the fp32 kernel (the round-1 behaviour)
+  int gshare = 1;                     // cross-split threshold sharing on the idle SMs (TcArgs::pool); 0 = off
+  int gshare_ctas = 4;                // at most this many sweeping CTAs
+  int gshare_sleep = 0;               // sweeps sleep elapsed / this between rounds (0 = spin)
 };
 static TcOptions tc_env_defaults() {
   TcOptions o;
@@ -1387,6 +1507,7 @@ static TcOptions tc_env_defaults() {
   if (const char* e = getenv("RAG_TC_PREPASS_DIV")) { if (atoi(e) >= 4) o.prepass_div = atoi(e); }
   if (const char* e = getenv("RAG_TC_KP")) { if (atoi(e) == 16 || atoi(e) == 32) o.kp = atoi(e); }
   if (const char* e = getenv("RAG_TC_PASS2")) o.pass2 = (e[0] == '0') ? 0 : 1;
+  if (const char* e = getenv("RAG_TC_GSHARE")) o.gshare = (e[0] == '0') ? 0 : 1;
   return o;
 }
 static TcOptions& tc_opts() {
@@ -1394,16 +1515,24 @@ static TcOptions& tc_opts() {
   return o;
 }
 
+constexpr int TC_MAX_K_WIDE_FWD = 128;
 // SS kernel shapes (query tile resident in shared memory)
 static bool tc_shape_ok_ss(int d, int k) {
   if (d < 1 || k < 1) return false;
-  if (d <= 128) return k <= 26;
+  if (d <= 128) return k <= TC_MAX_K_WIDE_FWD;
   if (d > 192 && d <= 256) return k <= 10;        // 128 KB of resident queries leave room for 16-entry lists only
   return false;
 }
 // TS kernel shapes (query tile resident in tensor memory): d <= 256; k' = 16 slots per (row, split) for k <= 10,
 // 32 for k <= 26 (d <= 128 only: 128 KB of lists + append buffers leave 4 pipeline stages, d > 128 needs 8)
-bool tc_shape_ok(int d, int k) { return d >= 1 && d <= 256 && k >= 1 && (k <= 10 || (k <= 26 && d <= 128)); }
+// k in (26, 128] (d <= 128; the edge variant's vanilla phase retrieves 50, RAGraph_edge/modules/RAGraph.py:36-38): no
+// longer lists -- MORE KEY SPLITS.  The exact top k lies in the union of the per-split top-32 lists unless one split holds
+// more than 32 of them, and the refine certificate (k-th exact score > every full list's minimum + eps) detects exactly
+// that case and sends the row through the second pass; the planner makes the lists of a row hold >= 4k entries together
+// (n_splits >= 4k / 32, CTAs run in waves when that exceeds the SM count), so on spread-out keys a split sees k / n_splits
+// of the winners on average and the certificate margin is the gap between the k-th and the (32 n_splits)-th best score.
+constexpr int TC_MAX_K_WIDE = TC_MAX_K_WIDE_FWD;
+bool tc_shape_ok(int d, int k) { return d >= 1 && d <= 256 && k >= 1 && (k <= 10 || (k <= TC_MAX_K_WIDE && d <= 128)); }
 // tf32 (SS kernel only): an fp32 operand row is twice as wide as a bf16 one, so d <= 64 has the bf16 d <= 128 budget
 // (k <= 26) and d <= 128 the bf16 d = 256 budget (128 KB of resident queries, 16-entry lists, k <= 10)
 bool tc_shape_ok_tf32(int d, int k) { return d >= 1 && k >= 1 && ((d <= 64 && k <= 26) || (d <= 128 && k <= 10)); }
@@ -1454,12 +1583,22 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = f
   p.n_tiles = (int)((N + TC_BN - 1) / TC_BN);
   int s = sm_count() / p.n_qtiles;
   if (s < 1) s = 1;
+  if (k > 26 && s * p.kp < 4 * k) s = (4 * k + p.kp - 1) / p.kp;     // wide k: the lists of a row hold >= 4k entries together
   if (s > p.n_tiles) s = p.n_tiles;
   p.tiles_per_split = (p.n_tiles + s - 1) / s;
   p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   int64_t sc = ((int64_t)1 << 26) / (Q > 0 ? Q : 1);
   p.spill_cap = (int)(sc > TC_SPILL_MAX ? TC_SPILL_MAX : (sc < 64 ? 64 : sc));
+  // cross-split sharing: needs idle SMs next to the worker grid, a long stream, and a row's published words in the sweep's
+  // registers (<= 512); the zero block is then [header | spill counters Q | gthr Qpad | pool Qpad * S * kp].  The workspace
+  // reserve depends on the shape only (not on options), so offsets are the same for every call of a shape.
+  const int64_t Qpad = (int64_t)p.n_qtiles * TC_ROWS;
+  const bool share_shape = ts && !tf32 && p.n_splits > 1 && p.n_splits * kp_layout <= 512 && sm_count() > p.n_qtiles * p.n_splits;
+  p.n_mergers = 0;
+  if (share_shape && o.gshare && p.tiles_per_split >= o.prepass_min_tiles)
+    p.n_mergers = std::min(o.gshare_ctas, sm_count() - p.n_qtiles * p.n_splits);
   p.n_zero = TC_ZERO_HDR + Q;
+  p.n_zero_share = TC_ZERO_HDR + Q + Qpad + Qpad * p.n_splits * p.kp;
   size_t off = 0;
   p.off_qbf = off; off += align_up((size_t)p.n_qtiles * TC_ROWS * p.d_pad * (tf32 ? 4 : 2), 256);
   p.off_qinv = off; off += align_up((size_t)Q * 4, 256);
@@ -1467,7 +1606,10 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = f
   p.off_ps = off; off += align_up((size_t)p.n_splits * Q * kp_layout * 4, 256);
   p.off_pi = off; off += align_up((size_t)p.n_splits * Q * kp_layout * 4, 256);
   p.off_fb = off; off += align_up((size_t)Q * 4, 256);
-  p.off_zero = off; off += align_up((size_t)p.n_zero * 4, 256);
+  p.off_zero = off; off += align_up((size_t)(TC_ZERO_HDR + Q + (share_shape ? Qpad + Qpad * p.n_splits * kp_layout : 0)) * 4, 256);
+  p.off_gthr = p.off_zero + (size_t)(TC_ZERO_HDR + Q) * 4;
+  p.off_pool = p.off_gthr + (size_t)Qpad * 4;
+  p.off_pthr = off; off += share_shape ? align_up((size_t)p.n_splits * Q * 4, 256) : 0;
   p.off_thr2 = off; off += align_up((size_t)Q * 4, 256);
   p.off_fb2 = off; off += align_up((size_t)Q * 4, 256);
   // threshold pre-pass (TS kernel): 1/64 of every split, worthwhile once a split has >= 1024 tiles; G = n_splits * groups
@@ -1558,7 +1700,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
                 "cosine_topk: the tf32 mode covers d <= 64 with k <= 26 and d <= 128 with k <= 10 (d=%d k=%d)", d, k);
   else
     RAG_REQUIRE(tc_shape_ok(d, k), RAG_EUNSUPPORTED,
-                "cosine_topk: tensor-core modes cover d <= 128 with k <= 26 and d <= 256 with k <= 10 (d=%d k=%d)", d, k);
+                "cosine_topk: tensor-core modes cover d <= 128 with k <= 128 and d <= 256 with k <= 10 (d=%d k=%d)", d, k);
   RAG_REQUIRE(key_inv_norm, RAG_EINVAL, "cosine_topk: the tensor-core modes need key_inv_norm (rag_row_inv_norm_f32)");
   RAG_REQUIRE(aligned16(keys_shadow), RAG_EALIGN, "cosine_topk: the key shadow must be 16-byte aligned");
   const int kp_req = (flags & RAG_SIM_WIDE_LISTS) ? 32 : 0;
@@ -1595,7 +1737,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   } else {
     // ONE prologue launch: normalised 16-bit query image, inverse norms, rounding-error norms, device counters cleared
     st = rows_to_16_launch(q, Q, d, f16 ? RAG_FMT_F16 : RAG_FMT_BF16, 1, 1e-12f, q_bf, p.d_pad, qinv, qerr, nullptr,
-                           reinterpret_cast<uint32_t*>(zero), L.n_zero, s);
+                           reinterpret_cast<uint32_t*>(zero), (ts && p.n_mergers > 0) ? p.n_zero_share : L.n_zero, s);
     if (st) return st;
   }
 
@@ -1635,7 +1777,20 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
       RAG_LAUNCH_OK("sample_threshold_kernel");
       a.thr0 = thr0;
     }
-    st = run_ts(mk, q_bf, a, p, grid, s);
+    unsigned grid_main = grid;
+    a.hit_count = reinterpret_cast<uint32_t*>(zero + 4);
+    if (p.n_mergers > 0 && a.debug == 0) {
+      // cross-split threshold sharing: p.n_mergers extra CTAs sweep the published candidates (TcArgs::pool)
+      a.pool = reinterpret_cast<uint32_t*>(w + L.off_pool);
+      a.gthr = reinterpret_cast<uint32_t*>(w + L.off_gthr);
+      a.part_thr = reinterpret_cast<float*>(w + L.off_pthr);
+      a.done = zero + 3;
+      a.pool_slots = ts_kpb(p.kp); a.n_mergers = p.n_mergers; a.g_k = k;
+      a.g_qerr = qerr; a.g_kerr = shadow_err; a.g_eps_fixed = TC_SLACK + (shadow_err ? 0.f : (f16 ? TC_U_F16 : TC_U_BF16));
+      a.g_exact = exact ? 1 : 0; a.g_sleep_div = tc_opts().gshare_sleep;
+      grid_main = grid + (unsigned)p.n_mergers;
+    }
+    st = run_ts(mk, q_bf, a, p, grid_main, s);
   } else {
     st = make_map_bf16(&mq, q_bf, Q, p.d_pad, 128, tf32);
     if (st) return st;
@@ -1658,6 +1813,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   r.fb_rows = reinterpret_cast<int32_t*>(w + L.off_fb);
   r.fb_count = fb_count;
   r.thr0 = a.thr0;
+  r.part_thr = a.part_thr;
   r.thr2 = reinterpret_cast<float*>(w + L.off_thr2);
   const float u = f16 ? TC_U_F16 : TC_U_BF16;
   r.qerr = tf32 ? nullptr : qerr;
@@ -1680,6 +1836,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
     //      the shard on the tensor cores with the fixed threshold thr2 and return EVERY key above it ----
     TcArgs c = a;
     c.thr0 = r.thr2; c.thr_exact = 1; c.collect = 1; c.premax = 0; c.trace = 0;
+    c.hit_count = nullptr; c.pool = nullptr; c.gthr = nullptr; c.part_thr = nullptr; c.done = nullptr; c.n_mergers = 0;
     c.row_map = r.fb_rows; c.n_rows_dev = fb_count;
     c.spill_s = reinterpret_cast<float*>(w + L.off_spill_s);
     c.spill_i = reinterpret_cast<int32_t*>(w + L.off_spill_i);
@@ -1728,6 +1885,9 @@ extern "C" RAG_API int rag_tc_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "prepass_div")) o.prepass_div = value >= 4 ? value : dflt.prepass_div;
   else if (!strcmp(name, "kp")) o.kp = (value == 16 || value == 32) ? value : dflt.kp;
   else if (!strcmp(name, "pass2")) o.pass2 = value < 0 ? dflt.pass2 : (value != 0);
+  else if (!strcmp(name, "gshare")) o.gshare = value < 0 ? dflt.gshare : (value != 0);
+  else if (!strcmp(name, "gshare_ctas")) o.gshare_ctas = (value >= 1 && value <= 16) ? value : dflt.gshare_ctas;
+  else if (!strcmp(name, "gshare_sleep")) o.gshare_sleep = value >= 0 ? value : dflt.gshare_sleep;
   else return rag::fail(RAG_EINVAL, "tc_set_option: unknown option '%s'", name);
   return RAG_OK;
 }
