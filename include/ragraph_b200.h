@@ -149,13 +149,16 @@ RAG_API int rag_cosine_topk_f32(const float* q, int64_t Q, const float* keys, co
 /* Byte offsets, inside the caller's workspace of the same (Q, N, d, k, mode), of three consecutive int32 counters the
  * *_REFINE modes leave behind: offsets_out[0] = rows that needed the second tensor-core pass, offsets_out[1] = rows that
  * fell back to the fp32 kernel, offsets_out[2] = rows whose certificate would fail under an 8x larger error bound (what a
- * bf16 filter would have: lets a caller running fp16 decide whether bf16 would do).  Valid after the call's work has
- * finished on the stream; all 0 for other modes. */
+ * bf16 filter would have: lets a caller running fp16 decide whether bf16 would do).  Two diagnostic words follow at
+ * offsets_out[0] + 12 and + 16: the worker CTAs counted by the cross-split threshold sweep (0 = the sweep did not run) and
+ * the (lane, 32-score chunk) hits the query-stationary filter queued.  Valid after the call's work has finished on the
+ * stream; all 0 for other modes. */
 RAG_API int rag_cosine_topk_stat_offsets(int64_t Q, int64_t N, int32_t d, int32_t k, int32_t mode, size_t* offsets_out);
 /* Process-wide tuning / test hooks of the tensor-core path, read from the environment ONCE at load (RAG_TC_VARIANT,
  * RAG_TC_PREPASS, RAG_TC_PREPASS_MIN_TILES, RAG_TC_PREPASS_DIV, RAG_TC_KP) and settable here: name without the RAG_TC_
  * prefix in lower case ("variant": 0 auto / 1 ss / 2 ts; "prepass": 0/1; "prepass_min_tiles"; "prepass_div"; "kp": 0 auto /
- * 16 / 32; "pass2": 0/1).  value < 0 restores the default.  Returns RAG_EINVAL for an unknown name. */
+ * 16 / 32; "pass2": 0/1; "gshare": 0/1 = cross-split threshold sharing by sweeping CTAs on the SMs the (query tile, key
+ * split) grid leaves idle, "gshare_ctas": how many at most).  value < 0 restores the default.  Returns RAG_EINVAL for an unknown name. */
 RAG_API int rag_tc_set_option(const char* name, int32_t value);
 
 /* Small-problem retrieve in ONE launch (the reference's real call sites: RAGraph_graph/ragraph_utils/ToyGraphBase.py:56-87 --
@@ -254,12 +257,6 @@ RAG_API int rag_csr_spmm_f32(const void* rowptr, int32_t ptr_is_64, const int32_
                      int64_t n_rows, int64_t n_src, int64_t nnz, const float* X, int32_t F,
                      uint32_t epilogue, const float* bias, const float* alpha, const float* blend_in,
                      float blend_w, const float* accum_in, float* Y, rag_stream_t stream);
-/* Feature-sliced schedule of rag_csr_spmm_f32.  When X is far larger than the 126 MB L2 (>= 512 MB) and source rows are
- * reused (nnz >= 8 n_src), the call runs one launch per 32-float column slice of X / Y (row-major in and out, no workspace):
- * the slice's rows of the frequently used sources stay in L2 between their uses, the (col, val) stream is re-read per slice.
- * Same results up to the fp32 order of the partial sums.  Tuning / test hook: "slice" = -1 auto, 0 never, 32 / 64 / 128
- * forced width; "l2_hints" = 0/1 (evict_last on the gathers, evict_first on the streams).  RAG_EINVAL for unknown names. */
-RAG_API int rag_spmm_set_option(const char* name, int32_t value);
 
 /* CSR construction on the device (no host round trip).
  * COO (edges[E,2] int64: [:,0]=src, [:,1]=dst as in modules/RAGraph.py:22-24) -> CSR by dst.

@@ -45,7 +45,6 @@ SIGNATURES = {
     "rag_cosine_topk_f32": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _i64, _p, _p, _p, _sz, _p]),
     "rag_cosine_topk_stat_offsets": (C.c_int, [_i64, _i64, _i32, _i32, _i32, _p]),
     "rag_tc_set_option": (C.c_int, [C.c_char_p, _i32]),
-    "rag_spmm_set_option": (C.c_int, [C.c_char_p, _i32]),
     "rag_retrieve_small_supported": (C.c_int, [_i64, _i64, _i32, _i32]),
     "rag_retrieve_small_workspace": (_sz, [_i64, _i64, _i32, _i32]),
     "rag_retrieve_small_f32": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _u32, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
@@ -103,11 +102,6 @@ def check(status: int, what: str) -> None:
     if status != RAG_OK:
         lib = load()
         raise RagError(f"{what}: {lib.rag_status_string(status).decode()}: {lib.rag_last_error().decode()}")
-
-
-def spmm_set_option(name: str, value: int) -> None:
-    """process-wide tuning / test hook of the SpMM's feature-sliced schedule (see rag_spmm_set_option)"""
-    check(load().rag_spmm_set_option(name.encode(), int(value)), "spmm_set_option")
 
 
 def tc_set_option(name: str, value: int) -> None:

@@ -22,7 +22,6 @@
 //     8 warps of the CTA and reduced through shared memory in warp order, so a 17k-degree
 //     hub costs ~2k nonzeros of latency instead of 17k.  No atomics on Y: results are
 //     deterministic.
-#include <cstring>
 #include "common.cuh"
 
 namespace rag {
@@ -32,33 +31,14 @@ constexpr int SPMM_WARPS = SPMM_THREADS / 32;
 constexpr int ROWS_PER_GRAB = 64;   // rows per dynamic work item (8 per warp)
 constexpr int LONG_ROW = 1024;      // rows with more nonzeros are split across the CTA
 constexpr int STAGE = 32;           // (col,val) entries per cp.async tile
-constexpr int SPMM_AUTO_SLICE = 32; // floats per column slice of the feature-sliced schedule (measured)
 
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
 }
-__device__ __forceinline__ void cp_async4_hint(void* smem, const void* gmem, uint64_t pol) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem), "l"(pol));
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// X gather with an L2 eviction-priority hint (feature-sliced schedule: the slice's rows should outlive the streams)
-__device__ __forceinline__ float4 ldg_x(const float4* p, uint64_t pol) {
-  if (pol == 0) return __ldg(p);
-  float4 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ void st_y(float4* p, float4 v, uint64_t pol) {
-  if (pol == 0) { *p = v; return; }
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
-               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
-}
 
 struct SpmmArgs {
   const void* rowptr; int ptr_is_64;
@@ -68,20 +48,7 @@ struct SpmmArgs {
   uint32_t epi; const float* bias; const float* alpha; const float* blend_in; float blend_w;
   const float* accum_in; float* Y;
   unsigned long long* work_counter;   // dynamic row-block scheduler
-  // column slice [c0, c0 + 4*LANES*VPL) of row-major X / Y / bias / blend_in / accum_in whose rows are ld4 float4 apart
-  // (feature-sliced schedule below); a whole-row launch has c0_4 = 0 and ld4 = LANES*VPL
-  int64_t ld4; int c0_4;
-  int l2_hints;                       // 1: X gathers evict_last, (col, val) / Y streams evict_first (createpolicy in the kernel)
 };
-struct SpmmPolicies { uint64_t keep, stream; };   // 0 = no hint
-__device__ __forceinline__ SpmmPolicies make_policies(int on) {
-  SpmmPolicies p{0ull, 0ull};
-  if (on) {
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
-  }
-  return p;
-}
 
 __device__ __forceinline__ int64_t load_ptr(const void* rowptr, int is64, int64_t i) {
   return is64 ? __ldg(reinterpret_cast<const int64_t*>(rowptr) + i)
@@ -104,8 +71,9 @@ __device__ __forceinline__ float apply_epi(float y, float inv_deg_num, bool rown
 template <int LANES, int VPL>
 __device__ __forceinline__ void accumulate_range(const SpmmArgs& a, int64_t beg, int64_t end, int lane,
                                                  int32_t* ring_col, float* ring_val, float4 (&acc)[VPL],
-                                                 float& valsum, const SpmmPolicies pol) {
+                                                 float& valsum) {
   constexpr int GROUPS = 32 / LANES;            // nonzeros processed per warp step
+  constexpr int F4 = LANES * VPL;
   const int sub = lane % LANES;
   const int grp = lane / LANES;
   const float4* X4 = reinterpret_cast<const float4*>(a.X);
@@ -114,13 +82,8 @@ __device__ __forceinline__ void accumulate_range(const SpmmArgs& a, int64_t beg,
   auto stage_tile = [&](int64_t base, int buf) {
     int64_t j = base + lane;
     if (j < end) {
-      if (pol.stream) {
-        cp_async4_hint(ring_col + buf * STAGE + lane, a.col + j, pol.stream);
-        if (has_val) cp_async4_hint(ring_val + buf * STAGE + lane, a.val + j, pol.stream);
-      } else {
-        cp_async4(ring_col + buf * STAGE + lane, a.col + j);
-        if (has_val) cp_async4(ring_val + buf * STAGE + lane, a.val + j);
-      }
+      cp_async4(ring_col + buf * STAGE + lane, a.col + j);
+      if (has_val) cp_async4(ring_val + buf * STAGE + lane, a.val + j);
     }
     cp_async_commit();
   };
@@ -147,7 +110,7 @@ __device__ __forceinline__ void accumulate_range(const SpmmArgs& a, int64_t beg,
         w[u] = ok ? (has_val ? rv[e] : 1.0f) : 0.f;
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
-          x[u][v] = ok ? ldg_x(X4 + (int64_t)c * a.ld4 + a.c0_4 + sub + v * LANES, pol.keep) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x[u][v] = ok ? __ldg(X4 + (int64_t)c * F4 + sub + v * LANES) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -181,23 +144,24 @@ __device__ __forceinline__ void fold_groups(float4 (&acc)[VPL], float& valsum) {
 
 template <int LANES, int VPL>
 __device__ __forceinline__ void store_row(const SpmmArgs& a, int64_t row, int lane, const float4 (&acc)[VPL],
-                                          float valsum, const SpmmPolicies pol) {
+                                          float valsum) {
+  constexpr int F4 = LANES * VPL;
   if (lane >= LANES) return;
   const bool rownorm = (a.epi & RAG_EPI_ROWNORM) != 0;
   const float alpha = (a.epi & RAG_EPI_PRELU) ? __ldg(a.alpha) : 0.f;
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
-    const int c4 = a.c0_4 + lane + v * LANES;
+    const int c4 = lane + v * LANES;
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f), bl = b, ac = b;
     if (a.epi & RAG_EPI_BIAS) b = __ldg(reinterpret_cast<const float4*>(a.bias) + c4);
-    if (a.epi & RAG_EPI_BLEND) bl = __ldg(reinterpret_cast<const float4*>(a.blend_in) + row * a.ld4 + c4);
-    if (a.epi & RAG_EPI_ACCUM) ac = __ldg(reinterpret_cast<const float4*>(a.accum_in) + row * a.ld4 + c4);
+    if (a.epi & RAG_EPI_BLEND) bl = __ldg(reinterpret_cast<const float4*>(a.blend_in) + row * F4 + c4);
+    if (a.epi & RAG_EPI_ACCUM) ac = __ldg(reinterpret_cast<const float4*>(a.accum_in) + row * F4 + c4);
     float4 y;
     y.x = apply_epi(acc[v].x, valsum, rownorm, a.epi, b.x, alpha, bl.x, a.blend_w, ac.x);
     y.y = apply_epi(acc[v].y, valsum, rownorm, a.epi, b.y, alpha, bl.y, a.blend_w, ac.y);
     y.z = apply_epi(acc[v].z, valsum, rownorm, a.epi, b.z, alpha, bl.z, a.blend_w, ac.z);
     y.w = apply_epi(acc[v].w, valsum, rownorm, a.epi, b.w, alpha, bl.w, a.blend_w, ac.w);
-    st_y(reinterpret_cast<float4*>(a.Y) + row * a.ld4 + c4, y, pol.stream);
+    reinterpret_cast<float4*>(a.Y)[row * F4 + c4] = y;
   }
 }
 
@@ -213,7 +177,6 @@ csr_spmm_kernel(const SpmmArgs a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_blocks = (a.n_rows + ROWS_PER_GRAB - 1) / ROWS_PER_GRAB;
-  const SpmmPolicies pol = make_policies(a.l2_hints);
 
   for (;;) {
     __syncthreads();                               // s_block / s_part reuse
@@ -233,9 +196,9 @@ csr_spmm_kernel(const SpmmArgs a) {
 #pragma unroll
       for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
       float valsum = 0.f;
-      accumulate_range<LANES, VPL>(a, beg, end, lane, s_col[warp], s_val[warp], acc, valsum, pol);
+      accumulate_range<LANES, VPL>(a, beg, end, lane, s_col[warp], s_val[warp], acc, valsum);
       fold_groups<LANES, VPL>(acc, valsum);
-      store_row<LANES, VPL>(a, row, lane, acc, valsum, pol);
+      store_row<LANES, VPL>(a, row, lane, acc, valsum);
     }
     // pass 2: long rows, the whole CTA per row
     if (__syncthreads_or(any_long)) {
@@ -249,7 +212,7 @@ csr_spmm_kernel(const SpmmArgs a) {
 #pragma unroll
         for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         float valsum = 0.f;
-        accumulate_range<LANES, VPL>(a, b, e, lane, s_col[warp], s_val[warp], acc, valsum, pol);
+        accumulate_range<LANES, VPL>(a, b, e, lane, s_col[warp], s_val[warp], acc, valsum);
         fold_groups<LANES, VPL>(acc, valsum);
         if (lane < LANES) {
 #pragma unroll
@@ -272,7 +235,7 @@ csr_spmm_kernel(const SpmmArgs a) {
               }
             }
           }
-          store_row<LANES, VPL>(a, row, lane, tot, vs, pol);
+          store_row<LANES, VPL>(a, row, lane, tot, vs);
         }
         __syncthreads();
       }
@@ -328,36 +291,7 @@ static int launch_spmm(SpmmArgs a, cudaStream_t s) {
   return RAG_OK;
 }
 
-// Feature-sliced schedule: tuning state (rag_spmm_set_option) and the slice width for a problem (0 = one launch).
-struct SpmmOptions {
-  int slice = -1;       // -1 auto, 0 never, 32 / 64 / 128 = forced slice width in floats
-  int l2_hints = 1;     // sliced launches: X gathers evict_last, streams evict_first
-};
-static SpmmOptions& spmm_opts() {
-  static SpmmOptions o;
-  return o;
-}
-static int spmm_slice_for(int64_t n_src, int64_t nnz, int F) {
-  const int forced = spmm_opts().slice;
-  if (forced == 0) return 0;
-  if (forced > 0) return (F % forced == 0 && forced < F) ? forced : 0;
-  // auto: X must dwarf L2 (else the one-launch schedule already hits), rows must be reused (edges per source row), and
-  // F must split into whole 32-float slices
-  if (F < 64 || F % 32 != 0) return 0;
-  if ((double)n_src * F * 4.0 < 512e6 || nnz < 8 * n_src) return 0;
-  return SPMM_AUTO_SLICE;
-}
-
 }  // namespace rag
-
-extern "C" RAG_API int rag_spmm_set_option(const char* name, int32_t value) {
-  if (!name) return rag::fail(RAG_EINVAL, "spmm_set_option: null name");
-  rag::SpmmOptions& o = rag::spmm_opts();
-  if (!strcmp(name, "slice")) o.slice = (value == 0 || value == 32 || value == 64 || value == 128) ? value : -1;
-  else if (!strcmp(name, "l2_hints")) o.l2_hints = value < 0 ? 1 : (value != 0);
-  else return rag::fail(RAG_EINVAL, "spmm_set_option: unknown option '%s'", name);
-  return RAG_OK;
-}
 
 extern "C" int rag_csr_spmm_f32(const void* rowptr, int32_t ptr_is_64, const int32_t* col, const float* val,
                                 int64_t n_rows, int64_t n_src, int64_t nnz, const float* X, int32_t F,
@@ -377,28 +311,11 @@ extern "C" int rag_csr_spmm_f32(const void* rowptr, int32_t ptr_is_64, const int
   RAG_REQUIRE(!(epilogue & RAG_EPI_BLEND) || blend_in, RAG_EINVAL, "csr_spmm: RAG_EPI_BLEND without blend_in");
   RAG_REQUIRE(!(epilogue & RAG_EPI_ACCUM) || accum_in, RAG_EINVAL, "csr_spmm: RAG_EPI_ACCUM without accum_in");
   SpmmArgs a{rowptr, ptr_is_64, col, val, n_rows, n_src, X, F, epilogue, bias, alpha, blend_in, blend_w,
-             accum_in, Y, nullptr, F / 4, 0, 0};
+             accum_in, Y, nullptr};
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec = (F % 4 == 0) && aligned16(X) && aligned16(Y) && (!bias || aligned16(bias)) &&
                    (!blend_in || aligned16(blend_in)) && (!accum_in || aligned16(accum_in));
   if (vec) {
-    // Feature-sliced schedule.  When X is far larger than L2 every edge costs a DRAM fetch of its source row; run over one
-    // column slice of X / Y at a time (one launch per slice, same kernel, row stride = the full F) and the slice's rows of
-    // the frequently used sources stay in the 126 MB L2 between their uses: the (col, val) stream is re-read per slice
-    // (8 bytes per edge against the 4*slice bytes gathered), the gathers hit L2 instead of DRAM.  Row-major in and out,
-    // no workspace; a slice is >= 128 bytes per row (a whole L2 line).  Results are bit-identical to the one-launch
-    // schedule for slices of 128 floats (same lanes, same order of additions); 32- and 64-float slices fold the lane
-    // groups' partial sums in a different order (fp32 rounding only).
-    const int slice = spmm_slice_for(n_src, nnz, F);
-    if (slice > 0 && slice < F) {
-      a.l2_hints = spmm_opts().l2_hints;
-      for (int c0 = 0; c0 < F; c0 += slice) {
-        a.c0_4 = c0 / 4;
-        int st = slice == 128 ? launch_spmm<32, 1>(a, s) : (slice == 64 ? launch_spmm<16, 1>(a, s) : launch_spmm<8, 1>(a, s));
-        if (st) return st;
-      }
-      return RAG_OK;
-    }
     switch (F) {
       case 512: return launch_spmm<32, 4>(a, s);
       case 256: return launch_spmm<32, 2>(a, s);

@@ -274,7 +274,7 @@ struct TcArgs {
   // every few tiles.  A word of 0 means "nothing yet" (the prologue clears pool and gthr).  part_thr[split][row] = the
   // threshold a CTA ended with (refine: every key the split did not list scores <= it).
   uint32_t* pool; uint32_t* gthr; float* part_thr; int32_t* done;
-  int pool_slots; int n_mergers; int g_k; int g_sleep_div;
+  int pool_slots; int n_mergers; int g_k; int g_dbg;   // g_dbg (experiments): 1 = sweeping CTAs leave at once, 2 = workers ignore gthr, 3 = workers do not publish
   const float* g_qerr; const float* g_kerr; float g_eps_fixed; int g_exact;
   uint32_t* hit_count;             // nullable diagnostic: (lane, chunk) hits queued by all epilogue warps of the launch
   int trace;                       // RAG_TC_DEBUG=3 or RAG_TC_TRACE=1: CTA 0 stamps clock64 at pipeline events (g_tc_trace)
@@ -696,7 +696,7 @@ __device__ __forceinline__ TsServed ts_serve_entry(const float* ev, int key0, in
       pi[pos * TS_LSTRIDE + orow] = key0 + lane;
       // TcArgs::pool.  The shared bound is (k-th largest published score) - margin and thr_l >= it, so a score <= thr_l +
       // margin cannot raise that k-th largest: only the others are worth a global store (dense clusters: very few)
-      if (a.pool && val > thr_l + mg) a.pool[((crow0 + orow) * a.n_splits + split) * KPB + pos] = __float_as_uint(val);
+      if (a.pool && a.g_dbg != 3 && val > thr_l + mg) a.pool[((crow0 + orow) * a.n_splits + split) * KPB + pos] = __float_as_uint(val);
     }
     pm = fminf(pm, f32_unordered(__reduce_min_sync(0xffffffffu, fit ? f32_ordered(val) : 0x7fffffff)));
     np = min(np + __popc(cm), KPB);
@@ -740,7 +740,7 @@ __device__ __forceinline__ void queue_put(float* entry, const uint32_t (&v)[32],
 // ---- cross-split threshold sharing: the sweep run by the CTAs past the worker grid (TcArgs::pool) -------------------
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
@@ -748,63 +748,96 @@ __device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
 }
 // One warp per query row and sweep: the row's n_splits * pool_slots published words (<= 32 * NREG) go to registers, the
 // k-th largest is found by removing the maximum (one instance: equal scores of distinct keys count separately) k times.
+// A lone warp runs this dependent code at 6-15 cycles per instruction, and the sweep rate is what the workers feel (measured,
+// 12.5 M x 128: 1 / 2 / 4 sweeping CTAs -> 716 k / 543 k / 452 k hits, 9.80 / 9.63 / 9.07 ms), so a warp works on TWO rows
+// at a time (two independent dependency chains) and skips a row whose words are unchanged since its last visit (XOR
+// checksum kept in shared memory; late in the stream almost every row).
 // The workers never wait for this: a late, stale or missing gthr only costs them hits, never correctness, and the loop
 // ends when every worker CTA has counted itself in *done (or at once, when the workers already finished).
 template <int NREG>
-__device__ void ts_merger_loop(const TcArgs& a, int n_workers) {
+__device__ void ts_merger_loop(const TcArgs& a, int n_workers, uint32_t* sums, int sums_per_warp) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int words = a.n_splits * a.pool_slots;
   const int64_t first = (int64_t)(blockIdx.x - n_workers) * nw + warp, stride = (int64_t)a.n_mergers * nw;
   const float kerr = a.g_kerr ? __ldg(a.g_kerr) : 0.f;
+  uint32_t* my_sums = sums + (size_t)warp * sums_per_warp;
+  for (int i = lane; i < sums_per_warp; i += 32) my_sums[i] = 0u;      // (an all-empty row XORs to 0: nothing to do for it)
+  __syncwarp();
   const unsigned long long t_begin = clock64();
-  while (true) {
-    const int done = (int)ld_relaxed_u32(reinterpret_cast<const uint32_t*>(a.done));
-    for (int64_t row = first; row < a.Q; row += stride) {
-      const uint32_t* pr = a.pool + row * words;
-      float v[NREG];
+  // The launch ends with its last CTA, so a sweep must not outlive the workers: the worker count is polled at every row pair
+  // (measured: with ONE sweeping CTA a full sweep takes ~1 ms, and checking only between sweeps added half of that to every call).
+  bool finished = false;
+  while (!finished) {
+    int n = 0;
+    for (int64_t row = first; row < a.Q; row += 2 * stride, n += 2) {
+      if ((int)ld_relaxed_u32(reinterpret_cast<const uint32_t*>(a.done)) >= n_workers) { finished = true; break; }
+      const int64_t rows[2] = {row, row + stride};
+      float v[2][NREG];
+      bool live[2];
 #pragma unroll
-      for (int t = 0; t < NREG; ++t) {
-        const int w = lane + 32 * t;
-        const uint32_t bits = (w < words) ? ld_relaxed_u32(pr + w) : 0u;
-        v[t] = bits ? __uint_as_float(bits) : -INFINITY;
-      }
-      float kth = -INFINITY;
-      for (int it = 0; it < a.g_k; ++it) {
-        float m = v[0];
+      for (int r = 0; r < 2; ++r) {
+        const bool in = rows[r] < a.Q;
+        const uint32_t* pr = a.pool + rows[r] * words;
+        uint32_t x = 0u;
 #pragma unroll
-        for (int t = 1; t < NREG; ++t) m = fmaxf(m, v[t]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        kth = m;
-        if (m == -INFINITY) break;
-        int mine = -1;
-#pragma unroll
-        for (int t = NREG - 1; t >= 0; --t) mine = (v[t] == m) ? t : mine;
-        const unsigned who = __ballot_sync(0xffffffffu, mine >= 0);
-        if (lane == __ffs(who) - 1) {
-#pragma unroll
-          for (int t = 0; t < NREG; ++t) if (t == mine) v[t] = -INFINITY;
+        for (int t = 0; t < NREG; ++t) {
+          const int w = lane + 32 * t;
+          const uint32_t bits = (in && w < words) ? ld_relaxed_u32(pr + w) : 0u;
+          v[r][t] = bits ? __uint_as_float(bits) : -INFINITY;
+          x ^= bits * (uint32_t)(2 * w + 1);                       // position-dependent, so that a moved value counts
+        }
+        x = __reduce_xor_sync(0xffffffffu, x);
+        live[r] = in;
+        if (in && n + r < sums_per_warp) {
+          live[r] = my_sums[n + r] != x;
+          __syncwarp();
+          if (lane == 0) my_sums[n + r] = x;
         }
       }
-      if (lane == 0 && kth > -INFINITY) {
-        // exact modes: refine needs every key whose 16-bit score is within 2 eps of the k-th best (TcArgs::pool); raw
-        // modes: one notch below, so that keys tying with the k-th best are still taken
-        float g;
-        if (a.g_exact) g = kth - (2.0f * ((a.g_qerr ? __ldg(a.g_qerr + row) : 0.f) + kerr + a.g_eps_fixed) + 1e-6f);
-        else g = (kth > 0.f) ? kth * (1.0f - 1e-6f) : kth * (1.0f + 1e-6f) - 1e-30f;
-        const uint32_t old = a.gthr[row];                       // only this warp ever writes the word
-        if (g != 0.f && (old == 0u || g > __uint_as_float(old))) st_relaxed_u32(a.gthr + row, __float_as_uint(g));
+      if (!live[0] && !live[1]) continue;
+      float kth[2] = {-INFINITY, -INFINITY};
+      for (int it = 0; it < a.g_k; ++it) {
+        float m[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          m[r] = v[r][0];
+#pragma unroll
+          for (int t = 1; t < NREG; ++t) m[r] = fmaxf(m[r], v[r][t]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          m[0] = fmaxf(m[0], __shfl_xor_sync(0xffffffffu, m[0], o));
+          m[1] = fmaxf(m[1], __shfl_xor_sync(0xffffffffu, m[1], o));
+        }
+        kth[0] = m[0]; kth[1] = m[1];
+        if (m[0] == -INFINITY && m[1] == -INFINITY) break;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          int mine = -1;
+#pragma unroll
+          for (int t = NREG - 1; t >= 0; --t) mine = (v[r][t] == m[r] && m[r] > -INFINITY) ? t : mine;
+          const unsigned who = __ballot_sync(0xffffffffu, mine >= 0);
+          if (who != 0u && lane == __ffs(who) - 1) {
+#pragma unroll
+            for (int t = 0; t < NREG; ++t) if (t == mine) v[r][t] = -INFINITY;
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (lane == 0 && live[r] && kth[r] > -INFINITY) {
+          // exact modes: refine needs every key whose 16-bit score is within 2 eps of the k-th best (TcArgs::pool); raw
+          // modes: one notch below, so that keys tying with the k-th best are still taken
+          float g;
+          if (a.g_exact) g = kth[r] - (2.0f * ((a.g_qerr ? __ldg(a.g_qerr + rows[r]) : 0.f) + kerr + a.g_eps_fixed) + 1e-6f);
+          else g = (kth[r] > 0.f) ? kth[r] * (1.0f - 1e-6f) : kth[r] * (1.0f + 1e-6f) - 1e-30f;
+          const uint32_t old = a.gthr[rows[r]];                   // only this warp ever writes the word
+          if (g != 0.f && (old == 0u || g > __uint_as_float(old))) st_relaxed_u32(a.gthr + rows[r], __float_as_uint(g));
+        }
       }
     }
-    if (done >= n_workers) break;
-    const unsigned long long el = clock64() - t_begin;
-    if (el > TC_TIMEOUT_CYCLES) __trap();
-    // Candidates arrive at a rate ~ 1/t, so the value of a fresh bound decays the same way: sleep a fixed fraction of the
-    // time elapsed between sweeps (an always-spinning sweep costs power the tensor pipe wants under the board's cap)
-    if (a.g_sleep_div > 0) {
-      unsigned long long ns = el / (unsigned long long)a.g_sleep_div;        // cycles ~ ns at 1-2 GHz
-      __nanosleep((unsigned)(ns > 100000ull ? 100000ull : ns));
-    }
+    if (first >= a.Q && (int)ld_relaxed_u32(reinterpret_cast<const uint32_t*>(a.done)) >= n_workers) finished = true;   // (a warp without rows)
+    if (clock64() - t_begin > TC_TIMEOUT_CYCLES) __trap();
   }
 }
 
@@ -860,8 +893,11 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
   }
   if constexpr (!PRE) {
     if (a.n_mergers > 0 && (int)blockIdx.x >= a.n_qtiles * a.n_splits) {     // (uniform per CTA, before any barrier / TMEM)
-      if (a.n_splits * a.pool_slots <= 160) ts_merger_loop<5>(a, a.n_qtiles * a.n_splits);
-      else ts_merger_loop<16>(a, a.n_qtiles * a.n_splits);
+      if (a.g_dbg == 1) return;
+      uint32_t* sums = reinterpret_cast<uint32_t*>(smem_dyn);                 // row checksums: all of the dynamic window
+      const int spw = (int)((size_t)(NSTAGE * TC_BOX_BYTES) / 4 / (TS_THREADS / 32));
+      if (a.n_splits * a.pool_slots <= 160) ts_merger_loop<5>(a, a.n_qtiles * a.n_splits, sums, spw);
+      else ts_merger_loop<16>(a, a.n_qtiles * a.n_splits, sums, spw);
       return;
     }
   }
@@ -1035,15 +1071,17 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
       ++qhead;
       __syncwarp();
     };
-    // cross-split bound (TcArgs::pool): read every 4th tile, folded in one iteration later (the load's latency is off the
-    // tile loop's critical path); padding rows keep thr = +inf
+    // cross-split bound (TcArgs::pool): every 16th tile the value read 16 tiles earlier is folded in and the next read is
+    // issued -- ONE predictable branch per tile and no wait on the load.  (Measured at 100 M keys: a read every 4th tile
+    // consumed one tile later cost the epilogue warps 1.9 % of the step -- every instruction in this loop is on the
+    // critical path of a lone warp.)  Padding rows keep thr = +inf.
     uint32_t gbits = 0u;
-    const bool g_on = !PRE && a.gthr != nullptr && grow < Qn;
+    const bool g_on = !PRE && a.gthr != nullptr && grow < Qn && a.g_dbg != 2;
     if (g_on && a.g_exact) gmargin = 2.0f * ((a.g_qerr ? __ldg(a.g_qerr + grow) : 0.f) + (a.g_kerr ? __ldg(a.g_kerr) : 0.f) + a.g_eps_fixed) + 1e-6f;
     for (int t = 0; t <= n_my_tiles; ++t) {
-      if (g_on) {
+      if ((t & 15) == 0 && g_on) {
         if (gbits) thr = fmaxf(thr, __uint_as_float(gbits));
-        if ((t & 3) == 0) gbits = ld_relaxed_u32(a.gthr + grow);
+        gbits = ld_relaxed_u32(a.gthr + grow);
       }
       // use u = 2t + rb -> buffer u % NBUF; this row block's (t / 3)-th visit of it (ring of 3), t-th (ring of 2)
       const uint32_t u = 2u * (uint32_t)t + (uint32_t)rb;
@@ -1497,7 +1535,7 @@ struct TcOptions {
   int pass2 = 1;                      // 0: uncertified rows go straight to the fp32 kernel (the round-1 behaviour)
   int gshare = 1;                     // cross-split threshold sharing on the idle SMs (TcArgs::pool); 0 = off
   int gshare_ctas = 4;                // at most this many sweeping CTAs
-  int gshare_sleep = 0;               // sweeps sleep elapsed / this between rounds (0 = spin)
+  int gshare_dbg = 0;                 // experiments (TcArgs::g_dbg)
 };
 static TcOptions tc_env_defaults() {
   TcOptions o;
@@ -1787,7 +1825,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
       a.done = zero + 3;
       a.pool_slots = ts_kpb(p.kp); a.n_mergers = p.n_mergers; a.g_k = k;
       a.g_qerr = qerr; a.g_kerr = shadow_err; a.g_eps_fixed = TC_SLACK + (shadow_err ? 0.f : (f16 ? TC_U_F16 : TC_U_BF16));
-      a.g_exact = exact ? 1 : 0; a.g_sleep_div = tc_opts().gshare_sleep;
+      a.g_exact = exact ? 1 : 0; a.g_dbg = tc_opts().gshare_dbg;
       grid_main = grid + (unsigned)p.n_mergers;
     }
     st = run_ts(mk, q_bf, a, p, grid_main, s);
@@ -1886,8 +1924,8 @@ extern "C" RAG_API int rag_tc_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "kp")) o.kp = (value == 16 || value == 32) ? value : dflt.kp;
   else if (!strcmp(name, "pass2")) o.pass2 = value < 0 ? dflt.pass2 : (value != 0);
   else if (!strcmp(name, "gshare")) o.gshare = value < 0 ? dflt.gshare : (value != 0);
+  else if (!strcmp(name, "gshare_dbg")) o.gshare_dbg = value >= 0 ? value : 0;
   else if (!strcmp(name, "gshare_ctas")) o.gshare_ctas = (value >= 1 && value <= 16) ? value : dflt.gshare_ctas;
-  else if (!strcmp(name, "gshare_sleep")) o.gshare_sleep = value >= 0 ? value : dflt.gshare_sleep;
   else return rag::fail(RAG_EINVAL, "tc_set_option: unknown option '%s'", name);
   return RAG_OK;
 }

@@ -211,9 +211,9 @@ def _cosine_topk_impl(q, keys, k, key_inv_norm, keys_shadow, mode, flags, idx_of
     offs = (C.c_size_t * 3)()
     L.check(lib.rag_cosine_topk_stat_offsets(Q, N, d, k, mode, offs), "cosine_topk_stat_offsets")
     if offs[0] == 0 and offs[1] == 0:
-        stats = torch.zeros(3, dtype=torch.int32, device=q.device)
+        stats = torch.zeros(5, dtype=torch.int32, device=q.device)
     else:
-        stats = ws[offs[0]:offs[0] + 12].view(torch.int32)         # the three counters are consecutive; view keeps ws alive
+        stats = ws[offs[0]:offs[0] + 20].view(torch.int32)         # the five counters are consecutive; view keeps ws alive
     return scores, idx, stats
 
 
@@ -235,8 +235,10 @@ def _(q, keys, k, key_inv_norm=None, keys_bf16=None, mode=0, flags=0, idx_offset
 def cosine_topk_with_stats(q: Tensor, keys: Tensor, k: int, key_inv_norm: Optional[Tensor] = None,
                            keys_shadow: Optional[Tensor] = None, mode: int = 0, flags: int = 0, idx_offset: int = 0,
                            shadow_err: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
-    """cosine_topk plus an int32 [3] device tensor {rows that took the second tensor-core pass, rows that fell back to the
-    fp32 kernel, rows whose certificate would fail under an 8x error bound} (zeros for modes without a certificate)."""
+    """cosine_topk plus an int32 [5] device tensor {rows that took the second tensor-core pass, rows that fell back to the
+    fp32 kernel, rows whose certificate would fail under an 8x error bound, worker CTAs counted by the cross-split sweep
+    (0 = the sweep did not run), (lane, 32-score chunk) hits the query-stationary filter queued} (zeros for modes without
+    a certificate)."""
     return _cosine_topk_impl(q, keys, k, key_inv_norm, keys_shadow, mode, flags, idx_offset, shadow_err, True)
 
 

@@ -408,7 +408,7 @@ class ToyGraphBase:
             self.last_stats = stats
         if adapt and len(self._pol_pending) < 4:
             host = self._pol_free.pop() if self._pol_free else torch.empty(3, dtype=torch.int32).pin_memory()
-            host.copy_(stats, non_blocking=True)
+            host.copy_(stats[:3], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             self._pol_pending.append((ev, host, Q, self._pol["gen"], self.emb_size <= 128 and k <= 10))

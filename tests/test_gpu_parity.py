@@ -291,41 +291,6 @@ def test_csr_spmm_powerlaw_vs_fp64(F):
     assert np.array_equal(ops.csr_spmm(cu(rowptr), cu(col), cu(val), cu(x)).cpu().numpy(), y)   # deterministic
 
 
-@pytest.mark.parametrize("F,slice_", [(256, 32), (256, 64), (256, 128), (128, 32), (64, 32), (512, 128)])
-def test_csr_spmm_feature_sliced_schedule(F, slice_):
-    """The feature-sliced schedule (one launch per column slice of X / Y, rag_spmm_set_option("slice", w)) against the
-    one-launch schedule and fp64: every epilogue, empty rows (0/0 -> NaN), rows longer than the CTA-split threshold."""
-    import scipy.sparse as sp
-    n = 2500
-    rowptr, col, val, x = _powerlaw_csr(n, 20, 5000, F, seed=100 + F)
-    A = sp.csr_matrix((val.astype(np.float64), col, rowptr), shape=(n, n))
-    ref = A @ x.astype(np.float64)
-    bias = np.linspace(-1, 1, F).astype(np.float32); alpha = np.array([0.25], np.float32)
-    blend = np.random.default_rng(1).standard_normal((n, F)).astype(np.float32)
-    acc = np.random.default_rng(2).standard_normal((n, F)).astype(np.float32)
-    epi = L.EPI_ROWNORM | L.EPI_BIAS | L.EPI_PRELU | L.EPI_BLEND | L.EPI_ACCUM
-    args = (cu(rowptr), cu(col), cu(val), cu(x))
-    try:
-        outs = {}
-        for hints in (1, 0):
-            L.spmm_set_option("slice", slice_); L.spmm_set_option("l2_hints", hints)
-            outs[hints] = (ops.csr_spmm(*args), ops.csr_spmm(*args, epi, cu(bias), cu(alpha), cu(blend), 0.3, cu(acc)),
-                           ops.csr_spmm(cu(rowptr), cu(col), None, cu(x), L.EPI_RELU))
-        L.spmm_set_option("slice", 0)
-        whole = (ops.csr_spmm(*args), ops.csr_spmm(*args, epi, cu(bias), cu(alpha), cu(blend), 0.3, cu(acc)),
-                 ops.csr_spmm(cu(rowptr), cu(col), None, cu(x), L.EPI_RELU))
-    finally:
-        L.spmm_set_option("slice", -1); L.spmm_set_option("l2_hints", -1)
-    assert O.rel_err(outs[1][0].cpu().numpy(), ref) < REL
-    for h in (0, 1):
-        for got, want in zip(outs[h], whole):
-            g, w = got.cpu().numpy(), want.cpu().numpy()
-            assert np.array_equal(np.isnan(g), np.isnan(w))
-            m = ~np.isnan(w)
-            assert O.rel_err(g[m], w[m]) < REL
-    assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))           # the cache hints never change a value
-
-
 def test_csr_from_dense_roundtrip():
     g = torch.Generator().manual_seed(3)
     adj = (torch.rand(70, 90, generator=g) < 0.1).float() * torch.rand(70, 90, generator=g)

@@ -20,7 +20,7 @@ def tc_variant(request):
     auto = the library's own choice by stream length."""
     L.tc_set_option("variant", {"auto": 0, "ss": 1, "ts": 2}[request.param])
     yield request.param
-    for name in ("variant", "prepass", "prepass_min_tiles", "kp", "pass2"):
+    for name in ("variant", "prepass", "prepass_min_tiles", "kp", "pass2", "gshare"):
         L.tc_set_option(name, -1)
 
 
@@ -90,8 +90,9 @@ def test_clustered_library_second_pass_is_exact(mode, d, k):
     q, keys = _clustered(g, 60000, 300, d, 8, 0.1, 0.1)
     s3, i3, st = _run(q, keys, k, mode, stats=True)
     _assert_exact(q, keys, k, s3, i3)
-    if mode == L.SIM_F16_REFINE and k <= 26:    # (k = 50: more than 1 024 keys within the bound of the 50th best may overflow)
-        assert st[1] == 0, f"rows fell through to the fp32 kernel: {st}"
+    if mode == L.SIM_F16_REFINE:
+        if k <= 26:                         # (k = 50: more than 1 024 keys within the bound of the 50th best may overflow)
+            assert st[1] == 0, f"rows fell through to the fp32 kernel: {st}"
     else:                                   # bf16: ~4 sigma of the in-cluster score spread -> thousands of near-ties per row
         assert st[0] > 0, "the bf16 certificate cannot hold on this library: the second pass must have run"
 
@@ -246,3 +247,35 @@ def test_prepass_threshold_keeps_exactness(min_tiles, tc_variant):
         assert float(same.float().mean()) > 0.99
         for r in torch.nonzero(~same).flatten().tolist():                  # any difference must be a tie within 1e-6
             assert float((s3[r].sort().values - s0[r].sort().values).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("mode", EXACT_MODES + [L.SIM_BF16])
+def test_cross_split_threshold_sharing_same_results(mode):
+    """The sweeping CTAs (cross-split threshold sharing, TcArgs::pool) only ever raise a row's threshold to a proven lower
+    bound of what refine needs, so the answers with and without them are bit-identical -- and with them the filter queues
+    several times fewer hits.  Shape: 10 query tiles x 14 key splits = 140 worker CTAs (idle SMs left), >= 1024 tiles each."""
+    torch.manual_seed(77)
+    Q, N, d, k = 2400, 1_900_000, 64, 10
+    kd = torch.randn(N, d, device=DEV)
+    kd[N // 3] = kd[5]                                   # an exact duplicate: a tie inside the top k of the rows near it
+    qd = torch.randn(Q, d, device=DEV)
+    qd[7] = kd[5] + 0.01 * torch.randn(d, device=DEV)
+    inv = ops.row_inv_norm(kd)
+    shadow, err = _shadow(kd, mode)
+    L.tc_set_option("variant", 2)
+    res = {}
+    for g in (0, 1):
+        L.tc_set_option("gshare", g)
+        s, i, st = ops.cosine_topk_with_stats(qd, kd, k, inv, shadow, mode, shadow_err=err)
+        res[g] = (s.clone(), i.clone(), st.tolist())
+    L.tc_set_option("gshare", -1); L.tc_set_option("variant", -1)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert res[0][2][3] == 0 and res[1][2][3] == 140, (res[0][2], res[1][2])      # worker CTAs seen by the sweep
+    assert res[1][2][4] < res[0][2][4], (res[0][2], res[1][2])                    # fewer hits queued
+    if mode != L.SIM_BF16:
+        rows = torch.arange(0, Q, 16, device=DEV)
+        s0, i0 = ops.cosine_topk(qd[rows].contiguous(), kd, k, inv)
+        assert float((res[1][0][rows] - s0).abs().max()) < 2e-6
+        diff = (res[1][1][rows] != i0).any(dim=1)
+        for r in torch.nonzero(diff).flatten().tolist():                           # any difference must be a tie
+            assert float((res[1][0][rows][r] - s0[r]).abs().max()) < 1e-6

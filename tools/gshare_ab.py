@@ -11,17 +11,16 @@ from ragraph_b200 import _lib as L, ops
 N, d = int(sys.argv[1]), int(sys.argv[2])
 kinds = sys.argv[3].split(",")
 modes = [int(x) for x in sys.argv[4].split(",")]
-# sweep configurations "ctas[:sleep_div[:prepass_div]]", e.g. 4,4:8,2:0:128
+# sweep configurations "ctas[:prepass_div[:dbg]]", e.g. 4,2,4:128,4:64:1
 def _cfg(x):
     p = [int(v) for v in x.split(":")]
-    return (p[0], p[1] if len(p) > 1 else 0, p[2] if len(p) > 2 else 64)
-ctas = [_cfg(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [(4, 0, 64)]
+    return (p[0], p[1] if len(p) > 1 else 64, p[2] if len(p) > 2 else 0)
+ctas = [_cfg(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [(4, 64, 0)]
 dev = torch.device("cuda", 0)
 
 
 def setcfg(g, c):
-    L.tc_set_option("gshare", g); L.tc_set_option("gshare_ctas", c[0]); L.tc_set_option("gshare_sleep", c[1])
-    L.tc_set_option("prepass_div", c[2])
+    L.tc_set_option("gshare", g); L.tc_set_option("gshare_ctas", c[0]); L.tc_set_option("prepass_div", c[1]); L.tc_set_option("gshare_dbg", c[2])
 
 
 Q, k = 4096, 10
@@ -42,13 +41,13 @@ for kind in kinds:
             shadows[fmt] = (ops.rows_to_shadow16(keys, fmt, True, err_max=err)[0], err)
         sh, err = shadows[fmt]
         ref = None
-        cfgs = [(0, (4, 0, 64))] + [(1, c) for c in ctas]
+        cfgs = [(0, (4, 64, 0))] + [(1, c) for c in ctas]
         outs = []
         for g, nc in cfgs:
             setcfg(g, nc)
             s, i, st = ops.cosine_topk_with_stats(q, keys, k, inv, sh, mode, shadow_err=err)
-            st5 = torch.as_strided(st, (5,), (1,)).tolist()       # + {worker CTAs counted by the sweep, (lane, chunk) hits queued}
-            out = {"kind": kind, "N": N, "d": d, "mode": mode, "gshare": g, "sweep_ctas": nc[0] if g else 0, "sleep_div": nc[1], "prepass_div": nc[2],
+            st5 = st.tolist()
+            out = {"kind": kind, "N": N, "d": d, "mode": mode, "gshare": g, "sweep_ctas": nc[0] if g else 0, "prepass_div": nc[1], "dbg": nc[2],
                    "pass2_rows": int(st5[0]), "fp32_rows": int(st5[1]), "hits_queued": int(st5[4]) & 0xffffffff,
                    "rows_differ_vs_fp32": int((i[rows] != i0).any(dim=1).sum()), "max_score_diff_vs_fp32": float((s[rows] - s0).abs().max())}
             if ref is None:
@@ -66,4 +65,4 @@ for kind in kinds:
             ms = sorted(ts)[len(ts) // 2]
             out.update({"ms": round(ms, 3), "ms_all": [round(t, 3) for t in ts], "tflops": round(2 * Q * N * d / ms / 1e9, 1)})
             print(json.dumps(out), flush=True)
-    L.tc_set_option("gshare", -1); L.tc_set_option("gshare_ctas", -1); L.tc_set_option("gshare_sleep", -1); L.tc_set_option("prepass_div", -1)
+    L.tc_set_option("gshare", -1); L.tc_set_option("gshare_ctas", -1); L.tc_set_option("prepass_div", -1); L.tc_set_option("gshare_dbg", 0)
