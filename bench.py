@@ -609,7 +609,7 @@ def main():
                 line["spmm"] = {"skipped": f"OOM: {str(e)[:80]}"}
         if world == 1 and not args.no_extras:
             for name, fn in (("gather", bench_gather), ("cfg3", bench_cfg3), ("gpu_stock_baseline", bench_stock_retrieve),
-                             ("small", bench_small)):
+                             ("small", bench_small), ("edge_widek", bench_edge_widek)):
                 try:
                     line[name] = fn(dev, args, peaks)
                 except Exception as e:                              # an extra must never cost the headline line
@@ -813,6 +813,41 @@ def bench_small(dev, args, peaks):
                      "stock_torch_us": wall_us(stock, iters), "rows_identical_to_stock": same}
         out[name]["ours_speedup"] = out[name]["stock_torch_us"] / out[name]["ours_us"]
     return out
+
+
+def bench_edge_widek(dev, args, peaks):
+    """The edge variant's vanilla phase (RAGraph_edge/modules/RAGraph.py:36-38, 298-311): batches of 32 768 node embeddings
+    (d = 64) against the whole resource library, retrieve_num = 50 -- k beyond the 32-entry candidate lists, served on the
+    tensor cores by MORE KEY SPLITS.  Ours (store.topk: automatic exact mode) vs the fp32 CUDA-core kernel and
+    the reference's calls on stock torch (normalize + matmul + topk, query-chunked: [32768, 240000] fp32 is 31 GB)."""
+    import ragraph_b200 as R
+    from ragraph_b200 import _lib as L, ops
+    Q, N, d, k = 32768, 240_000, 64, 50
+    g = torch.Generator(device=dev).manual_seed(11)
+    keys = torch.randn(N, d, generator=g, device=dev)
+    q = torch.randn(Q, d, generator=g, device=dev)
+    base = R.ToyGraphBase(None, 2, d, 3, device=dev, capacity=N)
+    base.add_entries(keys, keys, torch.zeros(N, 2, device=dev))
+    s1, i1 = base.topk(q, k)
+    inv = ops.row_inv_norm(base.resource_keys)
+    s0, i0 = ops.cosine_topk(q, base.resource_keys, k, inv)
+    chunk = 4096
+
+    def stock():
+        kn = F.normalize(keys, p=2, dim=-1)
+        outs = [torch.topk(torch.matmul(F.normalize(q[a:a + chunk], p=2, dim=-1), kn.t()), k, largest=True, sorted=True)
+                for a in range(0, Q, chunk)]
+        return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+    ss, si = stock()
+    ms = timeit_events(lambda: base.topk(q, k), 5, 2)
+    ms_f32 = timeit_events(lambda: ops.cosine_topk(q, base.resource_keys, k, inv), 2, 1)
+    ms_stock = timeit_events(stock, 2, 1)
+    # rows whose index lists differ from the fp32 kernel's / stock torch's must be near-ties: compare the score rows
+    return {"workload": f"top-{k} cosine, Q={Q} N={N} d={d} (edge variant, vanilla phase)", "ours_ms": ms,
+            "fp32_kernel_ms": ms_f32, "stock_torch_ms": ms_stock, "ours_over_stock": ms_stock / ms, "ours_over_fp32_kernel": ms_f32 / ms,
+            "tflops": 2.0 * Q * N * d / ms / 1e9, "max_score_diff_vs_fp32_kernel": float((s1 - s0).abs().max()),
+            "max_score_diff_vs_stock": float((s1 - ss).abs().max()),
+            "rows_idx_differ_vs_stock": int((i1 != si).any(dim=1).sum()), "rows_idx_differ_vs_fp32_kernel": int((i1 != i0).any(dim=1).sum())}
 
 
 if __name__ == "__main__":

@@ -1323,6 +1323,9 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
     }
     tmax = warp_max(tmax);
     if (a.thr0) tmax = fmaxf(tmax, __ldg(a.thr0 + row));
+    // (diagnostic for the format policy: what would bound the row under a LARGER error bound -- the shared threshold below
+    // sits 2 eps under the k-th best by construction and would move with eps, the list minima and the pre-pass bound would not)
+    const float tmax_lists = tmax;
     if (a.part_thr) {
       float tp = -INFINITY;
       for (int sp = lane; sp < a.n_splits; sp += 32) tp = fmaxf(tp, __ldg(a.part_thr + (size_t)sp * a.Q + row));
@@ -1399,7 +1402,7 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
       a.out_scores[row * a.k + p] = lv[p];
       a.out_idx[row * a.k + p] = (li[p] == INT64_MAX) ? (int64_t)-1 : li[p] + a.idx_offset;
     }
-    if (a.exact && a.loose_count && lane == 0 && !(have_k && kth > tmax + a.loose_mult * eps)) atomicAdd(a.loose_count, 1);
+    if (a.exact && a.loose_count && lane == 0 && !(have_k && kth > tmax_lists + a.loose_mult * eps)) atomicAdd(a.loose_count, 1);
     if (!certified && lane == 0) {
       const int slot = atomicAdd(a.fb_count, 1);
       a.fb_rows[slot] = (int32_t)row;

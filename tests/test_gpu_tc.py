@@ -270,9 +270,9 @@ def test_cross_split_threshold_sharing_same_results(mode):
         res[g] = (s.clone(), i.clone(), st.tolist())
     L.tc_set_option("gshare", -1); L.tc_set_option("variant", -1)
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
-    assert res[0][2][3] == 0 and res[1][2][3] == 140, (res[0][2], res[1][2])      # worker CTAs seen by the sweep
-    assert res[1][2][4] < res[0][2][4], (res[0][2], res[1][2])                    # fewer hits queued
-    if mode != L.SIM_BF16:
+    if mode != L.SIM_BF16:                                                         # (the raw modes leave no counters)
+        assert res[0][2][3] == 0 and res[1][2][3] == 140, (res[0][2], res[1][2])  # worker CTAs seen by the sweep
+        assert res[1][2][4] < res[0][2][4], (res[0][2], res[1][2])                # fewer hits queued
         rows = torch.arange(0, Q, 16, device=DEV)
         s0, i0 = ops.cosine_topk(qd[rows].contiguous(), kd, k, inv)
         assert float((res[1][0][rows] - s0).abs().max()) < 2e-6

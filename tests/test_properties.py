@@ -220,3 +220,85 @@ def test_filter_refine_certificate_model(seed, k, clustered, prepass):
         assert ok, bad
     if not clustered:
         assert cert.all()                                     # well separated random keys always certify
+
+
+def _streaming_shared_threshold_model(approx_row, exact_row, k, kp, n_splits, eps, rng, margin_mult=2.0):
+    """NumPy model of ONE query row through the query-stationary filter with cross-split threshold sharing (DESIGN.md 3.1,
+    TcArgs::pool), independent of the CUDA code.  The key splits advance in an arbitrary interleaving; a split accepts a key
+    iff its approximate score beats the split's threshold, keeps its kp best (threshold = the kp-th best once it has kp),
+    and mirrors accepted scores into a pool of published scores (any subset may be visible, slots may be overwritten by later
+    candidates: both are modelled by publishing each accepted score with probability 1/2 and dropping a random published
+    one now and then).  At random moments the sweep takes the k-th largest published score minus margin_mult * eps as the
+    shared bound, which every split folds into its threshold at a random later moment.  Refine: t_split = max(the threshold
+    a split ended with, its list minimum if full); certify iff the k-th exact score > max t_split + eps."""
+    N = approx_row.shape[0]
+    bounds = np.linspace(0, N, n_splits + 1).astype(int)
+    pos = bounds[:-1].copy()
+    lists = [[] for _ in range(n_splits)]                  # (approx, idx)
+    thr = np.full(n_splits, -np.inf)
+    seen_bound = np.full(n_splits, -np.inf)
+    published, shared = [], -np.inf
+    live = [s for s in range(n_splits) if pos[s] < bounds[s + 1]]
+    while live:
+        s = live[rng.integers(len(live))]
+        j = pos[s]; pos[s] += 1
+        if pos[s] >= bounds[s + 1]:
+            live.remove(s)
+        if rng.random() < 0.3:                              # the split reads the shared bound (possibly a stale one)
+            seen_bound[s] = shared
+            thr[s] = max(thr[s], seen_bound[s])
+        a = approx_row[j]
+        if a > thr[s]:
+            lists[s].append((a, j))
+            if rng.random() < 0.5:
+                published.append(a)
+            if len(lists[s]) > kp:
+                lists[s].sort(key=lambda t: (-t[0], t[1]))
+                lists[s] = lists[s][:kp]
+            if len(lists[s]) == kp:
+                thr[s] = max(thr[s], min(t[0] for t in lists[s]))
+        if published and rng.random() < 0.05:
+            published.pop(rng.integers(len(published)))     # a slot overwritten before the sweep saw it
+        if len(published) >= k and rng.random() < 0.2:      # a sweep
+            shared = max(shared, np.sort(published)[-k] - margin_mult * eps - 1e-6)
+    cand = sorted({j for l in lists for _, j in l})
+    if len(cand) < k:
+        return None, False
+    tmax = max(max(thr[s], min((t[0] for t in lists[s]), default=-np.inf) if len(lists[s]) == kp else -np.inf) for s in range(n_splits))
+    cand = np.array(cand, dtype=np.int64)
+    a = approx_row[cand]
+    tau = np.sort(a)[-k]
+    sel = cand[a >= tau - 2 * eps]
+    e = exact_row[sel]
+    order = np.lexsort((sel, -e))[:k]
+    return sel[order], bool(e[order[-1]] > tmax + eps)
+
+
+@FAST
+@given(seed=st.integers(0, 2 ** 31 - 1), k=st.integers(1, 10), clustered=st.booleans())
+def test_cross_split_shared_threshold_model(seed, k, clustered):
+    """Sharing thresholds across key splits never costs exactness: whatever subset of the candidates the sweep sees and
+    however stale the bound a split folds in, a certified row is the exact top-k -- and with margin 2 eps rows whose splits
+    never overflow a list do certify (the bound sits far enough under the k-th best by construction)."""
+    g = torch.Generator().manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    Q, N, d, kp, n_splits = 4, 360, 32, 16, 4
+    keys = torch.randn(N, d, generator=g)
+    if clustered:
+        cent = torch.randn(4, d, generator=g)
+        keys = cent[torch.randint(0, 4, (N,), generator=g)] + 0.02 * keys
+        keys[1] = keys[0]
+    q = torch.randn(Q, d, generator=g)
+    qn = torch.nn.functional.normalize(q, dim=-1); kn = torch.nn.functional.normalize(keys, dim=-1)
+    approx = (qn.bfloat16().double() @ kn.bfloat16().double().T).numpy()
+    exact = (qn.double() @ kn.double().T).numpy()
+    eps = 2.0 ** -8 + 2.0 ** -10
+    n_cert = 0
+    for r in range(Q):
+        idx, cert = _streaming_shared_threshold_model(approx[r], exact[r], k, kp, n_splits, eps, rng)
+        if cert:
+            n_cert += 1
+            ok, bad = O.topk_sets_match(idx[None, :], exact[r][None, :], k)
+            assert ok, bad
+    if not clustered:
+        assert n_cert > 0                                   # spread-out keys: the certificate does hold with a shared bound

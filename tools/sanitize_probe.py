@@ -27,6 +27,24 @@ for mode, fmt in ((L.SIM_F16_REFINE, L.FMT_F16), (L.SIM_BF16_REFINE, L.FMT_BF16)
         torch.cuda.synchronize()
         assert float((s - s0).abs().max()) < 2e-6, (mode, variant)
         print(f"mode {mode} variant {variant}: ok, pass2 rows {int(st[0])}, fp32 rows {int(st[1])}", flush=True)
+# cross-split threshold sharing (sweeping CTAs next to the workers) and k > 26 (more key splits): 10 query tiles x 14 splits
+L.tc_set_option("variant", 2)
+Q2, N2, d2 = 2400, 14 * 64 * 128, 64
+keys2 = torch.randn(N2, d2, generator=g).to(dev); q2 = torch.randn(Q2, d2, generator=g).to(dev)
+inv2 = ops.row_inv_norm(keys2)
+err2 = torch.zeros(1, device=dev)
+sh2, _ = ops.rows_to_shadow16(keys2, L.FMT_F16, True, err_max=err2)
+rows = torch.arange(0, Q2, 8, device=dev)
+for kk in (10, 50):
+    if kk == 50:          # 32-entry lists: a shorter stream (racecheck slows the kernel ~100x; its barrier waits trap after 10 s)
+        q2, keys2, inv2, sh2 = q2[:520].contiguous(), keys2[:40000].contiguous(), inv2[:40000].contiguous(), sh2[:40000].contiguous()
+        rows = torch.arange(0, 520, 8, device=dev)
+    s, i, st = ops.cosine_topk_with_stats(q2, keys2, kk, inv2, sh2, L.SIM_F16_REFINE, shadow_err=err2)
+    sr, ir = ops.cosine_topk(q2[rows].contiguous(), keys2, kk, inv2)
+    torch.cuda.synchronize()
+    assert float((s[rows] - sr).abs().max()) < 2e-6, kk
+    print(f"sweep / wide-k probe k={kk}: ok, worker CTAs seen by the sweep {int(st[3])}, hits queued {int(st[4])}", flush=True)
+L.tc_set_option("variant", -1)
 vals = torch.randn(N, d, device=dev)
 out = ops.gather_rows(vals, i0)
 assert torch.equal(out, vals[i0])
