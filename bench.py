@@ -812,7 +812,67 @@ def bench_small(dev, args, peaks):
         out[name] = {"workload": f"retrieve Q={Q} N={N} d={d} k={k}", "ours_us": wall_us(ours, iters),
                      "stock_torch_us": wall_us(stock, iters), "rows_identical_to_stock": same}
         out[name]["ours_speedup"] = out[name]["stock_torch_us"] / out[name]["ours_us"]
+    out["cfg1_forward"] = _bench_forward(dev, wall_us, "node", 2708, 1433, 256, 7, 10832, 4, 3, 0.5)
+    out["cfg2_forward"] = _bench_forward(dev, wall_us, "graph", 40, 3, 256, 2, 480, 3, 1, 0.3)
     return out
+
+
+def _bench_forward(dev, wall_us, variant, n, f, d, C, N, k, hops, w):
+    """BASELINE configs 1 / 2 as the reference runs them: a whole RAGraph.forward (RAGraph_node/RAGraph.py:39-63 over a
+    Cora-shaped graph; RAGraph_graph/RAGraph.py:58-75 over one PROTEINS-shaped graph, the query = mean node embedding) --
+    retrieve + gathers + k-hop propagation + decoder + fusion, with a one-layer GCN as the pre-trained encoder.  Ours
+    eager, ours replayed as one CUDA graph (graphs.GraphedForward), the reference's formulas on stock torch."""
+    import ragraph_b200 as R
+    g = torch.Generator(device=dev).manual_seed(3)
+    a = (torch.rand(n, n, generator=g, device=dev) < 3.9 / n).float()
+    a = torch.triu(a, 1); a = a + a.t() + torch.eye(n, device=dev)
+    dinv = a.sum(1).pow(-0.5); adj = (dinv[:, None] * a * dinv[None, :]).contiguous()
+    x = torch.randn(n, f, generator=g, device=dev)
+    keys = F.normalize(torch.randn(N, d, generator=g, device=dev), dim=-1)
+    vals = torch.randn(N, d, generator=g, device=dev)
+    labs = F.one_hot(torch.randint(0, C, (N,), generator=g, device=dev), C).float()
+
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gcn = R.GCN(f, d, "prelu")
+
+        def inference(self, features, adj_):
+            return self.gcn([features, adj_])
+    base = R.ToyGraphBase(None, C, d, 3, device=dev, capacity=N, variant=variant)
+    base.retrieve_num = k
+    base.add_entries(keys, vals, labs)
+    model = R.RAGraph(Enc(), base, f, C, d, variant=variant).to(dev).eval()
+    enc, dec = model.pretrain_model.gcn, model.decoder
+
+    def ours():
+        with torch.no_grad():
+            return model(x, adj)
+
+    def stock():
+        with torch.no_grad():
+            emb = enc.act(torch.mm(adj, enc.fc(x)) + enc.bias)                      # layers/gcn.py:32-40
+            qv = emb if variant == "node" else emb.mean(0, keepdim=True)
+            s = torch.matmul(F.normalize(qv, p=2, dim=-1), F.normalize(keys, p=2, dim=-1).t())
+            _, i = torch.topk(s, k, largest=True, sorted=True)
+            re, rl = vals[i].sum(1), labs[i].mean(1)
+            an = adj / adj.sum(1, keepdim=True)
+            h = emb
+            for _ in range(hops):
+                h = F.relu(torch.matmul(an, h))
+            if variant == "graph":
+                h = h.mean(0, keepdim=True)
+            h = h * (1 - w) + re * w
+            return torch.softmax(dec(h), 1) * (1 - w) + rl * w
+    graphed = R.GraphedForward(model, x, adj)
+    o_e, o_s, o_g = ours(), stock(), graphed(x).clone()
+    res = {"workload": f"RAGraph.forward {variant} variant: n={n} f={f} d={d} library N={N} k={k}, {hops} hop(s) (dense [n,n] adjacency in)",
+           "ours_eager_us": wall_us(ours, 200), "ours_graphed_us": wall_us(lambda: graphed(x), 200),
+           "stock_torch_us": wall_us(stock, 200), "graphed_equals_eager": bool(torch.equal(o_e, o_g)),
+           "max_abs_diff_vs_stock": float((o_e - o_s).abs().max())}
+    res["graphed_speedup_vs_stock"] = res["stock_torch_us"] / res["ours_graphed_us"]
+    res["eager_speedup_vs_stock"] = res["stock_torch_us"] / res["ours_eager_us"]
+    return res
 
 
 def bench_edge_widek(dev, args, peaks):

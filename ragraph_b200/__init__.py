@@ -13,11 +13,12 @@ from .ragraph_utils import Propagation, SimilarityFunctions, TaskDecoder, ToyGra
 from .RAGraph import RAGraph, RAGraphFewShot
 from .sampling import InverseSampling
 from . import downprompt, fewshot
+from .graphs import GraphedForward
 from .sharded import ShardedRetriever, owner_of, shard_bounds
 from .utility import normalized_adjacency_csr, process_graph_batch, process_tu_dataset
 
 __all__ = ["_lib", "ops", "CSRGraph", "as_csr", "EdgeAggregator", "edge_rag_forward", "rating_topk", "scatter_add", "scatter_sum",
            "GCN", "Propagation", "SimilarityFunctions", "TaskDecoder", "ToyGraphBase", "RAGraph", "RAGraphFewShot", "downprompt", "fewshot",
            "relative_edge_time_encoding", "scatter_softmax", "make_resource_graph", "InverseSampling",
-           "ShardedRetriever", "owner_of", "shard_bounds", "normalized_adjacency_csr", "process_graph_batch", "process_tu_dataset"]
+           "GraphedForward", "ShardedRetriever", "owner_of", "shard_bounds", "normalized_adjacency_csr", "process_graph_batch", "process_tu_dataset"]
 __version__ = "0.1.0"

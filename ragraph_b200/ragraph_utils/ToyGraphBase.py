@@ -392,6 +392,8 @@ class ToyGraphBase:
         Q = search_keys.shape[0]
         flags = 0
         adapt = self.mode is None and mode == L.SIM_F16_REFINE and Q * self._n >= self.ADAPT_MIN_SCORES
+        if adapt and torch.cuda.is_current_stream_capturing():
+            adapt = False                       # (graphs.GraphedForward: the policy's events / pinned copies stay out of a capture)
         if adapt:
             self._policy_poll()
             if self._pol["fmt"] == L.FMT_BF16:
