@@ -147,7 +147,8 @@ RAG_API int rag_cosine_topk_f32(const float* q, int64_t Q, const float* keys, co
                         int32_t mode, uint32_t flags, int64_t idx_offset, float* out_scores, int64_t* out_idx,
                         void* workspace, size_t workspace_bytes, rag_stream_t stream);
 /* Byte offsets, inside the caller's workspace of the same (Q, N, d, k, mode), of three consecutive int32 counters the
- * *_REFINE modes leave behind: offsets_out[0] = rows that needed the second tensor-core pass, offsets_out[1] = rows that
+ * *_REFINE modes leave behind: offsets_out[0] = rows the first pass could not certify (they take the second tensor-core pass;
+ * libraries below 32 768 keys, or "pass2" = 0, send them straight to the fp32 kernel), offsets_out[1] = rows that
  * fell back to the fp32 kernel, offsets_out[2] = rows whose certificate would fail under an 8x larger error bound (what a
  * bf16 filter would have: lets a caller running fp16 decide whether bf16 would do).  Two diagnostic words follow at
  * offsets_out[0] + 12 and + 16: the worker CTAs counted by the cross-split threshold sweep (0 = the sweep did not run) and

@@ -28,7 +28,7 @@ namespace rag {
 
 constexpr int SPMM_THREADS = 256;
 constexpr int SPMM_WARPS = SPMM_THREADS / 32;
-constexpr int ROWS_PER_GRAB = 64;   // rows per dynamic work item (8 per warp)
+constexpr int ROWS_PER_GRAB = 64;   // rows per dynamic work item (8 per warp) on large graphs; see SpmmArgs::rows_per_grab
 constexpr int LONG_ROW = 1024;      // rows with more nonzeros are split across the CTA
 constexpr int STAGE = 32;           // (col,val) entries per cp.async tile
 
@@ -48,6 +48,10 @@ struct SpmmArgs {
   uint32_t epi; const float* bias; const float* alpha; const float* blend_in; float blend_w;
   const float* accum_in; float* Y;
   unsigned long long* work_counter;   // dynamic row-block scheduler
+  // rows per work item: ROWS_PER_GRAB on large graphs; small graphs (the reference's real ones: a few thousand rows of ~5
+  // non-zeros, where a row is three dependent memory round trips) get down to one row per warp, so that every SM has work
+  // and no warp walks eight latency chains back to back (measured, Cora-shaped graph n = 2 708: 24 us -> see DESIGN 3.4)
+  int rows_per_grab;
 };
 
 __device__ __forceinline__ int64_t load_ptr(const void* rowptr, int is64, int64_t i) {
@@ -176,7 +180,7 @@ csr_spmm_kernel(const SpmmArgs a) {
   __shared__ long long s_block;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n_blocks = (a.n_rows + ROWS_PER_GRAB - 1) / ROWS_PER_GRAB;
+  const int64_t n_blocks = (a.n_rows + a.rows_per_grab - 1) / a.rows_per_grab;
 
   for (;;) {
     __syncthreads();                               // s_block / s_part reuse
@@ -184,8 +188,8 @@ csr_spmm_kernel(const SpmmArgs a) {
     __syncthreads();
     const int64_t blk = s_block;
     if (blk >= n_blocks) break;
-    const int64_t r0 = blk * ROWS_PER_GRAB;
-    const int64_t r1 = min(r0 + (int64_t)ROWS_PER_GRAB, a.n_rows);
+    const int64_t r0 = blk * a.rows_per_grab;
+    const int64_t r1 = min(r0 + (int64_t)a.rows_per_grab, a.n_rows);
 
     // pass 1: short rows, one warp each (rows interleaved across the 8 warps)
     bool any_long = false;
@@ -283,8 +287,10 @@ static int launch_spmm(SpmmArgs a, cudaStream_t s) {
   e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(work_counter)");
   const int resident = (VPL <= 2 ? 4 : 2);
-  int64_t n_blocks = (a.n_rows + ROWS_PER_GRAB - 1) / ROWS_PER_GRAB;
   int64_t grid = (int64_t)sm_count() * resident;
+  a.rows_per_grab = ROWS_PER_GRAB;
+  while (a.rows_per_grab > SPMM_WARPS && (a.n_rows + a.rows_per_grab - 1) / a.rows_per_grab < 2 * grid) a.rows_per_grab /= 2;
+  int64_t n_blocks = (a.n_rows + a.rows_per_grab - 1) / a.rows_per_grab;
   if (grid > n_blocks) grid = n_blocks;
   csr_spmm_kernel<LANES, VPL><<<(unsigned)grid, SPMM_THREADS, 0, s>>>(a);
   RAG_LAUNCH_OK("csr_spmm_kernel");
@@ -311,7 +317,7 @@ extern "C" int rag_csr_spmm_f32(const void* rowptr, int32_t ptr_is_64, const int
   RAG_REQUIRE(!(epilogue & RAG_EPI_BLEND) || blend_in, RAG_EINVAL, "csr_spmm: RAG_EPI_BLEND without blend_in");
   RAG_REQUIRE(!(epilogue & RAG_EPI_ACCUM) || accum_in, RAG_EINVAL, "csr_spmm: RAG_EPI_ACCUM without accum_in");
   SpmmArgs a{rowptr, ptr_is_64, col, val, n_rows, n_src, X, F, epilogue, bias, alpha, blend_in, blend_w,
-             accum_in, Y, nullptr};
+             accum_in, Y, nullptr, ROWS_PER_GRAB};
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec = (F % 4 == 0) && aligned16(X) && aligned16(Y) && (!bias || aligned16(bias)) &&
                    (!blend_in || aligned16(blend_in)) && (!accum_in || aligned16(accum_in));

@@ -56,6 +56,7 @@ constexpr int TC_PQ = 4;               // per-row pending-candidate queue depth 
 constexpr float TC_SLACK = 3.0517578125e-05f;           // 2^-15
 constexpr float TC_U_BF16 = 0.00390625f;                // 2^-8
 constexpr float TC_U_F16 = 0.00048828125f;              // 2^-11
+constexpr int64_t TC_PASS2_MIN_KEYS = 32768;             // smaller libraries skip the second tensor-core pass
 constexpr int TC_SPILL_MAX = 1024;                      // pass-2 candidates per row (second tensor-core pass)
 constexpr unsigned long long TC_TIMEOUT_CYCLES = 20000000000ull;   // ~10 s: trap instead of hanging the GPU
 
@@ -1872,7 +1873,9 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
 
   const int32_t* fp32_rows = r.fb_rows;
   const int32_t* fp32_count = fb_count;
-  if (tc_opts().pass2 && a.debug == 0) {
+  // (libraries below TC_PASS2_MIN_KEYS: the fp32 kernel rescans the few uncertified rows faster than two more launches cost
+  //  -- the reference's own shapes are launch-latency problems; the first counter then still holds the uncertified rows)
+  if (tc_opts().pass2 && a.debug == 0 && N >= TC_PASS2_MIN_KEYS) {
     // ---- second pass: the uncertified rows (device-side list, usually empty: the CTAs read the count and leave) rescan
     //      the shard on the tensor cores with the fixed threshold thr2 and return EVERY key above it ----
     TcArgs c = a;

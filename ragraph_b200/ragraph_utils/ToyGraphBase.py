@@ -447,10 +447,10 @@ class ToyGraphBase:
         from .PositionAwareEncoder import PositionAwareEncoder
         return PositionAwareEncoder.encode_position_aware_code(search_adj, self.num_anchors, self.dis_q)
 
-    def _small_retrieve(self, search_keys: Tensor, k: int):
+    def _small_retrieve(self, search_keys: Tensor, k: int, gather: bool = True):
         """The reference's real shapes (one pooled graph query against a few hundred rows, RAGraph_graph/.../ToyGraphBase.py:
         56-87) are launch-latency problems: normalise + scores + top-k + both gathers run as ONE kernel when the shape fits
-        (Q <= 64, N <= 65 536, k <= 16) and no similarity mode was forced.  Returns (values[idx], labels[idx]) or None."""
+        (Q <= 64, N <= 65 536, k <= 16) and no similarity mode was forced.  Returns (idx, values[idx], labels[idx]) or None."""
         if self.mode is not None or self.collect_stats or (self.variant == "node_fewshot" and self.structure_weight != 0.0):
             return None
         n, Q = self._n, search_keys.shape[0]
@@ -466,9 +466,9 @@ class ToyGraphBase:
             return None
         if self._small_ws is None or self._small_ws.numel() < need:
             self._small_ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
-        _, _, emb, lab = ops.retrieve_small(search_keys.contiguous(), self._keys[:n], k, self._values[:n], self._labels[:n],
-                                            self._small_ws)
-        return emb, lab
+        _, idx, emb, lab = ops.retrieve_small(search_keys.contiguous(), self._keys[:n], k, self._values[:n] if gather else None,
+                                              self._labels[:n] if gather else None, self._small_ws)
+        return idx, emb, lab
 
     def retrieve(self, search_keys: Tensor, search_adj, add_noise: bool, search_positions: Optional[Tensor] = None):
         """Same contract as the reference: returns (rag_embeddings[Q,k',d], rag_labels[Q,k',C]).
@@ -482,7 +482,7 @@ class ToyGraphBase:
         gather_rows = ops.direct(ops.gather_rows)
         small = self._small_retrieve(search_keys, retrieve_num) if search_positions is None else None
         if small is not None:
-            rag_embeddings, rag_labels = small
+            _, rag_embeddings, rag_labels = small
         else:
             _, topk_indices = self.topk(search_keys, retrieve_num, search_positions)
             rag_embeddings = gather_rows(self.resource_values, topk_indices)
@@ -517,7 +517,9 @@ class ToyGraphBase:
         if search_keys.dim() == 1:
             search_keys = search_keys.unsqueeze(0)
         k = self.retrieve_num if k is None else k
-        _, idx = self.topk(search_keys, k)
+        # (the graph variant's single pooled query: one launch instead of a 142 us pass of the tiled fp32 kernel over ONE row)
+        small = self._small_retrieve(search_keys, k, gather=False)
+        idx = small[0] if small is not None else self.topk(search_keys, k)[1]
         gather_reduce = ops.direct(ops.gather_reduce)
         emb = self.gather_reduce_blend(idx, reduce, blend_in, blend_w)
         labels = self.resource_labels if self.resource_labels.dtype == torch.float32 else self.resource_labels.float()

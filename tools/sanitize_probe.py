@@ -11,7 +11,7 @@ dev = "cuda"
 g = torch.Generator().manual_seed(0)
 d, k = 128, 10
 cent = torch.randn(6, d, generator=g)
-N, Q = 24000, 300
+N, Q = 40000, 300
 keys = (cent[torch.randint(0, 6, (N,), generator=g)] + 0.1 * torch.randn(N, d, generator=g)).to(dev)
 q = (cent[torch.randint(0, 6, (Q,), generator=g)] + 0.1 * torch.randn(Q, d, generator=g)).to(dev)
 keys[100:140] = keys[7]                                   # duplicates: ties + spill

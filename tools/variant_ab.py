@@ -1,6 +1,6 @@
 """A/B of the tensor-core filter kernel variants on ONE GPU (event-timed medians):
 
-    python tools/variant_ab.py [N d]...     default: 12.5 M x 128 and 10 M x 256; Q = 4096, k = 10
+    python tools/variant_ab.py [N d]...     default: 12.5 M x 128 and 10 M x 256; Q = 4096, k = 10 (AB_Q / AB_K override)
 
 variant ts = query tile stationary in tensor memory, ss = query tile in shared memory; for each: exact mode 3, raw
 mode 2, MMA only (RAG_TC_DEBUG=1: epilogue skips TMEM reads) and MMA + TMEM loads without the filter (=2).
@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ragraph_b200 import ops, _lib as L
 
-dev, Q, k = "cuda", 4096, 10
+dev, Q, k = "cuda", int(os.environ.get("AB_Q", 4096)), int(os.environ.get("AB_K", 10))
 
 
 def med(fn, iters=12, warmup=3):
