@@ -1635,9 +1635,9 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = f
   // registers (<= 512); the zero block is then [header | spill counters Q | gthr Qpad | pool Qpad * S * kp].  The workspace
   // reserve depends on the shape only (not on options), so offsets are the same for every call of a shape.
   const int64_t Qpad = (int64_t)p.n_qtiles * TC_ROWS;
-  const bool share_shape = ts && !tf32 && p.n_splits > 1 && p.n_splits * kp_layout <= 512 && sm_count() > p.n_qtiles * p.n_splits;
+  const bool share_shape = ts && !tf32 && p.n_splits > 1 && p.n_splits * 16 <= 512 && sm_count() > p.n_qtiles * p.n_splits;
   p.n_mergers = 0;
-  if (share_shape && o.gshare && p.tiles_per_split >= o.prepass_min_tiles)
+  if (share_shape && o.gshare && p.n_splits * p.kp <= 512 && p.tiles_per_split >= o.prepass_min_tiles)
     p.n_mergers = std::min(o.gshare_ctas, sm_count() - p.n_qtiles * p.n_splits);
   p.n_zero = TC_ZERO_HDR + Q;
   p.n_zero_share = TC_ZERO_HDR + Q + Qpad + Qpad * p.n_splits * p.kp;
