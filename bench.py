@@ -609,7 +609,7 @@ def main():
                 line["spmm"] = {"skipped": f"OOM: {str(e)[:80]}"}
         if world == 1 and not args.no_extras:
             for name, fn in (("gather", bench_gather), ("cfg3", bench_cfg3), ("gpu_stock_baseline", bench_stock_retrieve),
-                             ("small", bench_small), ("edge_widek", bench_edge_widek)):
+                             ("small", bench_small), ("edge_widek", bench_edge_widek), ("edge_eval", bench_edge_eval)):
                 try:
                     line[name] = fn(dev, args, peaks)
                 except Exception as e:                              # an extra must never cost the headline line
@@ -908,6 +908,37 @@ def bench_edge_widek(dev, args, peaks):
             "tflops": 2.0 * Q * N * d / ms / 1e9, "max_score_diff_vs_fp32_kernel": float((s1 - s0).abs().max()),
             "max_score_diff_vs_stock": float((s1 - ss).abs().max()),
             "rows_idx_differ_vs_stock": int((i1 != si).any(dim=1).sum()), "rows_idx_differ_vs_fp32_kernel": int((i1 != i0).any(dim=1).sum())}
+
+
+def bench_edge_eval(dev, args, peaks):
+    """The edge variant's evaluation ranking (RAGraph_edge/utils/metrics.py:96-118): a batch of user embeddings against
+    every item (d = 64), history items excluded, top-20.  Ours on the tensor cores (edge.rating_topk: fp16 filter over the
+    scaled item table + fp32 refine that drops the history + certificate), ours on the fp32 CUDA-core kernel, and the
+    reference's formulation on stock torch kept on the GPU (matmul -> masked_fill of the history -> topk; the reference
+    moves the [B, n_items] matrix to the CPU first, :110-117)."""
+    from ragraph_b200 import edge as E
+    B, I, d, k, h = 4096, 100_000, 64, 20, 30
+    g = torch.Generator(device=dev).manual_seed(13)
+    users = torch.randn(B, d, generator=g, device=dev) * 0.3
+    items = torch.randn(I, d, generator=g, device=dev) * (0.5 + torch.rand(I, 1, generator=g, device=dev))
+    hist_items = torch.randint(0, I, (B, h), generator=g, device=dev).sort(dim=1).values.reshape(-1)
+    rowptr = torch.arange(0, (B + 1) * h, h, device=dev, dtype=torch.int64)
+    rows = torch.arange(B, device=dev).repeat_interleave(h)
+
+    def stock():
+        pred = torch.matmul(users, items.t())
+        pred[rows, hist_items] = float("-inf")
+        return torch.topk(pred, k)[1]
+    i_tc = E.rating_topk(users, items, k, rowptr, hist_items, tensor_cores=True)
+    i_f32 = E.rating_topk(users, items, k, rowptr, hist_items, tensor_cores=False)
+    i_st = stock()
+    ms_tc = timeit_events(lambda: E.rating_topk(users, items, k, rowptr, hist_items, tensor_cores=True), 10, 3)
+    ms_f32 = timeit_events(lambda: E.rating_topk(users, items, k, rowptr, hist_items, tensor_cores=False), 5, 2)
+    ms_st = timeit_events(stock, 5, 2)
+    return {"workload": f"masked dot-product top-{k}: {B} users x {I} items, d={d}, {h} history items per user",
+            "ours_tensor_core_ms": ms_tc, "ours_fp32_kernel_ms": ms_f32, "stock_torch_gpu_ms": ms_st,
+            "ours_over_stock": ms_st / ms_tc, "rows_identical_tc_vs_fp32_kernel": float((i_tc == i_f32).all(dim=1).float().mean()),
+            "rows_identical_tc_vs_stock": float((i_tc == i_st).all(dim=1).float().mean())}
 
 
 if __name__ == "__main__":

@@ -188,6 +188,20 @@ RAG_API int rag_topk_masked_f32(const float* q, int64_t Q, const float* keys, co
                         int64_t idx_offset, float* out_scores, int64_t* out_idx, void* workspace,
                         size_t workspace_bytes, rag_stream_t stream);
 
+/* The same ranking on the tensor cores (exact: 16-bit filter + fp32 refine + certificate, mode = RAG_SIM_F16_REFINE or
+ * RAG_SIM_BF16_REFINE; d <= 128 with k <= 128, d <= 256 with k <= 10).  The filter ignores the exclusion lists; the refine
+ * passes drop excluded candidates, a row whose candidate lists hold fewer than k admissible keys fails its certificate and
+ * takes the second pass / the fp32 kernel, so results equal rag_topk_masked_f32's (ties within 1e-6 aside).
+ * RAG_SIM_DOT: keys_shadow = rag_rows_to_shadow16(keys * key_scale, normalize = 0) with key_scale = 1 / max_j |keys[j]| (row
+ * norms <= 1; shadow_err = that shadow's err_max), key_inv_norm unused (may be NULL); returned scores are q . k.
+ * Without RAG_SIM_DOT (cosine): key_scale = 0, shadow / key_inv_norm as for rag_cosine_topk_f32.
+ * Workspace: rag_cosine_topk_workspace(Q, N, d, k, mode). */
+RAG_API int rag_topk_masked_tc_f32(const float* q, int64_t Q, const float* keys, const float* key_inv_norm,
+                           const void* keys_shadow, const float* shadow_err, int64_t N, int32_t d, int32_t k,
+                           int32_t mode, uint32_t flags, float key_scale, const int64_t* mask_rowptr,
+                           const int64_t* mask_col, int64_t idx_offset, float* out_scores, int64_t* out_idx,
+                           void* workspace, size_t workspace_bytes, rag_stream_t stream);
+
 /* weighted two-metric variant (RAGraph_node_fewshot/ragraph_utils/ToyGraphBase.py:47-79):
  * score = w_a * cos(qa, ka) + w_b * cos(qb, kb), fp32 path only. */
 RAG_API size_t rag_cosine2_topk_workspace(int64_t Q, int64_t N, int32_t da, int32_t db, int32_t k);

@@ -49,6 +49,8 @@ SIGNATURES = {
     "rag_retrieve_small_workspace": (_sz, [_i64, _i64, _i32, _i32]),
     "rag_retrieve_small_f32": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _u32, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "rag_topk_masked_f32": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _u32, _p, _p, _i64, _p, _p, _p, _sz, _p]),
+    "rag_topk_masked_tc_f32": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, C.c_float, _p, _p, _i64, _p, _p,
+                                        _p, _sz, _p]),
     "rag_cosine2_topk_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "rag_cosine2_topk_f32": (C.c_int, [_p, _p, _i32, _f32, _p, _p, _i32, _f32, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
     "rag_topk_merge": (C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _p, _p, _p]),

@@ -14,7 +14,8 @@ bool topk_tc_tf32_available(int d, int k);
 int topk_tc_tf32_dpad(int d);
 int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const void* keys_shadow,
                 const float* shadow_err, int64_t N, int d, int k, int mode, uint32_t flags, int64_t idx_offset,
-                float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s);
+                float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s,
+                const int64_t* mask_rowptr = nullptr, const int64_t* mask_col = nullptr, float key_scale = 0.f);
 void topk_tc_stat_offsets(int64_t Q, int64_t N, int d, int k, int mode, size_t* out);
 
 // out[r, :] = [ wa * xa[r]/max(|xa[r]|,eps)  (padded to da4) | wb * xb[r]/max(|xb[r]|,eps) (padded to db4) ]
@@ -108,6 +109,23 @@ extern "C" int rag_topk_masked_f32(const float* q, int64_t Q, const float* keys,
               "topk_masked: mask_col without mask_rowptr");
   return rag::topk_f32_run(q, Q, keys, key_inv_norm, N, d, k, flags, idx_offset, out_scores, out_idx, workspace,
                            workspace_bytes, (cudaStream_t)stream, mask_rowptr, mask_rowptr ? mask_col : nullptr);
+}
+
+extern "C" int rag_topk_masked_tc_f32(const float* q, int64_t Q, const float* keys, const float* key_inv_norm,
+                                      const void* keys_shadow, const float* shadow_err, int64_t N, int32_t d, int32_t k,
+                                      int32_t mode, uint32_t flags, float key_scale, const int64_t* mask_rowptr,
+                                      const int64_t* mask_col, int64_t idx_offset, float* out_scores, int64_t* out_idx,
+                                      void* workspace, size_t workspace_bytes, rag_stream_t stream) {
+  int st = check_topk_args("topk_masked_tc", q, Q, keys, N, d, k, out_scores, out_idx);
+  if (st || Q == 0) return st;
+  RAG_REQUIRE(mode == RAG_SIM_BF16_REFINE || mode == RAG_SIM_F16_REFINE, RAG_EUNSUPPORTED,
+              "topk_masked_tc: mode %d (exact tensor-core modes only: RAG_SIM_BF16_REFINE / RAG_SIM_F16_REFINE)", mode);
+  RAG_REQUIRE(keys_shadow, RAG_EINVAL, "topk_masked_tc: needs the key shadow (rag_rows_to_shadow16)");
+  RAG_REQUIRE((mask_rowptr == nullptr) == (mask_col == nullptr) || mask_rowptr, RAG_EINVAL,
+              "topk_masked_tc: mask_col without mask_rowptr");
+  return rag::topk_tc_run(q, Q, keys, key_inv_norm, keys_shadow, shadow_err, N, d, k, mode, flags, idx_offset, out_scores,
+                          out_idx, workspace, workspace_bytes, (cudaStream_t)stream, mask_rowptr,
+                          mask_rowptr ? mask_col : nullptr, key_scale);
 }
 
 extern "C" size_t rag_cosine2_topk_workspace(int64_t Q, int64_t N, int32_t da, int32_t db, int32_t k) {

@@ -392,11 +392,12 @@ size_t topk_f32_rows_workspace(int64_t Q, int64_t N, int d, int k) { return tk_p
 
 int topk_f32_run_rows(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const float* q_inv_norm,
                       int64_t N, int d, int k, int64_t idx_offset, const int32_t* row_map, const int32_t* n_rows_dev,
-                      float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
+                      float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s,
+                      const int64_t* mask_rowptr, const int64_t* mask_col) {
   TkPlan p = tk_plan(Q, N, d, k, false);
   RAG_REQUIRE(ws_bytes >= p.total, RAG_EWORKSPACE, "cosine_topk(rows): workspace %zu < %zu bytes", ws_bytes, p.total);
   return topk_f32_core(q, Q, keys, key_inv_norm, q_inv_norm, N, d, k, idx_offset, p, static_cast<unsigned char*>(ws),
-                       row_map, n_rows_dev, out_scores, out_idx, s);
+                       row_map, n_rows_dev, out_scores, out_idx, s, mask_rowptr, mask_col);
 }
 
 }  // namespace rag

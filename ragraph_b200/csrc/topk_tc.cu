@@ -38,7 +38,8 @@ namespace rag {
 // topk_f32.cu: fp32 path restricted to a device-side list of rows
 int topk_f32_run_rows(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const float* q_inv_norm,
                       int64_t N, int d, int k, int64_t idx_offset, const int32_t* row_map, const int32_t* n_rows_dev,
-                      float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s);
+                      float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s,
+                      const int64_t* mask_rowptr = nullptr, const int64_t* mask_col = nullptr);
 size_t topk_f32_rows_workspace(int64_t Q, int64_t N, int d, int k);
 
 constexpr int TC_ROWS = 256;          // query rows per CTA (2 row blocks of 128)
@@ -1267,6 +1268,15 @@ struct RefineArgs {
   int32_t* fb_rows; int32_t* fb_count;   // uncertified rows (exact only)
   const float* thr0;                     // nullable: pre-pass bound; keys never listed score <= thr0[row] (16-bit score)
   const float* part_thr;                 // nullable: [n_splits][Q] threshold each split ended with (cross-split sharing)
+  // Exclusion lists (nullable): query row r never returns the GLOBAL key indices mask_col[mask_rowptr[r] .. mask_rowptr[r+1])
+  // (the evaluation ranking's history mask, RAGraph_edge/utils/metrics.py:48-53,110-117).  The filter knows nothing about
+  // them: excluded candidates are dropped here, the certificate still bounds every key outside the lists, and a row whose
+  // lists hold fewer than k admissible candidates simply fails it and takes the second pass.
+  const int64_t* mask_rowptr; const int64_t* mask_col;
+  // Dot-product ranking (RAG_SIM_DOT): the caller's shadow holds keys * key_scale (row norms <= 1), the queries are
+  // normalised like in the cosine modes, so filter and certificate work in units of q_hat . (key_scale * k); key_scale > 0
+  // replaces the per-key inverse norms in the exact re-score and the returned scores are scaled back to q . k.
+  float key_scale;
   // error bound of the 16-bit scores, per row: qerr[row] (nullable) + *kerr_max (nullable) + eps_fixed
   const float* qerr; const float* kerr_max; float eps_fixed;
   float* thr2;                           // per uncertified row (same slot as fb_rows): threshold of the second pass
@@ -1313,7 +1323,19 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
       const int32_t j = in ? __ldg(a.part_i + o) : -1;
       const float s = in ? __ldg(a.part_s + o) : 0.f;
       const bool valid = j >= 0;
-      if (in) ap[c] = valid ? s : -INFINITY;
+      // history mask: an excluded candidate keeps its place in the list statistics below (it bounds what the split did
+      // not list) but never becomes a result.  All 32 lanes scan the row's exclusion list together.
+      bool excluded = false;
+      if (a.mask_rowptr) {
+        const int64_t mlo = __ldg(a.mask_rowptr + row), mhi = __ldg(a.mask_rowptr + row + 1);
+        const int64_t gj = (int64_t)j + a.idx_offset;
+        for (int64_t m0 = mlo; m0 < mhi; m0 += 32) {
+          const int64_t mv = (m0 + lane < mhi) ? __ldg(a.mask_col + m0 + lane) : (int64_t)-1;
+#pragma unroll 8
+          for (int t = 0; t < 32; ++t) excluded |= (__shfl_sync(0xffffffffu, mv, t) == gj);
+        }
+      }
+      if (in) ap[c] = (valid && !excluded) ? s : -INFINITY;
       float mn = valid ? s : INFINITY;
       int full = valid ? 1 : 0;
       for (int w = 1; w < a.kp; w <<= 1) {
@@ -1388,7 +1410,8 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
         if (a.exact) {
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (id[u] >= 0) sc[u] = warp_sum(sc[u]) * (a.key_inv_norm ? __ldg(a.key_inv_norm + id[u]) : 1.0f);
+            if (id[u] >= 0)
+              sc[u] = warp_sum(sc[u]) * (a.key_scale > 0.f ? a.key_scale : (a.key_inv_norm ? __ldg(a.key_inv_norm + id[u]) : 1.0f));
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -1397,10 +1420,12 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
       }
     }
     const float kth = lv[a.k - 1];
+    // dot-product ranking: back from q_hat . (key_scale * k) to q . k (a zero query row scores 0 everywhere)
+    const float out_scale = (a.exact && a.key_scale > 0.f) ? 1.0f / (qinv * a.key_scale) : 1.0f;
     const bool have_k = li[a.k - 1] != INT64_MAX;
     const bool certified = !a.exact || (have_k && kth > tmax + eps);
     for (int p = lane; p < a.k; p += 32) {
-      a.out_scores[row * a.k + p] = lv[p];
+      a.out_scores[row * a.k + p] = (li[p] == INT64_MAX) ? lv[p] : lv[p] * out_scale;
       a.out_idx[row * a.k + p] = (li[p] == INT64_MAX) ? (int64_t)-1 : li[p] + a.idx_offset;
     }
     if (a.exact && a.loose_count && lane == 0 && !(have_k && kth > tmax_lists + a.loose_mult * eps)) atomicAdd(a.loose_count, 1);
@@ -1426,6 +1451,7 @@ struct Refine2Args {
   const float* spill_s; const int32_t* spill_i; const int32_t* spill_cnt; int spill_cap;
   float* out_scores; int64_t* out_idx;
   int32_t* fb_rows; int32_t* fb_count;
+  const int64_t* mask_rowptr; const int64_t* mask_col; float key_scale;      // as in RefineArgs
 };
 
 __global__ void __launch_bounds__(256) refine2_kernel(const Refine2Args a) {
@@ -1457,6 +1483,13 @@ __global__ void __launch_bounds__(256) refine2_kernel(const Refine2Args a) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         id[u] = (c0 + u < cnt) ? (int64_t)ci[c0 + u] : -1;     // plain loads: written by the collect pass on this stream
+        if (a.mask_rowptr && id[u] >= 0) {                     // history mask (RefineArgs::mask_rowptr)
+          const int64_t mlo = __ldg(a.mask_rowptr + row), mhi = __ldg(a.mask_rowptr + row + 1), gj = id[u] + a.idx_offset;
+          bool ex = false;
+          for (int64_t m0 = mlo; m0 < mhi && !ex; m0 += 32)
+            ex = __any_sync(0xffffffffu, m0 + lane < mhi && __ldg(a.mask_col + m0 + lane) == gj);
+          if (ex) id[u] = -1;
+        }
         float dot = 0.f;
         if (id[u] >= 0) {
           const float* kr = a.keys + id[u] * a.d;
@@ -1470,14 +1503,16 @@ __global__ void __launch_bounds__(256) refine2_kernel(const Refine2Args a) {
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (id[u] >= 0) sc[u] = warp_sum(sc[u]) * (a.key_inv_norm ? __ldg(a.key_inv_norm + id[u]) : 1.0f);
+        if (id[u] >= 0)
+          sc[u] = warp_sum(sc[u]) * (a.key_scale > 0.f ? a.key_scale : (a.key_inv_norm ? __ldg(a.key_inv_norm + id[u]) : 1.0f));
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         if (id[u] >= 0 && ranks_before(sc[u], id[u], lv[a.k - 1], li[a.k - 1]))
           warp_sorted_insert<int64_t>(lv, li, a.k, sc[u], id[u], lane);
     }
+    const float out_scale = a.key_scale > 0.f ? 1.0f / (qinv * a.key_scale) : 1.0f;
     for (int p = lane; p < a.k; p += 32) {
-      a.out_scores[row * a.k + p] = lv[p];
+      a.out_scores[row * a.k + p] = (li[p] == INT64_MAX) ? lv[p] : lv[p] * out_scale;
       a.out_idx[row * a.k + p] = (li[p] == INT64_MAX) ? (int64_t)-1 : li[p] + a.idx_offset;
     }
     __syncwarp();
@@ -1729,13 +1764,20 @@ static int run_ts(const CUtensorMap& mk, const uint16_t* q_bf, const TcArgs& ta,
 int rows_to_16_launch(const float* x, int64_t rows, int d, int fmt, int normalize, float eps, uint16_t* out, int d_pad,
                       float* inv_out, float* err_rows, float* err_max, uint32_t* zero_words, int64_t n_zero, cudaStream_t s);
 
+// mask_rowptr / mask_col (nullable): per-row exclusion lists of GLOBAL key indices; key_scale > 0 (with RAG_SIM_DOT): dot-product
+// ranking over a shadow of keys * key_scale (RefineArgs::key_scale).  Both need an exact (refine) mode.
 int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const void* keys_shadow,
                 const float* shadow_err, int64_t N, int d, int k, int mode, uint32_t flags, int64_t idx_offset,
-                float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s) {
+                float* out_scores, int64_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t s,
+                const int64_t* mask_rowptr, const int64_t* mask_col, float key_scale) {
   const bool tf32 = (mode == RAG_SIM_TF32);
   const bool f16 = (mode == RAG_SIM_F16 || mode == RAG_SIM_F16_REFINE);
   const bool exact = (mode == RAG_SIM_BF16_REFINE || mode == RAG_SIM_F16_REFINE);
-  RAG_REQUIRE(!(flags & RAG_SIM_DOT), RAG_EUNSUPPORTED, "cosine_topk: the tensor-core modes implement cosine only");
+  const bool dot = (flags & RAG_SIM_DOT) != 0;
+  RAG_REQUIRE(!dot || (exact && key_scale > 0.f), RAG_EUNSUPPORTED,
+              "cosine_topk: RAG_SIM_DOT on the tensor cores needs an exact mode and key_scale > 0 (rag_topk_masked_tc_f32)");
+  RAG_REQUIRE(dot || key_scale == 0.f, RAG_EINVAL, "cosine_topk: key_scale without RAG_SIM_DOT");
+  RAG_REQUIRE(!mask_rowptr || (exact && mask_col), RAG_EUNSUPPORTED, "cosine_topk: exclusion lists need an exact mode");
   RAG_REQUIRE(!(flags & ~(RAG_SIM_DOT | RAG_SIM_WIDE_LISTS)), RAG_EINVAL, "cosine_topk: unknown flag bits 0x%x", flags);
   if (tf32)
     RAG_REQUIRE(tc_shape_ok_tf32(d, k), RAG_EUNSUPPORTED,
@@ -1743,7 +1785,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   else
     RAG_REQUIRE(tc_shape_ok(d, k), RAG_EUNSUPPORTED,
                 "cosine_topk: tensor-core modes cover d <= 128 with k <= 128 and d <= 256 with k <= 10 (d=%d k=%d)", d, k);
-  RAG_REQUIRE(key_inv_norm, RAG_EINVAL, "cosine_topk: the tensor-core modes need key_inv_norm (rag_row_inv_norm_f32)");
+  RAG_REQUIRE(key_inv_norm || dot, RAG_EINVAL, "cosine_topk: the tensor-core modes need key_inv_norm (rag_row_inv_norm_f32)");
   RAG_REQUIRE(aligned16(keys_shadow), RAG_EALIGN, "cosine_topk: the key shadow must be 16-byte aligned");
   const int kp_req = (flags & RAG_SIM_WIDE_LISTS) ? 32 : 0;
   const TcPlan pts = tc_plan(Q, N, d, k, true, false, kp_req);   // TS plan: workspace layout + the second pass
@@ -1821,7 +1863,8 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
     }
     unsigned grid_main = grid;
     a.hit_count = reinterpret_cast<uint32_t*>(zero + 4);
-    if (p.n_mergers > 0 && a.debug == 0) {
+    // (exclusion lists: the k-th best ADMISSIBLE key may sit far below the k-th best key the sweep would share -- no sweep)
+    if (p.n_mergers > 0 && a.debug == 0 && !mask_rowptr) {
       // cross-split threshold sharing: p.n_mergers extra CTAs sweep the published candidates (TcArgs::pool)
       a.pool = reinterpret_cast<uint32_t*>(w + L.off_pool);
       a.gthr = reinterpret_cast<uint32_t*>(w + L.off_gthr);
@@ -1856,6 +1899,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   r.fb_count = fb_count;
   r.thr0 = a.thr0;
   r.part_thr = a.part_thr;
+  r.mask_rowptr = mask_rowptr; r.mask_col = mask_col; r.key_scale = dot ? key_scale : 0.f;
   r.thr2 = reinterpret_cast<float*>(w + L.off_thr2);
   const float u = f16 ? TC_U_F16 : TC_U_BF16;
   r.qerr = tf32 ? nullptr : qerr;
@@ -1896,6 +1940,7 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
     r2.spill_s = c.spill_s; r2.spill_i = c.spill_i; r2.spill_cnt = spill_cnt; r2.spill_cap = pts.spill_cap;
     r2.out_scores = out_scores; r2.out_idx = out_idx;
     r2.fb_rows = reinterpret_cast<int32_t*>(w + L.off_fb2); r2.fb_count = fb2_count;
+    r2.mask_rowptr = mask_rowptr; r2.mask_col = mask_col; r2.key_scale = r.key_scale;
     int64_t b2 = (Q + 7) / 8;
     const int64_t cap2 = (int64_t)sm_count() * 8;
     if (b2 > cap2) b2 = cap2;
@@ -1905,8 +1950,9 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
     fp32_count = fb2_count;
   }
   // rows still open (spill overflow: more than spill_cap near-ties) are recomputed by the fp32 kernel
-  return topk_f32_run_rows(q, Q, keys, key_inv_norm, qinv, N, d, k, idx_offset, fp32_rows, fp32_count, out_scores,
-                           out_idx, w + L.off_f32, ws_bytes - L.off_f32, s);
+  // (dot-product ranking: the fp32 kernel scores q . k directly, no norms)
+  return topk_f32_run_rows(q, Q, keys, dot ? nullptr : key_inv_norm, dot ? nullptr : qinv, N, d, k, idx_offset, fp32_rows,
+                           fp32_count, out_scores, out_idx, w + L.off_f32, ws_bytes - L.off_f32, s, mask_rowptr, mask_col);
 }
 
 }  // namespace rag

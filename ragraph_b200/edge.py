@@ -177,12 +177,55 @@ def edge_rag_forward(all_emb: Tensor, edges: Tensor, edge_norm: Tensor, resource
     return out
 
 
-def rating_topk(user_emb: Tensor, item_emb: Tensor, k: int, hist_rowptr: Tensor, hist_items: Tensor) -> Tensor:
-    """Evaluation ranking of RAGraph_edge/utils/metrics.py:96-118 in one launch: top-k items by user . item, a user's
+_rating_shadow_cache: dict = {}
+
+
+def _rating_shadow(item_emb: Tensor):
+    """(fp16 shadow of item_emb * key_scale, err_max, key_scale) for the tensor-core ranking, cached per tensor object +
+    version: an evaluation ranks every user batch against the same item table (utils/metrics.py:96-118).  key_scale =
+    1 / (largest item norm) brings every row norm to <= 1, which is what the filter's error bound assumes."""
+    key = id(item_emb)
+    hit = _rating_shadow_cache.get(key)
+    if hit is not None and hit[0]() is item_emb and hit[1] == item_emb._version:
+        return hit[2]
+    norm_max = float(item_emb.detach().float().norm(dim=1).max())          # one host sync per item table
+    scale = 1.0 / norm_max if norm_max > 0.0 else 1.0
+    err = torch.zeros(1, dtype=torch.float32, device=item_emb.device)
+    shadow, _ = ops.rows_to_shadow16((item_emb.detach().float() * scale).contiguous(), L.FMT_F16, False, err_max=err)
+    out = (shadow, err, scale)
+    if len(_rating_shadow_cache) > 8:
+        _rating_shadow_cache.clear()
+    try:
+        import weakref
+        _rating_shadow_cache[key] = (weakref.ref(item_emb), item_emb._version, out)
+    except TypeError:
+        pass
+    return out
+
+
+RATING_TC_MIN_ITEMS, RATING_TC_MIN_USERS = 4096, 16
+
+
+def rating_topk(user_emb: Tensor, item_emb: Tensor, k: int, hist_rowptr: Tensor, hist_items: Tensor,
+                tensor_cores: Optional[bool] = None) -> Tensor:
+    """Evaluation ranking of RAGraph_edge/utils/metrics.py:96-118 in one op: top-k items by user . item, a user's
     history items excluded (Metric._mask_history_pos sets them to -inf, :48-53).  hist_rowptr int64[B+1] / hist_items
     int64[nnz] hold the batch users' history lists back to back.  Returns item indices int64 [B, k] like
-    ``torch.topk(batch_pred, k)[1]``; the [B, n_items] rating matrix and its .cpu() copy never exist."""
-    return ops.topk_masked(user_emb, item_emb, k, hist_rowptr, hist_items, L.SIM_DOT)[1]
+    ``torch.topk(batch_pred, k)[1]``; the [B, n_items] rating matrix and its .cpu() copy never exist.
+    Large tables (>= 4 096 items, >= 16 users, d <= 128, k <= 128) run on the tensor cores: fp16 filter over the scaled item
+    table + fp32 refine that drops the history items + certificate -- the same ranking as the fp32 kernel
+    (``tensor_cores`` = True / False forces one path)."""
+    B, d = user_emb.shape
+    n_items = item_emb.shape[0]
+    tc = tensor_cores
+    if tc is None:
+        tc = (n_items >= RATING_TC_MIN_ITEMS and B >= RATING_TC_MIN_USERS and user_emb.is_cuda
+              and bool(L.load().rag_sim_mode_supported(L.SIM_F16_REFINE, d, k)))
+    if not tc:
+        return ops.topk_masked(user_emb, item_emb, k, hist_rowptr, hist_items, L.SIM_DOT)[1]
+    shadow, err, scale = _rating_shadow(item_emb)
+    return ops.topk_masked(user_emb, item_emb, k, hist_rowptr, hist_items, L.SIM_DOT, None, 0, L.SIM_F16_REFINE, shadow, err,
+                           scale)[1]
 
 
 def history_csr(train_user_dict, num_users: int, device) -> tuple:

@@ -285,10 +285,15 @@ def retrieve_small(q: Tensor, keys: Tensor, k: int, values: Optional[Tensor], la
 
 @torch.library.custom_op("ragraph::topk_masked", mutates_args=())
 def topk_masked(q: Tensor, keys: Tensor, k: int, mask_rowptr: Tensor, mask_col: Tensor, flags: int = 0,
-                key_inv_norm: Optional[Tensor] = None, idx_offset: int = 0) -> Tuple[Tensor, Tensor]:
+                key_inv_norm: Optional[Tensor] = None, idx_offset: int = 0, mode: int = 0,
+                keys_shadow: Optional[Tensor] = None, shadow_err: Optional[Tensor] = None,
+                key_scale: float = 0.0) -> Tuple[Tensor, Tensor]:
     """Fused similarity + top-k where query row r never returns the key indices mask_col[mask_rowptr[r]:mask_rowptr[r+1]]
-    (int64 CSR of exclusions).  flags=SIM_DOT: plain dot product (edge evaluation ranking)."""
-    _need_cuda(q, keys, mask_rowptr, mask_col, key_inv_norm)
+    (int64 CSR of exclusions).  flags=SIM_DOT: plain dot product (edge evaluation ranking).
+    mode = SIM_F16_REFINE / SIM_BF16_REFINE runs it on the tensor cores (exact): ``keys_shadow`` / ``shadow_err`` from
+    rows_to_shadow16 -- of the normalised keys (cosine; ``key_inv_norm`` required) or, with SIM_DOT, of ``keys * key_scale``
+    un-normalised with ``key_scale`` = 1 / (largest key norm)."""
+    _need_cuda(q, keys, mask_rowptr, mask_col, key_inv_norm, keys_shadow, shadow_err)
     q, keys = _f32c(q, "topk_masked"), _f32c(keys, "topk_masked")
     if q.dim() != 2 or keys.dim() != 2 or q.shape[1] != keys.shape[1]:
         raise RuntimeError(f"topk_masked: shapes {tuple(q.shape)} vs {tuple(keys.shape)}")
@@ -301,15 +306,27 @@ def topk_masked(q: Tensor, keys: Tensor, k: int, mask_rowptr: Tensor, mask_col: 
     scores = torch.empty((Q, k), dtype=torch.float32, device=q.device)
     idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
     lib = L.load()
-    ws = _workspace(lib.rag_cosine_topk_workspace(Q, N, d, k, L.SIM_FP32), q.device)
+    if mode == L.SIM_FP32:
+        ws = _workspace(lib.rag_cosine_topk_workspace(Q, N, d, k, L.SIM_FP32), q.device)
+        with torch.cuda.device(q.device):
+            L.check(lib.rag_topk_masked_f32(_p(q), Q, _p(keys), _p(key_inv_norm), N, d, k, flags, _p(mask_rowptr), _p(mask_col),
+                                            idx_offset, _p(scores), _p(idx), _p(ws), ws.numel(), _stream()), "topk_masked")
+        return scores, idx
+    want = torch.float16 if mode == L.SIM_F16_REFINE else torch.bfloat16
+    if keys_shadow is None or keys_shadow.dtype != want or tuple(keys_shadow.shape) != (N, round_up(d, 64)) \
+            or not keys_shadow.is_contiguous():
+        raise RuntimeError(f"topk_masked: mode {mode} needs the contiguous [N, round_up(d,64)] {want} shadow (rows_to_shadow16)")
+    ws = _workspace(lib.rag_cosine_topk_workspace(Q, N, d, k, mode), q.device)
     with torch.cuda.device(q.device):
-        L.check(lib.rag_topk_masked_f32(_p(q), Q, _p(keys), _p(key_inv_norm), N, d, k, flags, _p(mask_rowptr), _p(mask_col),
-                                        idx_offset, _p(scores), _p(idx), _p(ws), ws.numel(), _stream()), "topk_masked")
+        L.check(lib.rag_topk_masked_tc_f32(_p(q), Q, _p(keys), _p(key_inv_norm), _p(keys_shadow), _p(shadow_err), N, d, k, mode,
+                                           flags, float(key_scale), _p(mask_rowptr), _p(mask_col), idx_offset, _p(scores),
+                                           _p(idx), _p(ws), ws.numel(), _stream()), "topk_masked_tc")
     return scores, idx
 
 
 @topk_masked.register_fake
-def _(q, keys, k, mask_rowptr, mask_col, flags=0, key_inv_norm=None, idx_offset=0):
+def _(q, keys, k, mask_rowptr, mask_col, flags=0, key_inv_norm=None, idx_offset=0, mode=0, keys_shadow=None, shadow_err=None,
+      key_scale=0.0):
     return q.new_empty((q.shape[0], k)), q.new_empty((q.shape[0], k), dtype=torch.int64)
 
 

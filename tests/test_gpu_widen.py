@@ -407,3 +407,52 @@ def test_fewshot_finetune_step_backpropagates_into_the_encoder(golden):
     assert float((out2 - out).abs().max()) < 1e-5
     (out2 * torch.linspace(-1, 1, out.numel(), device=DEV).reshape(out.shape)).sum().backward()
     assert float((emb2.grad - emb.grad).abs().max()) < 1e-4 * float(emb2.grad.abs().max())
+
+
+# ---- f4 on the tensor cores: masked dot-product ranking -------------------------------------------------------------------
+@pytest.mark.parametrize("B,I,d,k,heavy", [(300, 20000, 64, 20, False), (64, 9000, 64, 50, False), (200, 30000, 128, 20, True),
+                                            (1100, 150000, 64, 20, True)])
+def test_rating_topk_tensor_cores_equals_fp32_path(B, I, d, k, heavy):
+    """rating_topk on the tensor cores (fp16 filter over the scaled item table, refine drops the history items, certificate,
+    second pass / fp32 kernel for the rest) == the fp32 CUDA-core kernel == the reference's formulation (dense rating,
+    history set to -inf, torch.topk; RAGraph_edge/utils/metrics.py:48-53,96-118), ties within 1e-6 aside.  ``heavy``: some
+    users' histories ARE their best-scoring items (hundreds of them), so their candidate lists hold too few admissible items
+    and the row must go through the second pass or the fp32 kernel; one user has a single admissible item."""
+    import numpy as np
+    from ragraph_b200 import edge as E
+    g = torch.Generator().manual_seed(B + I)
+    users = torch.randn(B, d, generator=g) * 0.3
+    items = torch.randn(I, d, generator=g) * torch.rand(I, 1, generator=g) * 2.0      # un-normalised, norms vary 0..~2 sqrt(d)
+    users[5] = 0.0                                                                     # a zero user: every score ties at 0
+    rating = users.double() @ items.double().T
+    hist = {}
+    for u in range(B):
+        n_h = int(torch.randint(0, 60, (1,), generator=g))
+        hist[u] = torch.randperm(I, generator=g)[:n_h].tolist()
+    if heavy:
+        for u in range(0, B, 7):                                                       # history = the user's own top items
+            hist[u] = rating[u].topk(int(torch.randint(100, 700, (1,), generator=g))).indices.tolist()
+        hist[3] = [i for i in range(I) if i != 777]                                    # ONE admissible item
+    rowptr, hitems = E.history_csr(hist, B, DEV)
+    ud, idv = users.to(DEV), items.to(DEV)
+    got_tc = E.rating_topk(ud, idv, k, rowptr, hitems, tensor_cores=True).cpu()
+    got_f32 = E.rating_topk(ud, idv, k, rowptr, hitems, tensor_cores=False).cpu()
+    masked = rating.clone()
+    for u, h in hist.items():
+        if h:
+            masked[u, torch.tensor(h)] = -float("inf")
+    for got in (got_tc, got_f32):
+        for u in range(B):
+            row = got[u]
+            valid = row[row >= 0]
+            n_adm = I - len(set(hist[u]))
+            assert valid.numel() == min(k, n_adm), (u, valid.numel(), n_adm)
+            assert not set(valid.tolist()) & set(hist[u]), u
+            assert len(set(valid.tolist())) == valid.numel(), u
+            if u == 5:
+                continue                                                               # all ties: any admissible set is right
+            ref_scores = masked[u].topk(valid.numel()).values
+            got_scores = rating[u, valid]
+            assert float((got_scores.sort(descending=True).values - ref_scores).abs().max()) < 1e-5 * max(1.0, float(ref_scores.abs().max())), u
+    same = (got_tc == got_f32).all(dim=1).float().mean()
+    assert float(same) > 0.99, float(same)
