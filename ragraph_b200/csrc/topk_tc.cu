@@ -1228,8 +1228,14 @@ cosine_topk_ts_kernel(const __grid_constant__ CUtensorMap map_k, const uint16_t*
 // ---- pre-pass threshold: thr0[row] = kp-th largest of the row's G group maxima ---------------------------
 // Each group maximum is the bf16 score of a distinct key of this shard, so at least kp keys score >= thr0: the final
 // kp-th best score of the row (over the whole shard, hence over the union of the split lists) is >= thr0.
+// margin = 1 (two-pass mode, below): the result is lowered by 2 eps_row + 1e-6, which makes it a COLLECT threshold -- at least kp
+// distinct keys score >= kth in 16 bits, so the kp-th best exact score is >= kth - eps and every key that can be among the
+// exact top kp scores > kth - 2 eps in 16 bits.
 __global__ void __launch_bounds__(256) sample_threshold_kernel(const float* __restrict__ gmax, int G, int64_t Q, int kp,
-                                                               float* __restrict__ thr0) {
+                                                               float* __restrict__ thr0, int margin = 0,
+                                                               const float* __restrict__ qerr = nullptr,
+                                                               const float* __restrict__ kerr_max = nullptr,
+                                                               float eps_fixed = 0.f) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= Q) return;
@@ -1254,6 +1260,8 @@ __global__ void __launch_bounds__(256) sample_threshold_kernel(const float* __re
       for (int t = 0; t < 8; ++t) if (t == mine) v[t] = -INFINITY;
     }
   }
+  if (margin && kth > -INFINITY)
+    kth -= 2.0f * ((qerr ? __ldg(qerr + row) : 0.f) + (kerr_max ? __ldg(kerr_max) : 0.f) + eps_fixed) + 1e-6f;
   if (lane == 0) thr0[row] = kth;
 }
 
@@ -1285,6 +1293,7 @@ struct RefineArgs {
   float loose_mult; int32_t* loose_count;
 };
 
+constexpr int REFINE_SEL_CAP = 64;        // candidates compacted per round of the re-score (uint16 slots per warp)
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -1308,6 +1317,8 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
   float* lv = reinterpret_cast<float*>(reinterpret_cast<int64_t*>(smem_raw) + (size_t)wpb * a.k) + (size_t)warp * a.k;
   float* ap = reinterpret_cast<float*>(reinterpret_cast<int64_t*>(smem_raw) + (size_t)wpb * a.k) + (size_t)wpb * a.k +
               (size_t)warp * total;
+  uint16_t* sel = reinterpret_cast<uint16_t*>(reinterpret_cast<float*>(reinterpret_cast<int64_t*>(smem_raw) + (size_t)wpb * a.k) +
+                                              (size_t)wpb * a.k + (size_t)wpb * total) + (size_t)warp * REFINE_SEL_CAP;
   const int nd = (a.d + 31) >> 5;                              // <= 8 (tensor-core shapes have d <= 256)
   const float kerr = a.kerr_max ? __ldg(a.kerr_max) : 0.f;
   for (int64_t row = (int64_t)blockIdx.x * wpb + warp; row < a.Q; row += (int64_t)gridDim.x * wpb) {
@@ -1377,19 +1388,28 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
       const int e = lane + 32 * t;
       qreg[t] = (a.exact && t < nd && e < a.d) ? __ldg(a.q + row * a.d + e) * qinv : 0.f;
     }
-    for (int c0 = 0; c0 < total; c0 += 32) {
-      const int c = c0 + lane;
-      const float mine = (c < total) ? ap[c] : -INFINITY;
-      unsigned mask = __ballot_sync(0xffffffffu, mine >= cut && mine > -INFINITY);
-      while (mask) {
+    // The selected candidates (typically 5-30 of the S * kp) are compacted into a short list first and re-scored four at a
+    // time from there: every batch is a chain of three dependent memory round trips (index -> key row -> inverse norm), and
+    // walking the candidate chunks one ballot at a time made that chain once per chunk holding a candidate (measured at the
+    // reference's Cora shape: 13 splits -> up to 7 chains, ~20 of the op's 190 us) instead of once per four candidates.
+    for (int c0 = 0; c0 < total;) {
+      int n_sel = 0;
+      for (; c0 < total && n_sel <= REFINE_SEL_CAP - 32; c0 += 32) {
+        const int c = c0 + lane;
+        const float mine = (c < total) ? ap[c] : -INFINITY;
+        const bool pick = mine >= cut && mine > -INFINITY;
+        const unsigned m = __ballot_sync(0xffffffffu, pick);
+        if (pick) sel[n_sel + __popc(m & ((1u << lane) - 1u))] = (uint16_t)c;
+        n_sel += __popc(m);
+      }
+      __syncwarp();
+      for (int b0 = 0; b0 < n_sel; b0 += 4) {
         float sc[4]; int64_t id[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           sc[u] = -FLT_MAX; id[u] = -1;
-          if (mask) {
-            const int b = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const int cc = c0 + b;
+          if (b0 + u < n_sel) {
+            const int cc = sel[b0 + u];
             const int sp = cc / a.kp, p = cc - sp * a.kp;
             const int32_t j = __ldg(a.part_i + ((size_t)sp * a.Q + row) * a.kp + p);
             id[u] = j;
@@ -1403,7 +1423,7 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
               }
               sc[u] = dot;
             } else {
-              sc[u] = __shfl_sync(0xffffffffu, mine, b);
+              sc[u] = ap[cc];
             }
           }
         }
@@ -1418,6 +1438,7 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
           if (id[u] >= 0 && ranks_before(sc[u], id[u], lv[a.k - 1], li[a.k - 1]))
             warp_sorted_insert<int64_t>(lv, li, a.k, sc[u], id[u], lane);
       }
+      __syncwarp();                                             // sel is refilled by the next round
     }
     const float kth = lv[a.k - 1];
     // dot-product ranking: back from q_hat . (key_scale * k) to q . k (a zero query row scores 0 everywhere)
@@ -1447,11 +1468,17 @@ __global__ void __launch_bounds__(256) refine_kernel(const RefineArgs a) {
 struct Refine2Args {
   const float* q; const float* keys; const float* q_inv_norm; const float* key_inv_norm;
   int d; int k; int64_t idx_offset;
-  const int32_t* rows; const int32_t* n_rows_dev;
+  const int32_t* rows; const int32_t* n_rows_dev;            // both NULL (two-pass mode): every row 0 .. n_rows - 1, slot = row
+  int n_rows;
   const float* spill_s; const int32_t* spill_i; const int32_t* spill_cnt; int spill_cap;
   float* out_scores; int64_t* out_idx;
   int32_t* fb_rows; int32_t* fb_count;
   const int64_t* mask_rowptr; const int64_t* mask_col; float key_scale;      // as in RefineArgs
+  // two-pass mode: a row whose spill area overflowed is not sent to the fp32 kernel but RETRIED -- the exact k-th score
+  // of the candidates that did fit is a lower bound of the row's true k-th best, so (row, that - eps) goes to the list
+  // the standard second pass consumes (NULL: overflow -> fb_rows as usual)
+  int32_t* retry_rows; float* retry_thr; int32_t* retry_count;
+  const float* qerr; const float* kerr_max; float eps_fixed;
 };
 
 __global__ void __launch_bounds__(256) refine2_kernel(const Refine2Args a) {
@@ -1459,15 +1486,17 @@ __global__ void __launch_bounds__(256) refine2_kernel(const Refine2Args a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   int64_t* li = reinterpret_cast<int64_t*>(smem_raw) + (size_t)warp * a.k;
   float* lv = reinterpret_cast<float*>(reinterpret_cast<int64_t*>(smem_raw) + (size_t)wpb * a.k) + (size_t)warp * a.k;
-  const int n = *a.n_rows_dev;
+  const int n = a.n_rows_dev ? *a.n_rows_dev : a.n_rows;
   const int nd = (a.d + 31) >> 5;
   for (int slot = blockIdx.x * wpb + warp; slot < n; slot += gridDim.x * wpb) {
-    const int64_t row = a.rows[slot];
-    const int cnt = a.spill_cnt[slot];
-    if (cnt > a.spill_cap) {
+    const int64_t row = a.rows ? (int64_t)a.rows[slot] : (int64_t)slot;
+    const int cnt_all = a.spill_cnt[slot];
+    const bool over = cnt_all > a.spill_cap;
+    if (over && !a.retry_rows) {
       if (lane == 0) a.fb_rows[atomicAdd(a.fb_count, 1)] = (int32_t)row;
       continue;
     }
+    const int cnt = over ? a.spill_cap : cnt_all;
     for (int p = lane; p < a.k; p += 32) { lv[p] = -FLT_MAX; li[p] = INT64_MAX; }
     __syncwarp();
     float qreg[8];
@@ -1509,6 +1538,16 @@ __global__ void __launch_bounds__(256) refine2_kernel(const Refine2Args a) {
       for (int u = 0; u < 4; ++u)
         if (id[u] >= 0 && ranks_before(sc[u], id[u], lv[a.k - 1], li[a.k - 1]))
           warp_sorted_insert<int64_t>(lv, li, a.k, sc[u], id[u], lane);
+    }
+    if (over) {                                              // (retry_rows != NULL: see Refine2Args)
+      if (lane == 0) {
+        const int s2 = atomicAdd(a.retry_count, 1);
+        const float eps = (a.qerr ? __ldg(a.qerr + row) : 0.f) + (a.kerr_max ? __ldg(a.kerr_max) : 0.f) + a.eps_fixed;
+        a.retry_rows[s2] = (int32_t)row;
+        a.retry_thr[s2] = (li[a.k - 1] != INT64_MAX) ? lv[a.k - 1] - eps - 1e-6f : -INFINITY;
+      }
+      __syncwarp();
+      continue;
     }
     const float out_scale = a.key_scale > 0.f ? 1.0f / (qinv * a.key_scale) : 1.0f;
     for (int p = lane; p < a.k; p += 32) {
@@ -1563,6 +1602,10 @@ struct TcPlan {
   int n_mergers; size_t off_gthr, off_pool, off_pthr;
 };
 constexpr int TC_ZERO_HDR = 64;       // words in front of the per-row spill counters
+constexpr int TWOPASS_RESERVE_TILES = 1024;
+// measured crossover against the one-pass SS kernel (profiles/r2_twopass_ab.jsonl): d <= 128 still 1.2x at 868 tiles per CTA
+// (4 096 x 1 M keys), d = 256 (twice the MMA time per tile, so the second pass costs more) even at ~220
+constexpr int TWOPASS_TILES_D128 = 1024, TWOPASS_TILES_D256 = 192;   // largest "twopass_max_tiles" the workspace is laid out for
 
 // Process-wide tuning / test hooks (rag_tc_set_option); the environment is read ONCE, when the first call needs them.
 struct TcOptions {
@@ -1575,6 +1618,8 @@ struct TcOptions {
   int gshare = 1;                     // cross-split threshold sharing on the idle SMs (TcArgs::pool); 0 = off
   int gshare_ctas = 4;                // at most this many sweeping CTAs
   int gshare_dbg = 0;                 // experiments (TcArgs::g_dbg)
+  int twopass = 1;                    // short streams: maxima pass + collect pass instead of list warm-up (topk_tc_run)
+  int twopass_max_tiles = 0;          // ... up to this many key tiles per CTA (0 = by d: TWOPASS_TILES_D128 / _D256)
 };
 static TcOptions tc_env_defaults() {
   TcOptions o;
@@ -1585,6 +1630,7 @@ static TcOptions tc_env_defaults() {
   if (const char* e = getenv("RAG_TC_KP")) { if (atoi(e) == 16 || atoi(e) == 32) o.kp = atoi(e); }
   if (const char* e = getenv("RAG_TC_PASS2")) o.pass2 = (e[0] == '0') ? 0 : 1;
   if (const char* e = getenv("RAG_TC_GSHARE")) o.gshare = (e[0] == '0') ? 0 : 1;
+  if (const char* e = getenv("RAG_TC_TWOPASS")) o.twopass = (e[0] == '0') ? 0 : 1;
   return o;
 }
 static TcOptions& tc_opts() {
@@ -1614,12 +1660,14 @@ bool tc_shape_ok(int d, int k) { return d >= 1 && d <= 256 && k >= 1 && (k <= 10
 // (k <= 26) and d <= 128 the bf16 d = 256 budget (128 KB of resident queries, 16-entry lists, k <= 10)
 bool tc_shape_ok_tf32(int d, int k) { return d >= 1 && k >= 1 && ((d <= 64 && k <= 26) || (d <= 128 && k <= 10)); }
 
-// Which filter kernel runs.  Measured on B200 (profiles/r1_midsize_ab.jsonl, r1_variant_ab_v4.jsonl): the query-stationary
-// TS kernel wins once a CTA streams many key tiles (12.5 M keys x 4096 queries: parity; 100 M: +6 %), because its hit
-// handling is built for the sparse steady state behind the pre-pass bound; short streams are one long warm-up phase, where
-// the SS kernel's lane-parallel list updates are 2-3x faster.  Default: TS from 8192 tiles per CTA, and for the shapes SS
-// does not instantiate.  rag_tc_set_option("variant", 1|2) forces one (A/B measurements, tests).
-constexpr int TS_MIN_TILES_PER_SPLIT = 8192;
+// Which filter kernel runs.  Round 1 measured the query-stationary TS kernel ahead only from ~8 192 key tiles per CTA (its
+// selection is built for the sparse steady state; short streams are one long warm-up, where the SS kernel's lane-parallel
+// list updates are 2-3x faster).  With the threshold pre-pass and the cross-split sharing of round 2 the TS kernel wins from
+// the first shape that has a pre-pass (profiles/r2_variant_ab_mid_streams.jsonl, Q = 4 096: 1.5 M x 128 keys 1.87 vs 2.30 ms,
+// 2 M x 64 1.73 vs 2.71, 2 M x 256 3.12 vs 3.12, 4 M x 256 6.32 vs 6.43, 8 M x 128 6.21 vs 6.59), and below that the two-pass
+// mode (topk_tc_run) replaces list warm-up altogether.  Default: TS from 1 024 tiles per CTA and for the shapes SS does not
+// instantiate; SS in between (d > 128: 192-1 024 tiles).  rag_tc_set_option("variant", 1|2) forces one (A/B, tests).
+constexpr int TS_MIN_TILES_PER_SPLIT = 1024;
 static bool tc_use_ts(int d, int k, int tiles_per_split) {
   const bool ss_ok = tc_shape_ok_ss(d, k);
   const int v = tc_opts().variant;
@@ -1697,7 +1745,11 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = f
     if (g < 1) g = 1;
     if ((int64_t)g * p.n_splits <= 256 && g <= p.tiles_per_split / o.prepass_div) { p.pre_tiles = p.tiles_per_split / o.prepass_div; p.pre_groups = g; }
   }
-  p.off_gmax = off; off += align_up((size_t)((2 * kp_layout + p.n_splits - 1) / p.n_splits) * p.n_splits * Q * 4, 256);
+  // (two-pass mode groups the WHOLE stream into up to 256 groups per row; only short streams qualify: TWOPASS_RESERVE_TILES)
+  size_t gmax_groups = (size_t)((2 * kp_layout + p.n_splits - 1) / p.n_splits) * p.n_splits;
+  if (ts && !tf32 && p.tiles_per_split <= TWOPASS_RESERVE_TILES)
+    gmax_groups = std::max(gmax_groups, (size_t)std::min(p.tiles_per_split, 256 / std::max(p.n_splits, 1)) * p.n_splits);
+  p.off_gmax = off; off += align_up(gmax_groups * Q * 4, 256);
   p.off_thr0 = off; off += align_up((size_t)Q * 4, 256);
   // hit-queue overflow area: one slice per CTA of the largest TS launch (the second pass runs max(#SMs, query tiles) CTAs)
   const int64_t ts_ctas = std::max<int64_t>((int64_t)p.n_qtiles * p.n_splits, std::max<int64_t>(sm_count(), p.n_qtiles));
@@ -1789,7 +1841,15 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   RAG_REQUIRE(aligned16(keys_shadow), RAG_EALIGN, "cosine_topk: the key shadow must be 16-byte aligned");
   const int kp_req = (flags & RAG_SIM_WIDE_LISTS) ? 32 : 0;
   const TcPlan pts = tc_plan(Q, N, d, k, true, false, kp_req);   // TS plan: workspace layout + the second pass
-  const bool ts = !tf32 && tc_use_ts(d, k, pts.tiles_per_split);
+  // two-pass mode for short streams (see below): exact modes, no exclusion lists (a group maximum may be an excluded key),
+  // k small against the <= 256 groups, automatic kernel choice (a forced variant runs that variant's own selection)
+  const TcOptions& opt = tc_opts();
+  const bool two_pass = exact && !tf32 && !mask_rowptr && !dot && k <= 16 && opt.twopass && opt.variant == 0 &&
+                        pts.tiles_per_split <= std::min(opt.twopass_max_tiles > 0 ? opt.twopass_max_tiles
+                                                                                  : (d <= 128 ? TWOPASS_TILES_D128 : TWOPASS_TILES_D256),
+                                                        TWOPASS_RESERVE_TILES) &&
+                        std::min(pts.tiles_per_split, 256 / std::max(pts.n_splits, 1)) * pts.n_splits >= 2 * k && N >= 4 * TC_BN;
+  const bool ts = !tf32 && (two_pass || tc_use_ts(d, k, pts.tiles_per_split));
   const TcPlan p = tf32 ? tc_plan(Q, N, d, k, false, true) : (ts ? pts : tc_plan(Q, N, d, k, false, false, kp_req));
   const size_t need = tf32 ? p.total : pts.total;
   RAG_REQUIRE(ws_bytes >= need, RAG_EWORKSPACE, "cosine_topk: workspace %zu < %zu bytes", ws_bytes, need);
@@ -1846,7 +1906,62 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   a.part_s = reinterpret_cast<float*>(w + L.off_ps);
   a.part_i = reinterpret_cast<int32_t*>(w + L.off_pi);
   a.overflow = reinterpret_cast<float*>(w + L.off_ovf);
-  if (ts) {
+  if (two_pass) {
+    // ---- short streams: maxima pass + collect pass ----------------------------------------------------------------------
+    // A CTA that sees a few dozen key tiles spends its time WARMING UP lists (every score is a candidate until a row's slots
+    // are full; measured at the reference's Cora shape, 2 708 x 10 832 x 256: 95 of 160 us).  Two passes over the same
+    // stream need no lists at all: (1) the pre-pass instantiation over the WHOLE stream keeps one maximum per (row, tile
+    // group) -- registers only; (2) the k-th largest of a row's G group maxima, each the 16-bit score of a distinct key,
+    // minus 2 eps is a collect threshold above which every member of the exact top k lies; (3) the collect instantiation
+    // rescans with that fixed threshold and returns the handful of keys above it; (4) refine2 re-scores exactly what came
+    // back.  Overflowing rows (> spill_cap keys above the bound: clusters) go to the fp32 kernel as always.
+    const unsigned grid = (unsigned)(pts.n_qtiles * pts.n_splits);
+    int g = std::min(pts.tiles_per_split, 256 / pts.n_splits);
+    TcArgs pre = a;
+    pre.premax = 1; pre.pre_tiles = pts.tiles_per_split; pre.pre_groups = g;
+    pre.gmax = reinterpret_cast<float*>(w + L.off_gmax);
+    pre.trace = 0;
+    st = run_ts(mk, q_bf, pre, pts, grid, s);
+    if (st) return st;
+    float* thr = reinterpret_cast<float*>(w + L.off_thr2);
+    sample_threshold_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, s>>>(pre.gmax, g * pts.n_splits, Q, k, thr, 1, qerr, shadow_err,
+                                                                   TC_SLACK + (shadow_err ? 0.f : (f16 ? TC_U_F16 : TC_U_BF16)));
+    RAG_LAUNCH_OK("sample_threshold_kernel");
+    TcArgs c = a;
+    c.thr0 = thr; c.thr_exact = 1; c.collect = 1; c.premax = 0; c.trace = 0;
+    c.spill_s = reinterpret_cast<float*>(w + L.off_spill_s);
+    c.spill_i = reinterpret_cast<int32_t*>(w + L.off_spill_i);
+    c.spill_cnt = spill_cnt; c.spill_cap = pts.spill_cap;
+    c.kp = pts.kp;
+    st = run_ts(mk, q_bf, c, pts, grid, s);
+    if (st) return st;
+    Refine2Args r2{};
+    r2.q = q; r2.keys = keys; r2.q_inv_norm = qinv; r2.key_inv_norm = key_inv_norm;
+    r2.d = d; r2.k = k; r2.idx_offset = idx_offset;
+    r2.rows = nullptr; r2.n_rows_dev = nullptr; r2.n_rows = (int)Q;
+    r2.spill_s = c.spill_s; r2.spill_i = c.spill_i; r2.spill_cnt = spill_cnt; r2.spill_cap = pts.spill_cap;
+    r2.out_scores = out_scores; r2.out_idx = out_idx;
+    // overflowing rows (clusters: more than spill_cap keys above the group-maximum bound) go to the list of the standard
+    // second pass with a threshold from their exact scores -- or, in small libraries, straight to the fp32 kernel
+    const bool retry = opt.pass2 && N >= TC_PASS2_MIN_KEYS;
+    r2.fb_rows = reinterpret_cast<int32_t*>(w + L.off_fb); r2.fb_count = fb_count;
+    if (retry) {
+      r2.retry_rows = reinterpret_cast<int32_t*>(w + L.off_fb); r2.retry_thr = thr; r2.retry_count = fb_count;
+      r2.qerr = qerr; r2.kerr_max = shadow_err; r2.eps_fixed = TC_SLACK + (shadow_err ? 0.f : (f16 ? TC_U_F16 : TC_U_BF16));
+    }
+    int64_t b2 = (Q + 7) / 8;
+    const int64_t cap2 = (int64_t)sm_count() * 8;
+    if (b2 > cap2) b2 = cap2;
+    refine2_kernel<<<(unsigned)b2, 256, (size_t)8 * k * 12, s>>>(r2);
+    RAG_LAUNCH_OK("refine2_kernel");
+    if (retry) {                                              // the second pass indexes the spill areas by list slot
+      cudaError_t e = cudaMemsetAsync(spill_cnt, 0, (size_t)Q * 4, s);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(spill_cnt)");
+    }
+  }
+  if (two_pass) {
+    // (front end done: the shared tail below picks up the retry list)
+  } else if (ts) {
     const unsigned grid = (unsigned)(p.n_qtiles * p.n_splits);
     if (p.pre_tiles > 0 && tc_opts().prepass && a.debug == 0) {
       // threshold pre-pass over the first 1/64 of every split (group maxima only), then the per-row bound
@@ -1911,8 +2026,11 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   int64_t blocks = (Q + wpb - 1) / wpb;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  refine_kernel<<<(unsigned)blocks, wpb * 32, (size_t)wpb * (k * 12 + total_c * 4), s>>>(r);
-  RAG_LAUNCH_OK("refine_kernel");
+  RAG_REQUIRE(total_c <= 65535, RAG_EUNSUPPORTED, "cosine_topk: %d candidates per row", total_c);
+  if (!two_pass) {                                              // (two-pass mode: its own refine already ran, r only carries the lists)
+    refine_kernel<<<(unsigned)blocks, wpb * 32, (size_t)wpb * (k * 12 + total_c * 4 + REFINE_SEL_CAP * 2), s>>>(r);
+    RAG_LAUNCH_OK("refine_kernel");
+  }
   if (!exact) return RAG_OK;
 
   const int32_t* fp32_rows = r.fb_rows;
@@ -1976,6 +2094,8 @@ extern "C" RAG_API int rag_tc_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "kp")) o.kp = (value == 16 || value == 32) ? value : dflt.kp;
   else if (!strcmp(name, "pass2")) o.pass2 = value < 0 ? dflt.pass2 : (value != 0);
   else if (!strcmp(name, "gshare")) o.gshare = value < 0 ? dflt.gshare : (value != 0);
+  else if (!strcmp(name, "twopass")) o.twopass = value < 0 ? dflt.twopass : (value != 0);
+  else if (!strcmp(name, "twopass_max_tiles")) o.twopass_max_tiles = value >= 1 ? value : dflt.twopass_max_tiles;
   else if (!strcmp(name, "gshare_dbg")) o.gshare_dbg = value >= 0 ? value : 0;
   else if (!strcmp(name, "gshare_ctas")) o.gshare_ctas = (value >= 1 && value <= 16) ? value : dflt.gshare_ctas;
   else return rag::fail(RAG_EINVAL, "tc_set_option: unknown option '%s'", name);

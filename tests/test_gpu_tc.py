@@ -279,3 +279,33 @@ def test_cross_split_threshold_sharing_same_results(mode):
         diff = (res[1][1][rows] != i0).any(dim=1)
         for r in torch.nonzero(diff).flatten().tolist():                           # any difference must be a tie
             assert float((res[1][0][rows][r] - s0[r]).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("mode", EXACT_MODES)
+@pytest.mark.parametrize("kind", ["gauss", "clustered", "tiny_clusters"])
+def test_two_pass_mode_same_results(mode, kind):
+    """Short key streams (automatic kernel choice): a maxima pass + a collect pass above (k-th largest group maximum - 2 eps)
+    replace the list warm-up.  Same answers as the one-pass path and as fp64; on a clustered library rows whose collect area
+    overflows are retried with a threshold from their exact scores (second pass) instead of going to the fp32 kernel."""
+    g = torch.Generator().manual_seed(31)
+    Q, N, d, k = 600, 70000, 128, 10
+    if kind == "gauss":
+        q, keys = torch.randn(Q, d, generator=g), torch.randn(N, d, generator=g)
+        keys[N // 2] = keys[1]; keys[3] = 0.0; q[Q // 2] = 0.0
+    elif kind == "clustered":
+        q, keys = _clustered(g, N, Q, d, 8, 0.1, 0.1)             # ~9 000 keys per cluster: the collect areas (1 024) overflow
+    else:
+        q, keys = _clustered(g, N, Q, d, 2000, 0.1, 0.1)          # ~35 near neighbours per query: the reference's kind of library
+    L.tc_set_option("variant", 0)
+    out = {}
+    for tp in (0, 1):
+        L.tc_set_option("twopass", tp)
+        out[tp] = _run(q, keys, k, mode, stats=True)
+    L.tc_set_option("twopass", -1)
+    _assert_exact(q, keys, k, out[1][0], out[1][1])
+    assert float((out[0][0] - out[1][0]).abs().max()) < 2e-6
+    assert float((out[0][1] == out[1][1]).all(dim=1).float().mean()) > 0.99          # near-ties may swap; both checked against fp64
+    if kind == "clustered" and mode == L.SIM_F16_REFINE:
+        assert out[1][2][0] > 0 and out[1][2][1] == 0, out[1][2]    # rows were retried by the second pass, none needed the fp32 kernel
+    if kind == "tiny_clusters":
+        assert out[1][2][:2] == [0, 0], out[1][2]

@@ -45,6 +45,15 @@ for kk in (10, 50):
     assert float((s[rows] - sr).abs().max()) < 2e-6, kk
     print(f"sweep / wide-k probe k={kk}: ok, worker CTAs seen by the sweep {int(st[3])}, hits queued {int(st[4])}", flush=True)
 L.tc_set_option("variant", -1)
+# two-pass mode (automatic kernel choice on short streams): Gaussian keys and the clustered library (overflow -> retry list)
+for nm, (qq, kk_, iv) in {"gauss": (q2[:300].contiguous(), keys2, inv2), "clustered": (q, keys, inv)}.items():
+    e3 = torch.zeros(1, device=dev)
+    s3h, _ = ops.rows_to_shadow16(kk_, L.FMT_F16, True, err_max=e3)
+    s, i, st = ops.cosine_topk_with_stats(qq, kk_, 10, iv, s3h, L.SIM_F16_REFINE, shadow_err=e3)
+    sr, ir = ops.cosine_topk(qq, kk_, 10, iv)
+    torch.cuda.synchronize()
+    assert float((s - sr).abs().max()) < 2e-6, nm
+    print(f"two-pass probe {nm}: ok, retried rows {int(st[0])}, fp32 rows {int(st[1])}", flush=True)
 vals = torch.randn(N, d, device=dev)
 out = ops.gather_rows(vals, i0)
 assert torch.equal(out, vals[i0])
