@@ -159,7 +159,8 @@ RAG_API int rag_cosine_topk_stat_offsets(int64_t Q, int64_t N, int32_t d, int32_
  * RAG_TC_PREPASS, RAG_TC_PREPASS_MIN_TILES, RAG_TC_PREPASS_DIV, RAG_TC_KP) and settable here: name without the RAG_TC_
  * prefix in lower case ("variant": 0 auto / 1 ss / 2 ts; "prepass": 0/1; "prepass_min_tiles"; "prepass_div"; "kp": 0 auto /
  * 16 / 32; "pass2": 0/1; "gshare": 0/1 = cross-split threshold sharing by sweeping CTAs on the SMs the (query tile, key
- * split) grid leaves idle, "gshare_ctas": how many at most).  value < 0 restores the default.  Returns RAG_EINVAL for an unknown name. */
+ * split) grid leaves idle, "gshare_ctas": how many at most; "twopass": 0/1 = short key streams in two passes (group maxima, then a collect pass)
+ * instead of list warm-up, "twopass_max_tiles": up to this many key tiles per CTA).  value < 0 restores the default.  Returns RAG_EINVAL for an unknown name. */
 RAG_API int rag_tc_set_option(const char* name, int32_t value);
 
 /* Small-problem retrieve in ONE launch (the reference's real call sites: RAGraph_graph/ragraph_utils/ToyGraphBase.py:56-87 --
