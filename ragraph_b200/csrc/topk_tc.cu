@@ -1602,10 +1602,12 @@ struct TcPlan {
   int n_mergers; size_t off_gthr, off_pool, off_pthr;
 };
 constexpr int TC_ZERO_HDR = 64;       // words in front of the per-row spill counters
-constexpr int TWOPASS_RESERVE_TILES = 1024;
+constexpr int TWOPASS_RESERVE_TILES = 8192;
+constexpr int64_t TWOPASS_MAX_Q = 262144;                 // (its group maxima take up to 1 KB of workspace per query row)
 // measured crossover against the one-pass SS kernel (profiles/r2_twopass_ab.jsonl): d <= 128 still 1.2x at 868 tiles per CTA
 // (4 096 x 1 M keys), d = 256 (twice the MMA time per tile, so the second pass costs more) even at ~220
-constexpr int TWOPASS_TILES_D128 = 1024, TWOPASS_TILES_D256 = 192;   // largest "twopass_max_tiles" the workspace is laid out for
+// k > 16 (32-entry lists, costlier warm-up): 1.3x at 1 202 tiles (4 096 x 2 M x 128, k = 100), 0.73x at 3 473
+constexpr int TWOPASS_TILES_D128 = 1024, TWOPASS_TILES_D256 = 192, TWOPASS_TILES_WIDEK = 1536;   // largest "twopass_max_tiles" the workspace is laid out for
 
 // Process-wide tuning / test hooks (rag_tc_set_option); the environment is read ONCE, when the first call needs them.
 struct TcOptions {
@@ -1747,7 +1749,7 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = f
   }
   // (two-pass mode groups the WHOLE stream into up to 256 groups per row; only short streams qualify: TWOPASS_RESERVE_TILES)
   size_t gmax_groups = (size_t)((2 * kp_layout + p.n_splits - 1) / p.n_splits) * p.n_splits;
-  if (ts && !tf32 && p.tiles_per_split <= TWOPASS_RESERVE_TILES)
+  if (ts && !tf32 && p.tiles_per_split <= TWOPASS_RESERVE_TILES && Q <= TWOPASS_MAX_Q)
     gmax_groups = std::max(gmax_groups, (size_t)std::min(p.tiles_per_split, 256 / std::max(p.n_splits, 1)) * p.n_splits);
   p.off_gmax = off; off += align_up(gmax_groups * Q * 4, 256);
   p.off_thr0 = off; off += align_up((size_t)Q * 4, 256);
@@ -1842,12 +1844,12 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
   const int kp_req = (flags & RAG_SIM_WIDE_LISTS) ? 32 : 0;
   const TcPlan pts = tc_plan(Q, N, d, k, true, false, kp_req);   // TS plan: workspace layout + the second pass
   // two-pass mode for short streams (see below): exact modes, no exclusion lists (a group maximum may be an excluded key),
-  // k small against the <= 256 groups, automatic kernel choice (a forced variant runs that variant's own selection)
+  // at least 2k of the <= 256 group maxima per row (k <= 128), automatic kernel choice (a forced variant runs its own selection)
   const TcOptions& opt = tc_opts();
-  const bool two_pass = exact && !tf32 && !mask_rowptr && !dot && k <= 16 && opt.twopass && opt.variant == 0 &&
+  const bool two_pass = exact && !tf32 && !mask_rowptr && !dot && k <= TC_MAX_K_WIDE && opt.twopass && opt.variant == 0 &&
                         pts.tiles_per_split <= std::min(opt.twopass_max_tiles > 0 ? opt.twopass_max_tiles
-                                                                                  : (d <= 128 ? TWOPASS_TILES_D128 : TWOPASS_TILES_D256),
-                                                        TWOPASS_RESERVE_TILES) &&
+                                                                                  : (d > 128 ? TWOPASS_TILES_D256 : (k > 16 ? TWOPASS_TILES_WIDEK : TWOPASS_TILES_D128)),
+                                                        TWOPASS_RESERVE_TILES) && Q <= TWOPASS_MAX_Q &&
                         std::min(pts.tiles_per_split, 256 / std::max(pts.n_splits, 1)) * pts.n_splits >= 2 * k && N >= 4 * TC_BN;
   const bool ts = !tf32 && (two_pass || tc_use_ts(d, k, pts.tiles_per_split));
   const TcPlan p = tf32 ? tc_plan(Q, N, d, k, false, true) : (ts ? pts : tc_plan(Q, N, d, k, false, false, kp_req));
