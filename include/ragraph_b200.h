@@ -162,6 +162,15 @@ RAG_API int rag_cosine_topk_stat_offsets(int64_t Q, int64_t N, int32_t d, int32_
  * split) grid leaves idle, "gshare_ctas": how many at most; "twopass": 0/1 = short key streams in two passes (group maxima, then a collect pass)
  * instead of list warm-up, "twopass_max_tiles": up to this many key tiles per CTA).  value < 0 restores the default.  Returns RAG_EINVAL for an unknown name. */
 RAG_API int rag_tc_set_option(const char* name, int32_t value);
+/* Introspection (pure host arithmetic; assumes 148 SMs without a device): which kernel would serve
+ * rag_cosine_topk_f32(Q, N, d, k, mode, flags) / rag_topk_masked_tc_f32 (has_mask = 1), and with what geometry.
+ * out[0] = kernel: 0 = the fp32 CUDA-core kernel (mode RAG_SIM_FP32 or a shape outside the tensor-core range), 1 = SS (query
+ * tile in shared memory), 2 = TS (query tile in tensor memory, threshold pre-pass), 3 = two-pass mode (group maxima + collect
+ * pass on the TS kernel); out[1] = query tiles, out[2] = key splits, out[3] = key tiles per CTA, out[4] = candidate-list
+ * length k', out[5] = sweeping CTAs of the cross-split threshold sharing, out[6] = pre-pass tiles per CTA, out[7] = pipeline
+ * stages.  out = int32[8]. */
+RAG_API int rag_cosine_topk_plan(int64_t Q, int64_t N, int32_t d, int32_t k, int32_t mode, uint32_t flags, int32_t has_mask,
+                         int32_t* out);
 
 /* Small-problem retrieve in ONE launch (the reference's real call sites: RAGraph_graph/ragraph_utils/ToyGraphBase.py:56-87 --
  * one pooled query against a few hundred library rows; the few-shot and noise branches): F.normalize + similarity + top-k +

@@ -45,6 +45,7 @@ SIGNATURES = {
     "rag_cosine_topk_f32": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _u32, _i64, _p, _p, _p, _sz, _p]),
     "rag_cosine_topk_stat_offsets": (C.c_int, [_i64, _i64, _i32, _i32, _i32, _p]),
     "rag_tc_set_option": (C.c_int, [C.c_char_p, _i32]),
+    "rag_cosine_topk_plan": (C.c_int, [_i64, _i64, _i32, _i32, _i32, _u32, _i32, _p]),
     "rag_retrieve_small_supported": (C.c_int, [_i64, _i64, _i32, _i32]),
     "rag_retrieve_small_workspace": (_sz, [_i64, _i64, _i32, _i32]),
     "rag_retrieve_small_f32": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _u32, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
@@ -104,6 +105,20 @@ def check(status: int, what: str) -> None:
     if status != RAG_OK:
         lib = load()
         raise RagError(f"{what}: {lib.rag_status_string(status).decode()}: {lib.rag_last_error().decode()}")
+
+
+PLAN_KERNELS = {0: "fp32", 1: "ss", 2: "ts", 3: "two_pass"}
+
+
+def cosine_topk_plan(Q: int, N: int, d: int, k: int, mode: int, flags: int = 0, has_mask: bool = False) -> dict:
+    """Which kernel would serve cosine_topk(Q, N, d, k, mode) and with what geometry (rag_cosine_topk_plan: host arithmetic
+    only, works without a GPU -- 148 SMs assumed)."""
+    out = (C.c_int32 * 8)()
+    check(load().rag_cosine_topk_plan(Q, N, d, k, mode, flags, int(has_mask), out), "cosine_topk_plan")
+    keys = ("kernel", "q_tiles", "key_splits", "tiles_per_cta", "list_len", "sweep_ctas", "prepass_tiles", "stages")
+    r = dict(zip(keys, list(out)))
+    r["kernel"] = PLAN_KERNELS[r["kernel"]]
+    return r
 
 
 def tc_set_option(name: str, value: int) -> None:

@@ -1818,6 +1818,32 @@ static int run_ts(const CUtensorMap& mk, const uint16_t* q_bf, const TcArgs& ta,
 int rows_to_16_launch(const float* x, int64_t rows, int d, int fmt, int normalize, float eps, uint16_t* out, int d_pad,
                       float* inv_out, float* err_rows, float* err_max, uint32_t* zero_words, int64_t n_zero, cudaStream_t s);
 
+// Which kernel serves a call -- one place, shared by topk_tc_run and rag_cosine_topk_plan (introspection, CPU tests).
+struct TcDispatch {
+  TcPlan pts, p;
+  bool two_pass, ts;
+};
+static TcDispatch tc_dispatch(int64_t Q, int64_t N, int d, int k, int mode, uint32_t flags, bool has_mask) {
+  const bool tf32 = (mode == RAG_SIM_TF32);
+  const bool exact = (mode == RAG_SIM_BF16_REFINE || mode == RAG_SIM_F16_REFINE);
+  const bool dot = (flags & RAG_SIM_DOT) != 0;
+  const int kp_req = (flags & RAG_SIM_WIDE_LISTS) ? 32 : 0;
+  TcDispatch D{};
+  D.pts = tc_plan(Q, N, d, k, true, false, kp_req);
+  const TcPlan& pts = D.pts;
+  // two-pass mode for short streams (topk_tc_run): exact modes, no exclusion lists (a group maximum may be an excluded key), at
+  // least 2k of the <= 256 group maxima per row (k <= 128), automatic kernel choice (a forced variant runs its own selection)
+  const TcOptions& opt = tc_opts();
+  const int tp_tiles = opt.twopass_max_tiles > 0 ? opt.twopass_max_tiles
+                                                 : (d > 128 ? TWOPASS_TILES_D256 : (k > 16 ? TWOPASS_TILES_WIDEK : TWOPASS_TILES_D128));
+  D.two_pass = exact && !tf32 && !has_mask && !dot && k <= TC_MAX_K_WIDE && opt.twopass && opt.variant == 0 &&
+               pts.tiles_per_split <= std::min(tp_tiles, TWOPASS_RESERVE_TILES) && Q <= TWOPASS_MAX_Q &&
+               std::min(pts.tiles_per_split, 256 / std::max(pts.n_splits, 1)) * pts.n_splits >= 2 * k && N >= 4 * TC_BN;
+  D.ts = !tf32 && (D.two_pass || tc_use_ts(d, k, pts.tiles_per_split));
+  D.p = tf32 ? tc_plan(Q, N, d, k, false, true) : (D.ts ? pts : tc_plan(Q, N, d, k, false, false, kp_req));
+  return D;
+}
+
 // mask_rowptr / mask_col (nullable): per-row exclusion lists of GLOBAL key indices; key_scale > 0 (with RAG_SIM_DOT): dot-product
 // ranking over a shadow of keys * key_scale (RefineArgs::key_scale).  Both need an exact (refine) mode.
 int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_inv_norm, const void* keys_shadow,
@@ -1841,18 +1867,11 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
                 "cosine_topk: tensor-core modes cover d <= 128 with k <= 128 and d <= 256 with k <= 10 (d=%d k=%d)", d, k);
   RAG_REQUIRE(key_inv_norm || dot, RAG_EINVAL, "cosine_topk: the tensor-core modes need key_inv_norm (rag_row_inv_norm_f32)");
   RAG_REQUIRE(aligned16(keys_shadow), RAG_EALIGN, "cosine_topk: the key shadow must be 16-byte aligned");
-  const int kp_req = (flags & RAG_SIM_WIDE_LISTS) ? 32 : 0;
-  const TcPlan pts = tc_plan(Q, N, d, k, true, false, kp_req);   // TS plan: workspace layout + the second pass
-  // two-pass mode for short streams (see below): exact modes, no exclusion lists (a group maximum may be an excluded key),
-  // at least 2k of the <= 256 group maxima per row (k <= 128), automatic kernel choice (a forced variant runs its own selection)
+  const TcDispatch D = tc_dispatch(Q, N, d, k, mode, flags, mask_rowptr != nullptr);
+  const TcPlan& pts = D.pts;                                    // TS plan: workspace layout + the second pass
+  const TcPlan& p = D.p;                                        // plan of the kernel that runs
   const TcOptions& opt = tc_opts();
-  const bool two_pass = exact && !tf32 && !mask_rowptr && !dot && k <= TC_MAX_K_WIDE && opt.twopass && opt.variant == 0 &&
-                        pts.tiles_per_split <= std::min(opt.twopass_max_tiles > 0 ? opt.twopass_max_tiles
-                                                                                  : (d > 128 ? TWOPASS_TILES_D256 : (k > 16 ? TWOPASS_TILES_WIDEK : TWOPASS_TILES_D128)),
-                                                        TWOPASS_RESERVE_TILES) && Q <= TWOPASS_MAX_Q &&
-                        std::min(pts.tiles_per_split, 256 / std::max(pts.n_splits, 1)) * pts.n_splits >= 2 * k && N >= 4 * TC_BN;
-  const bool ts = !tf32 && (two_pass || tc_use_ts(d, k, pts.tiles_per_split));
-  const TcPlan p = tf32 ? tc_plan(Q, N, d, k, false, true) : (ts ? pts : tc_plan(Q, N, d, k, false, false, kp_req));
+  const bool two_pass = D.two_pass, ts = D.ts;
   const size_t need = tf32 ? p.total : pts.total;
   RAG_REQUIRE(ws_bytes >= need, RAG_EWORKSPACE, "cosine_topk: workspace %zu < %zu bytes", ws_bytes, need);
   RAG_REQUIRE(ws && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, RAG_EALIGN, "cosine_topk: workspace must be 256-byte aligned");
@@ -2076,6 +2095,29 @@ int topk_tc_run(const float* q, int64_t Q, const float* keys, const float* key_i
 }
 
 }  // namespace rag
+
+// Introspection: which kernel would serve a call, and with what geometry.  Pure host arithmetic (148 SMs are assumed without
+// a device), so the dispatch rules are testable on a CPU-only box.  out[0] = kernel (0 = not a tensor-core shape: the fp32
+// kernel; 1 = SS, query tile in shared memory; 2 = TS, query tile in tensor memory; 3 = two-pass mode on the TS kernel),
+// out[1] = query tiles, out[2] = key splits, out[3] = key tiles per CTA, out[4] = list length k', out[5] = sweeping CTAs of the
+// cross-split threshold sharing, out[6] = tiles of the threshold pre-pass per CTA, out[7] = pipeline stages.
+extern "C" RAG_API int rag_cosine_topk_plan(int64_t Q, int64_t N, int32_t d, int32_t k, int32_t mode, uint32_t flags,
+                                            int32_t has_mask, int32_t* out) {
+  using namespace rag;
+  RAG_REQUIRE(out, RAG_EINVAL, "cosine_topk_plan: null pointer");
+  for (int i = 0; i < 8; ++i) out[i] = 0;
+  if (Q <= 0 || N <= 0 || mode == RAG_SIM_FP32) return RAG_OK;
+  const bool tf32 = (mode == RAG_SIM_TF32);
+  if (tf32 ? !tc_shape_ok_tf32(d, k) : !tc_shape_ok(d, k)) return RAG_OK;
+  const TcDispatch D = tc_dispatch(Q, N, d, k, mode, flags, has_mask != 0);
+  const bool sweep = D.ts && !D.two_pass && !has_mask && D.p.n_mergers > 0;
+  out[0] = D.two_pass ? 3 : (D.ts ? 2 : 1);
+  out[1] = D.p.n_qtiles; out[2] = D.p.n_splits; out[3] = D.p.tiles_per_split; out[4] = D.p.kp;
+  out[5] = sweep ? D.p.n_mergers : 0;
+  out[6] = (D.ts && !D.two_pass && tc_opts().prepass) ? D.p.pre_tiles : 0;
+  out[7] = D.p.nstage;
+  return RAG_OK;
+}
 
 // diagnostics: copy the pipeline trace (4 x 512 clock64 stamps + 2 x 512 uint32 + 16 x 256 uint32) to the host (36 KB)
 extern "C" RAG_API int rag_tc_trace_read(unsigned long long* host_out) {

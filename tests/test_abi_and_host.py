@@ -167,3 +167,51 @@ def test_bench_stdout_guard_keeps_one_line():
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout == '{"ok": 1}\n'
     assert "NCCL version x" in r.stderr and "python noise" in r.stderr
+
+
+def test_retrieval_dispatch_rules():
+    """rag_cosine_topk_plan (host arithmetic, 148 SMs assumed without a device): which kernel serves which shape.  Pins the
+    measured dispatch rules of DESIGN 3.1-3.2b: two-pass mode on short key streams, the TS kernel (pre-pass + cross-split sweep on
+    the SMs the grid leaves idle) from 1 024 key tiles per CTA, SS in between for d > 128, more key splits for k > 26."""
+    L = _lib
+    F16R, BF16R, BF16, FP32 = L.SIM_F16_REFINE, L.SIM_BF16_REFINE, L.SIM_BF16, L.SIM_FP32
+    plan = L.cosine_topk_plan
+    # the headline shapes: query-stationary kernel, 16 query tiles x 9 key splits = 144 workers + 4 sweeping CTAs, pre-pass = 1/64
+    for N in (100_000_000, 50_000_000, 25_000_000, 12_500_000):
+        p = plan(4096, N, 128, 10, BF16R)
+        assert (p["kernel"], p["q_tiles"], p["key_splits"], p["sweep_ctas"], p["list_len"]) == ("ts", 16, 9, 4, 16), p
+        assert p["prepass_tiles"] == p["tiles_per_cta"] // 64
+    assert plan(4096, 10_000_000, 256, 10, F16R)["kernel"] == "ts"
+    assert plan(4096, 100_000_000, 128, 10, BF16R, L.SIM_WIDE_LISTS)["list_len"] == 32
+    # the reference's own library sizes: two passes (group maxima + collect) instead of list warm-up -- exact modes only
+    for shape in ((2708, 10832, 256, 4), (4096, 240_000, 64, 10), (300, 20_000, 128, 10), (4096, 1_000_000, 128, 10),
+                  (32768, 240_000, 64, 50), (4096, 240_000, 64, 21)):
+        assert plan(*shape, F16R)["kernel"] == "two_pass", shape
+        assert plan(*shape, BF16)["kernel"] in ("ss", "ts"), shape                    # raw modes keep their lists
+    assert plan(4096, 240_000, 64, 10, F16R, 0, True)["kernel"] == "ss"               # exclusion lists: no two-pass, no sweep
+    assert plan(4096, 100_000_000, 128, 10, F16R, 0, True)["sweep_ctas"] == 0
+    # d > 128: the second pass costs twice the MMA time -> two-pass only up to 192 tiles per CTA, SS up to 1 024, then TS
+    assert plan(4096, 200_000, 256, 10, F16R)["kernel"] == "two_pass"
+    assert plan(4096, 500_000, 256, 10, F16R)["kernel"] == "ss"
+    assert plan(4096, 2_000_000, 256, 10, F16R)["kernel"] == "ts"
+    assert plan(4096, 2_000_000, 128, 10, F16R)["kernel"] == "ts"
+    # k in (26, 128]: the lists of a row hold >= 4k entries together (more key splits, CTAs in waves)
+    p = plan(32768, 240_000, 64, 50, BF16)
+    assert p["list_len"] == 32 and p["key_splits"] * 32 >= 4 * 50 and p["q_tiles"] * p["key_splits"] > 148, p
+    assert plan(4096, 2_000_000, 128, 100, BF16)["key_splits"] >= 13
+    # outside the tensor-core range: the fp32 kernel
+    assert plan(300, 70_000, 266, 5, F16R)["kernel"] == "fp32"
+    assert plan(300, 70_000, 256, 20, F16R)["kernel"] == "fp32"
+    assert plan(300, 70_000, 128, 10, FP32)["kernel"] == "fp32"
+    # options are honoured and restorable
+    try:
+        L.tc_set_option("twopass", 0)
+        assert plan(2708, 10832, 256, 4, F16R)["kernel"] == "ss"
+        L.tc_set_option("gshare", 0)
+        assert plan(4096, 12_500_000, 128, 10, BF16R)["sweep_ctas"] == 0
+        L.tc_set_option("variant", 1)
+        assert plan(4096, 12_500_000, 128, 10, BF16R)["kernel"] == "ss"
+    finally:
+        for name in ("twopass", "gshare", "variant"):
+            L.tc_set_option(name, -1)
+    assert plan(2708, 10832, 256, 4, F16R)["kernel"] == "two_pass"
