@@ -356,6 +356,7 @@ class ToyGraphBase:
     # a row whose certificates would also hold under a bf16-sized error bound -> bf16; a bf16 call with second-pass rows ->
     # back to fp16 for good.  Only large scans adapt (the format is noise below ~4 G scores per call).
     ADAPT_MIN_SCORES = 1 << 32
+    WIDE_LISTS_MIN_TILE_FRACTION = 0.3        # switch to 32-entry lists when the second pass touches more query tiles than this
 
     def _policy_reset(self) -> None:
         self._pol = {"fmt": L.FMT_F16, "wide": False, "locked": False, "calm": 0, "gen": 0}
@@ -372,7 +373,11 @@ class ToyGraphBase:
             if p["fmt"] == L.FMT_BF16:
                 if n2 > 0.02 * Q:
                     p.update(fmt=L.FMT_F16, locked=True, calm=0, gen=p["gen"] + 1)
-            elif n2 > 0.02 * Q and not p["wide"] and wide_ok:
+            elif not p["wide"] and wide_ok and -(-n2 // 256) > self.WIDE_LISTS_MIN_TILE_FRACTION * -(-Q // 256):
+                # The second pass rescans the shard for the uncertified rows, packed into 256-row query tiles: its cost is the
+                # FRACTION OF QUERY TILES it touches, against ~20-28 % for 32-entry lists on every tile.  Measured
+                # (profiles/r2_ab_fmt_kp_*.jsonl): 100 M keys, 2 400 of 4 096 rows uncertified (10 of 16 tiles) -> wide lists
+                # win 93.9 vs 125.6 ms; 12.5 M-key shards, 697 rows (3 of 16 tiles) -> 16-entry lists win 12.8 vs 14.5 ms.
                 p.update(wide=True, calm=0, gen=p["gen"] + 1)
             elif n2 == 0 and loose == 0 and not p["locked"] and not p["wide"]:
                 p["calm"] += 1
