@@ -57,7 +57,8 @@ def _peaks():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons during the timed region (pynvml; one sample per 100 ms)."""
+    """SM clock + throttle reasons during the timed region (pynvml; one sample per 10 ms -- the timed region of an 8-GPU run is
+    ~90 ms; the sample taken as the region opens is dropped when later ones exist: it still sees the idle clock)."""
 
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
@@ -83,7 +84,7 @@ class ClockSampler:
                 self.reasons |= {k for k, b in names.items() if mask & b}
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.01)
 
     def __enter__(self):
         if self.nv is not None:
@@ -97,7 +98,7 @@ class ClockSampler:
             self._t.join(timeout=2)
 
     def summary(self):
-        s = sorted(self.samples)
+        s = sorted(self.samples[1:] if len(self.samples) > 3 else self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(s)}
 
