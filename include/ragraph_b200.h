@@ -157,7 +157,7 @@ RAG_API int rag_cosine_topk_f32(const float* q, int64_t Q, const float* keys, co
 RAG_API int rag_cosine_topk_stat_offsets(int64_t Q, int64_t N, int32_t d, int32_t k, int32_t mode, size_t* offsets_out);
 /* Process-wide tuning / test hooks of the tensor-core path, read from the environment ONCE at load (RAG_TC_VARIANT,
  * RAG_TC_PREPASS, RAG_TC_PREPASS_MIN_TILES, RAG_TC_PREPASS_DIV, RAG_TC_KP) and settable here: name without the RAG_TC_
- * prefix in lower case ("variant": 0 auto / 1 ss / 2 ts; "prepass": 0/1; "prepass_min_tiles"; "prepass_div"; "kp": 0 auto /
+ * prefix in lower case ("variant": 0 auto / 1 ss / 2 ts; "prepass": 0/1; "prepass_min_tiles"; "prepass_div"; "prepass_max_tiles"; "kp": 0 auto /
  * 16 / 32; "pass2": 0/1; "gshare": 0/1 = cross-split threshold sharing by sweeping CTAs on the SMs the (query tile, key
  * split) grid leaves idle, "gshare_ctas": how many at most; "twopass": 0/1 = short key streams in two passes (group maxima, then a collect pass)
  * instead of list warm-up, "twopass_max_tiles": up to this many key tiles per CTA).  value < 0 restores the default.  Returns RAG_EINVAL for an unknown name. */

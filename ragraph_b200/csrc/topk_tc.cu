@@ -1615,6 +1615,7 @@ struct TcOptions {
   int prepass = 1;
   int prepass_min_tiles = 1024;
   int prepass_div = 64;
+  int prepass_max_tiles = 192;        // pre-pass length cap per CTA (key tiles)
   int kp = 0;                         // 0 auto, 16 / 32 = candidate-list length per (row, split) where the shape allows
   int pass2 = 1;                      // 0: uncertified rows go straight to the fp32 kernel (the round-1 behaviour)
   int gshare = 1;                     // cross-split threshold sharing on the idle SMs (TcArgs::pool); 0 = off
@@ -1745,7 +1746,11 @@ static TcPlan tc_plan(int64_t Q, int64_t N, int d, int k, bool ts, bool tf32 = f
   if (ts && p.tiles_per_split >= o.prepass_min_tiles) {
     int g = (2 * p.kp + p.n_splits - 1) / p.n_splits;
     if (g < 1) g = 1;
-    if ((int64_t)g * p.n_splits <= 256 && g <= p.tiles_per_split / o.prepass_div) { p.pre_tiles = p.tiles_per_split / o.prepass_div; p.pre_groups = g; }
+    // 1/64 of the stream, but no more than prepass_max_tiles: with the cross-split sharing tightening the bound within the
+    // first few hundred microseconds, what a longer sample buys no longer pays for its tiles (measured, 100 M x 128 keys:
+    // 1 356 / 339 / 169 pre-pass tiles per CTA -> 72.99 / 72.56 / 72.33 ms; 12.5 M: 169 tiles beat 85 and 42)
+    const int pre = std::min(p.tiles_per_split / o.prepass_div, o.prepass_max_tiles);
+    if ((int64_t)g * p.n_splits <= 256 && g <= pre) { p.pre_tiles = pre; p.pre_groups = g; }
   }
   // (two-pass mode groups the WHOLE stream into up to 256 groups per row; only short streams qualify: TWOPASS_RESERVE_TILES)
   size_t gmax_groups = (size_t)((2 * kp_layout + p.n_splits - 1) / p.n_splits) * p.n_splits;
@@ -2135,6 +2140,7 @@ extern "C" RAG_API int rag_tc_set_option(const char* name, int32_t value) {
   else if (!strcmp(name, "prepass")) o.prepass = value < 0 ? dflt.prepass : (value != 0);
   else if (!strcmp(name, "prepass_min_tiles")) o.prepass_min_tiles = value >= 64 ? value : dflt.prepass_min_tiles;
   else if (!strcmp(name, "prepass_div")) o.prepass_div = value >= 4 ? value : dflt.prepass_div;
+  else if (!strcmp(name, "prepass_max_tiles")) o.prepass_max_tiles = value >= 16 ? value : dflt.prepass_max_tiles;
   else if (!strcmp(name, "kp")) o.kp = (value == 16 || value == 32) ? value : dflt.kp;
   else if (!strcmp(name, "pass2")) o.pass2 = value < 0 ? dflt.pass2 : (value != 0);
   else if (!strcmp(name, "gshare")) o.gshare = value < 0 ? dflt.gshare : (value != 0);
