@@ -839,7 +839,9 @@ __device__ void ts_merger_loop(const TcArgs& a, int n_workers, uint32_t* sums, i
       }
     }
     if (first >= a.Q && (int)ld_relaxed_u32(reinterpret_cast<const uint32_t*>(a.done)) >= n_workers) finished = true;   // (a warp without rows)
-    if (clock64() - t_begin > TC_TIMEOUT_CYCLES) __trap();
+    // (a sweep that has run for ~10 s -- a debugger or sanitizer slowing the launch down 100x -- simply leaves: the workers
+    //  never depend on it, so giving up costs hits, not correctness; a trap here would kill a healthy launch)
+    if (clock64() - t_begin > TC_TIMEOUT_CYCLES) break;
   }
 }
 
