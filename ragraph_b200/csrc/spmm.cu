@@ -169,8 +169,10 @@ __device__ __forceinline__ void store_row(const SpmmArgs& a, int64_t row, int la
   }
 }
 
-template <int LANES, int VPL>
-__global__ void __launch_bounds__(SPMM_THREADS, (VPL <= 2 ? 4 : 2))
+// MINB (resident CTAs per SM the register budget is cut for): F = 256 (VPL = 2) needs 79 registers; squeezed into the 64 of
+// four CTAs per SM it spilled 24-32 bytes and ran 6 % slower than three spill-free ones (measured at cfg5: 10.58 vs 9.94 ms).
+template <int LANES, int VPL, int MINB = (VPL < 2 ? 4 : (VPL == 2 ? 3 : 2))>
+__global__ void __launch_bounds__(SPMM_THREADS, MINB)
 csr_spmm_kernel(const SpmmArgs a) {
   constexpr int F4 = LANES * VPL;
   __shared__ int32_t s_col[SPMM_WARPS][2 * STAGE];
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(256) csr_spmm_generic_kernel(const SpmmArgs a)
 __device__ unsigned long long g_spmm_counters[64];
 static unsigned g_spmm_next = 0;
 
-template <int LANES, int VPL>
+template <int LANES, int VPL, int MINB = (VPL < 2 ? 4 : (VPL == 2 ? 3 : 2))>
 static int launch_spmm(SpmmArgs a, cudaStream_t s) {
   unsigned long long* base = nullptr;
   cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_spmm_counters);
@@ -286,13 +288,13 @@ static int launch_spmm(SpmmArgs a, cudaStream_t s) {
   a.work_counter = base + (g_spmm_next++ & 63u);
   e = cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(work_counter)");
-  const int resident = (VPL <= 2 ? 4 : 2);
+  const int resident = MINB;
   int64_t grid = (int64_t)sm_count() * resident;
   a.rows_per_grab = ROWS_PER_GRAB;
   while (a.rows_per_grab > SPMM_WARPS && (a.n_rows + a.rows_per_grab - 1) / a.rows_per_grab < 2 * grid) a.rows_per_grab /= 2;
   int64_t n_blocks = (a.n_rows + a.rows_per_grab - 1) / a.rows_per_grab;
   if (grid > n_blocks) grid = n_blocks;
-  csr_spmm_kernel<LANES, VPL><<<(unsigned)grid, SPMM_THREADS, 0, s>>>(a);
+  csr_spmm_kernel<LANES, VPL, MINB><<<(unsigned)grid, SPMM_THREADS, 0, s>>>(a);
   RAG_LAUNCH_OK("csr_spmm_kernel");
   return RAG_OK;
 }
