@@ -302,3 +302,47 @@ def test_cross_split_shared_threshold_model(seed, k, clustered):
             assert ok, bad
     if not clustered:
         assert n_cert > 0                                   # spread-out keys: the certificate does hold with a shared bound
+
+
+@FAST
+@given(seed=st.integers(0, 2 ** 31 - 1), k=st.integers(1, 24), n_groups=st.integers(1, 64), clustered=st.booleans())
+def test_two_pass_collect_threshold_model(seed, k, n_groups, clustered):
+    """Two-pass mode, independent of the CUDA code: the k-th largest of a row's group maxima (16-bit scores
+    of distinct keys) minus 2 eps is a COLLECT threshold -- every member of the exact top k scores above it in 16 bits, so
+    re-scoring what the collect pass returns gives the exact top k.  With fewer than k groups the bound is -inf (everything
+    is collected).  Also pins the retry bound for rows whose collect area overflowed: the exact k-th score of ANY subset of
+    at least k keys, minus one eps, still collects the whole exact top k."""
+    g = torch.Generator().manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    Q, N, d = 4, 500, 32
+    keys = torch.randn(N, d, generator=g)
+    if clustered:
+        cent = torch.randn(3, d, generator=g)
+        keys = cent[torch.randint(0, 3, (N,), generator=g)] + 0.02 * keys
+        keys[1] = keys[0]
+    q = torch.randn(Q, d, generator=g)
+    qn = torch.nn.functional.normalize(q, dim=-1); kn = torch.nn.functional.normalize(keys, dim=-1)
+    approx = (qn.half().double() @ kn.half().double().T).numpy()
+    exact = (qn.double() @ kn.double().T).numpy()
+    eps = 2 * 2.0 ** -11 + 2.0 ** -15                        # worst-case fp16 rounding of two unit vectors + slack
+    assert np.abs(approx - exact).max() <= eps
+    bounds = np.linspace(0, N, n_groups + 1).astype(int)
+    for r in range(Q):
+        gmax = np.array([approx[r, a:b].max() if b > a else -np.inf for a, b in zip(bounds[:-1], bounds[1:])])
+        kth = np.sort(gmax)[-k] if n_groups >= k else -np.inf
+        thr = kth - 2 * eps - 1e-6 if np.isfinite(kth) else -np.inf
+        collected = np.nonzero(approx[r] > thr)[0]
+        assert collected.size >= min(k, N)
+        e = exact[r, collected]
+        got = collected[np.lexsort((collected, -e))[:k]]
+        ok, bad = O.topk_sets_match(got[None, :], exact[r][None, :], k)
+        assert ok, bad
+        # retry bound: exact k-th score of an arbitrary subset that holds at least k collected keys
+        if collected.size > k:
+            sub = rng.choice(collected, size=int(rng.integers(k, collected.size + 1)), replace=False)
+            thr2 = np.sort(exact[r, sub])[-k] - eps - 1e-6
+            coll2 = np.nonzero(approx[r] > thr2)[0]
+            e2 = exact[r, coll2]
+            got2 = coll2[np.lexsort((coll2, -e2))[:k]]
+            ok, bad = O.topk_sets_match(got2[None, :], exact[r][None, :], k)
+            assert ok, bad
