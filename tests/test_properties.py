@@ -346,3 +346,50 @@ def test_two_pass_collect_threshold_model(seed, k, n_groups, clustered):
             got2 = coll2[np.lexsort((coll2, -e2))[:k]]
             ok, bad = O.topk_sets_match(got2[None, :], exact[r][None, :], k)
             assert ok, bad
+
+
+@FAST
+@given(seed=st.integers(0, 2 ** 31 - 1), k=st.integers(1, 8), heavy=st.booleans())
+def test_masked_refine_certificate_model(seed, k, heavy):
+    """Exclusion lists on the tensor-core path: the filter ignores them (per-split lists hold the kp best
+    keys, excluded or not), refine drops excluded candidates, and the UNCHANGED certificate -- k-th exact admissible score >
+    every full list's minimum + eps -- still proves the answer: whatever the lists did not hold scores lower, admissible or
+    not.  ``heavy``: the exclusions ARE the row's best keys, so few rows certify; the ones that do are still exact."""
+    g = torch.Generator().manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    Q, N, d, kp, n_splits = 5, 300, 24, 16, 3
+    keys = torch.randn(N, d, generator=g) * (0.5 + torch.rand(N, 1, generator=g))     # dot-product ranking: norms vary
+    q = torch.randn(Q, d, generator=g)
+    scale = 1.0 / float(keys.norm(dim=1).max())
+    qn = torch.nn.functional.normalize(q, dim=-1)
+    ks = keys * scale                                                                  # row norms <= 1
+    approx = (qn.half().double() @ ks.half().double().T).numpy()
+    exact = (qn.double() @ ks.double().T).numpy()
+    eps = 2 * 2.0 ** -11 + 2.0 ** -15
+    assert np.abs(approx - exact).max() <= eps
+    bounds = np.linspace(0, N, n_splits + 1).astype(int)
+    n_cert = 0
+    for r in range(Q):
+        n_ex = int(rng.integers(0, 40))
+        excl = set(np.argsort(-exact[r])[:n_ex].tolist()) if heavy else set(rng.choice(N, n_ex, replace=False).tolist())
+        cand, tmax = [], -np.inf
+        for s in range(n_splits):
+            lo, hi = bounds[s], bounds[s + 1]
+            order = lo + np.argsort(-approx[r, lo:hi], kind="stable")[:kp]
+            cand.extend(order.tolist())
+            if len(order) == kp:
+                tmax = max(tmax, approx[r, order[-1]])
+        adm = np.array([c for c in cand if c not in excl], dtype=np.int64)
+        if adm.size < k:
+            continue                                                                   # (the product: second pass)
+        e = exact[r, adm]
+        order = np.lexsort((adm, -e))[:k]
+        if not e[order[-1]] > tmax + eps:
+            continue
+        n_cert += 1
+        masked = exact[r].copy()
+        masked[list(excl)] = -np.inf
+        ok, bad = O.topk_sets_match(adm[order][None, :], masked[None, :], k)
+        assert ok, bad
+    if not heavy:
+        assert n_cert > 0
